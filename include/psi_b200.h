@@ -1,0 +1,96 @@
+/* psi_b200.h -- C ABI of libpsi_b200.so: the B200 (sm_100a) implementation of the psitools
+ * D(omega; Kx, Kz) hot path.
+ *
+ * The reference (psitools, pure Python) has no FFI boundary; its boundary is the Python class API
+ * (SURVEY.md section 8b).  The entry points below are what a ctypes binding placed under those
+ * classes calls; each one names the reference interface it replaces (file:line relative to the
+ * psitools tree).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C types only; complex128 arrays are interleaved (re, im) doubles;
+ *   - every function returns PSI_OK (0) or a negative PSI_ERR_* code; psi_last_error() gives the text;
+ *     nothing throws, nothing falls back to the CPU: without a CUDA device psi_ctx_create fails;
+ *   - "*_host" entry points take HOST pointers and perform the H2D/D2H copies themselves
+ *     (synchronous on return); "*_dev" entry points take DEVICE pointers, enqueue on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the context's own stream) and return without
+ *     synchronising;
+ *   - a context is bound to one device and may be used from one host thread at a time.
+ */
+#ifndef PSI_B200_H
+#define PSI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSI_OK 0
+#define PSI_ERR_CUDA (-1)      /* a CUDA runtime call failed (text in psi_last_error) */
+#define PSI_ERR_ARG (-2)       /* invalid argument */
+#define PSI_ERR_NODEVICE (-3)  /* no usable CUDA device: there is NO CPU fallback */
+#define PSI_ERR_CAPACITY (-4)  /* a fixed capacity (distributions, poles, contour points) exceeded */
+
+#define PSI_KIND_POWERLAW 0       /* psi_dispersion.py:57-66 (default MRN-like size density) */
+#define PSI_KIND_POWERBUMP 1      /* power_bump.py:38-130  PowerBump.sigma0 */
+#define PSI_KIND_POWERBUMPTAIL 2  /* power_bump.py:133-212 PowerBumpTail.sigma0 */
+#define PSI_MAX_POLES 4
+
+typedef struct psi_ctx psi_ctx;
+
+/* One PSIDispersion instance (psi_dispersion.py:43-84): dust-to-gas ratio, Stokes range, sound
+ * speed, single-size flag and an analytic size density.  rhod is SizeDensity.rhod
+ * (sizedensity.py:37-40), poles is SizeDensity.poles (sizedensity.py:44), unscaled. */
+typedef struct psi_dist_desc {
+    int kind;
+    int single_size;
+    double mu, tau_min, tau_max, sound_speed;
+    double rhod;
+    double q;                                   /* POWERLAW: sigma(a) = a^q, q = 3 - power */
+    double beta, norm_pl, amp, curv, aL, aP, aBT, scale;   /* POWERBUMP / POWERBUMPTAIL */
+    int n_poles;
+    double poles[PSI_MAX_POLES];
+} psi_dist_desc;
+
+/* Library / device info. */
+const char* psi_version(void);
+const char* psi_last_error(void);
+int psi_device_count(void);
+
+/* Context = one device + one tanh-sinh node table.  Replaces TanhSinh.__init__'s tables
+ * (tanhsinh.py:34-66): the caller uploads the exact xj/wj it built on the host (n_nodes entries,
+ * original order), with max_level and eps = 10^-precision_digit. */
+int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj, int n_nodes,
+                   int max_level, double eps);
+void psi_ctx_destroy(psi_ctx* ctx);
+int psi_ctx_sm_count(psi_ctx* ctx);
+int psi_ctx_synchronize(psi_ctx* ctx);
+/* kernels launched by this context since creation (for bench.py's gpu_launches) */
+long long psi_ctx_launch_count(psi_ctx* ctx);
+
+/* Register a distribution and compute its background state on the device (kernel K0):
+ * replaces PSIDispersion.__init__ (psi_dispersion.py:43-84) + int_j (:183-187).
+ * Returns the distribution id (>= 0) or an error code. */
+int psi_dist_add(psi_ctx* ctx, const psi_dist_desc* desc);
+/* out = {J0, J1, denom, vgx, vgy}  (psi_dispersion.py:74-79) */
+int psi_dist_get_background(psi_ctx* ctx, int dist, double out[5]);
+
+/* Kernel K1 -- replaces PSIDispersion.calculate (psi_dispersion.py:375-456) for a batch of n
+ * points (one warp per point).  dist/kx/kz/alpha have n entries, or ONE entry when broadcast != 0.
+ * w and D are n interleaved complex128; M (optional, may be NULL) receives 7 complex per point
+ * {M11,M12,M13,M21,M22,M23,M33} (psi_dispersion.py:363-373); node_evals (optional) receives the
+ * number of joint integrand evaluations performed for the whole batch. */
+int psi_disp_eval_host(psi_ctx* ctx, long long n, int broadcast, const int* dist, const double* kx,
+                       const double* kz, const double* alpha, const double* w, double* D, double* M,
+                       unsigned long long* node_evals);
+/* Same with device pointers; node_evals_dev (optional) is a device counter that is INCREMENTED. */
+int psi_disp_eval_dev(psi_ctx* ctx, long long n, int broadcast, const int* dist, const double* kx,
+                      const double* kz, const double* alpha, const double* w, double* D, double* M,
+                      unsigned long long* node_evals_dev, void* stream);
+
+/* FP64 FMA-pipe peak of the device (roofline denominator; MEASURED_PEAKS.json has no FP64 entry):
+ * runs a register-resident DFMA chain kernel `reps` times and returns the best TFLOP/s. */
+int psi_measure_fp64_peak(psi_ctx* ctx, int reps, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSI_B200_H */

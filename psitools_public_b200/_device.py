@@ -1,0 +1,275 @@
+"""ctypes binding of libpsi_b200.so (C ABI in include/psi_b200.h) and the host-side translation of
+the reference's Python objects (TanhSinh, SizeDensity, PowerBump*) into device descriptors.
+
+There is deliberately NO CPU fallback: if the library is missing or no CUDA device is visible every
+entry point raises.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpsi_b200.so")
+
+PSI_MAX_POLES = 4
+KIND_POWERLAW, KIND_POWERBUMP, KIND_POWERBUMPTAIL = 0, 1, 2
+
+
+class PsiError(RuntimeError):
+    """An error code returned by libpsi_b200."""
+
+
+class DistDesc(C.Structure):
+    """Mirror of ``psi_dist_desc`` (include/psi_b200.h)."""
+    _fields_ = [("kind", C.c_int), ("single_size", C.c_int),
+                ("mu", C.c_double), ("tau_min", C.c_double), ("tau_max", C.c_double),
+                ("sound_speed", C.c_double), ("rhod", C.c_double), ("q", C.c_double),
+                ("beta", C.c_double), ("norm_pl", C.c_double), ("amp", C.c_double),
+                ("curv", C.c_double), ("aL", C.c_double), ("aP", C.c_double), ("aBT", C.c_double),
+                ("scale", C.c_double), ("n_poles", C.c_int), ("poles", C.c_double*PSI_MAX_POLES)]
+
+    def key(self):
+        return bytes(self)
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_vp = C.c_void_p
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "psi_version": (C.c_char_p, []),
+    "psi_last_error": (C.c_char_p, []),
+    "psi_device_count": (C.c_int, []),
+    "psi_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_double]),
+    "psi_ctx_destroy": (None, [_vp]),
+    "psi_ctx_sm_count": (C.c_int, [_vp]),
+    "psi_ctx_synchronize": (C.c_int, [_vp]),
+    "psi_ctx_launch_count": (C.c_longlong, [_vp]),
+    "psi_dist_add": (C.c_int, [_vp, C.POINTER(DistDesc)]),
+    "psi_dist_get_background": (C.c_int, [_vp, C.c_int, _dp]),
+    "psi_disp_eval_host": (C.c_int, [_vp, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     C.POINTER(C.c_ulonglong)]),
+    "psi_disp_eval_dev": (C.c_int, [_vp, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _vp, _vp]),
+    "psi_measure_fp64_peak": (C.c_int, [_vp, C.c_int, _dp]),
+}
+
+
+def exported_symbols():
+    """Names every build of the library must export (checked by the CPU test-suite)."""
+    return sorted(_SIGNATURES)
+
+
+def load_library():
+    """dlopen libpsi_b200.so and declare the prototypes.  Raises if the library is not built."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise PsiError("libpsi_b200.so not built (run `python -c 'import __graft_entry__ as g; "
+                               "g.build()'`); there is no CPU fallback")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc, what=""):
+    if rc < 0:
+        msg = load_library().psi_last_error().decode()
+        raise PsiError("%s failed (code %d): %s" % (what or "libpsi_b200 call", rc, msg))
+    return rc
+
+
+def default_device():
+    if "PSI_B200_DEVICE" in os.environ:
+        return int(os.environ["PSI_B200_DEVICE"])
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+class Context:
+    """One device + one node table (``psi_ctx``).  Distributions are registered once and cached by
+    the bytes of their descriptor."""
+
+    def __init__(self, integrator, device=None):
+        lib = load_library()
+        self.lib = lib
+        self.device = default_device() if device is None else device
+        xj = np.ascontiguousarray(integrator.xj, dtype=np.float64)
+        wj = np.ascontiguousarray(integrator.wj, dtype=np.float64)
+        h = _vp()
+        check(lib.psi_ctx_create(C.byref(h), self.device, _ptr(xj), _ptr(wj), len(xj),
+                                 int(integrator.max_m), float(integrator.eps)), "psi_ctx_create")
+        self.handle = h
+        self._dists = {}
+        self.node_evals = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.psi_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def sm_count(self):
+        return self.lib.psi_ctx_sm_count(self.handle)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.psi_ctx_launch_count(self.handle))
+
+    def synchronize(self):
+        check(self.lib.psi_ctx_synchronize(self.handle), "psi_ctx_synchronize")
+
+    def add_dist(self, desc):
+        k = desc.key()
+        if k not in self._dists:
+            self._dists[k] = check(self.lib.psi_dist_add(self.handle, C.byref(desc)), "psi_dist_add")
+        return self._dists[k]
+
+    def background(self, dist_id):
+        out = (C.c_double*5)()
+        check(self.lib.psi_dist_get_background(self.handle, dist_id, out), "psi_dist_get_background")
+        return dict(j0=out[0], j1=out[1], denom=out[2], vgx=out[3], vgy=out[4])
+
+    def disp_eval(self, dist, kx, kz, alpha, w, want_M=False):
+        """Batch D(omega).  dist/kx/kz/alpha are scalars (broadcast) or arrays shaped like w."""
+        w = np.ascontiguousarray(np.ravel(w), dtype=np.complex128)
+        n = len(w)
+        bc = int(np.ndim(kx) == 0 and np.ndim(kz) == 0 and np.ndim(alpha) == 0 and np.ndim(dist) == 0)
+        m = 1 if bc else n
+        da = np.ascontiguousarray(np.broadcast_to(np.asarray(dist, dtype=np.int32), (m,)))
+        kxa = np.ascontiguousarray(np.broadcast_to(np.asarray(kx, dtype=np.float64), (m,)))
+        kza = np.ascontiguousarray(np.broadcast_to(np.asarray(kz, dtype=np.float64), (m,)))
+        ala = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha, dtype=np.float64), (m,)))
+        D = np.empty(n, dtype=np.complex128)
+        M = np.empty((n, 7), dtype=np.complex128) if want_M else None
+        ne = C.c_ulonglong(0)
+        check(self.lib.psi_disp_eval_host(self.handle, n, bc, _ptr(da), _ptr(kxa), _ptr(kza),
+                                          _ptr(ala), _ptr(w), _ptr(D),
+                                          _ptr(M) if want_M else None, C.byref(ne)),
+              "psi_disp_eval_host")
+        self.node_evals += ne.value
+        return (D, M) if want_M else D
+
+    def measure_fp64_peak(self, reps=5):
+        out = C.c_double(0)
+        check(self.lib.psi_measure_fp64_peak(self.handle, reps, C.byref(out)), "psi_measure_fp64_peak")
+        return out.value
+
+
+_contexts = {}
+
+
+def get_context(integrator, device=None):
+    """Context cache keyed by (device, node-table identity)."""
+    dev = default_device() if device is None else device
+    key = (dev, int(integrator.p), int(integrator.max_m), len(integrator.xj),
+           hash(np.asarray(integrator.xj).tobytes()))
+    if key not in _contexts:
+        _contexts[key] = Context(integrator, dev)
+    return _contexts[key]
+
+
+# ------------------------------------------------------------------------------------------------
+# Python objects -> device descriptors
+# ------------------------------------------------------------------------------------------------
+def _closure_vars(fn):
+    code = getattr(fn, "__code__", None)
+    cells = getattr(fn, "__closure__", None)
+    if code is None or not cells:
+        return {}
+    out = {}
+    for name, cell in zip(code.co_freevars, cells):
+        try:
+            out[name] = cell.cell_contents
+        except ValueError:
+            pass
+    return out
+
+
+def _find_sigma(size_density):
+    """The sigma callable behind a SizeDensity: ours keeps ``.sigma``; the reference's keeps it
+    only inside the closure of ``.f`` (reference sizedensity.py:41)."""
+    s = getattr(size_density, "sigma", None)
+    if s is not None:
+        return s
+    return _closure_vars(getattr(size_density, "f", None)).get("sigma")
+
+
+def _bump_constants(pb):
+    """(beta, norm_pl, amp, curv) of a PowerBump-like object: attributes on ours, closure cells of
+    the ``fnn``/``b`` lambdas on the reference's (power_bump.py:75-80)."""
+    if all(hasattr(pb, k) for k in ("beta", "norm_pl", "amp", "curv")):
+        return float(pb.beta), float(pb.norm_pl), float(pb.amp), float(pb.curv)
+    bv = _closure_vars(pb.b)
+    amp, curv = float(bv["fac_b"]), float(bv["fac_b2"])
+    if hasattr(pb, "beta"):                       # reference PowerBumpTail
+        beta = float(pb.beta)
+        norm_pl = float(pb.aP**-(beta))
+    else:
+        fv = _closure_vars(pb.fnn)
+        beta, norm_pl = float(fv["beta"]), float(fv["fac_fnn"])
+    return beta, norm_pl, amp, curv
+
+
+def describe_size_density(mu, stokes_range, sound_speed, power, single_size, size_density):
+    """Build the ``psi_dist_desc`` for PSIDispersion's constructor arguments
+    (reference psi_dispersion.py:43-66)."""
+    d = DistDesc()
+    d.single_size = int(bool(single_size))
+    d.mu = float(mu)
+    d.tau_min = float(stokes_range[0])
+    d.tau_max = float(stokes_range[1])
+    d.sound_speed = float(sound_speed)
+    d.scale = 1.0
+    poles = []
+    if size_density is None:
+        d.kind = KIND_POWERLAW
+        d.q = 3 - power
+        d.rhod = (stokes_range[0]**(4.0 - power) - stokes_range[1]**(4.0 - power))/(power - 4.0)
+    else:
+        sigma = _find_sigma(size_density)
+        pb = getattr(sigma, "__self__", None)
+        is_sigma0 = getattr(sigma, "__name__", "") == "sigma0"
+        if pb is None or not is_sigma0 or not all(hasattr(pb, k) for k in ("aP", "aL", "aR", "amin")):
+            raise NotImplementedError(
+                "size_density must be None (power law) or a SizeDensity wrapping PowerBump.sigma0 / "
+                "PowerBumpTail.sigma0: the device evaluates sigma(a) analytically and cannot call "
+                "an arbitrary Python function")
+        beta, norm_pl, amp, curv = _bump_constants(pb)
+        d.kind = KIND_POWERBUMPTAIL if hasattr(pb, "aBT") else KIND_POWERBUMP
+        d.beta, d.norm_pl, d.amp, d.curv = beta, norm_pl, amp, curv
+        d.aL, d.aP = float(pb.aL), float(pb.aP)
+        d.aBT = float(getattr(pb, "aBT", -1.0))
+        if getattr(pb, "epstot", None) is not None:
+            d.scale = float(pb.epstot)/float(pb.mnorm)
+        d.rhod = float(size_density.rhod)
+        if float(size_density.amax) != d.tau_max:
+            # F(s) = amax*sigma(amax*s)/rhod uses the SizeDensity's own amax (sizedensity.py:41)
+            raise NotImplementedError("SizeDensity.amax must equal stokes_range[1]")
+        poles = [float(p) for p in size_density.poles]
+    if len(poles) > PSI_MAX_POLES:
+        raise ValueError("at most %d size-density poles are supported" % PSI_MAX_POLES)
+    d.n_poles = len(poles)
+    for i, p in enumerate(poles):
+        d.poles[i] = p
+    return d

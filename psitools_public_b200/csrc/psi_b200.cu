@@ -1,0 +1,361 @@
+// psi_b200.cu -- CUDA kernels (sm_100a) and the C ABI of libpsi_b200.so.
+//
+// K0 background_kernel : J0/J1 of a dust distribution              (psi_dispersion.py:74-84, 183-187)
+// K1 disp_eval_kernel  : D(omega; Kx, Kz, alpha), one warp per point  (psi_dispersion.py:375-456 +
+//                        tanhsinh.py:72-128)
+// Persistent CTAs (one per SM) stage the level-major node table in shared memory once and their
+// warps pull points from a device-side atomic queue, so unevenly expensive points (1-4 quadrature
+// sub-intervals, different early-exit levels) balance themselves.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/psi_b200.h"
+#include "psi_table.hpp"
+
+using namespace psi;
+
+// ------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(PSI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// warp policy on the device
+// ------------------------------------------------------------------------------------------------
+struct WarpCuda {
+    static constexpr int width = 32;
+    static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ double sum(double v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxDists = 4096;
+constexpr int kEvalThreads = 384;          // 12 warps per persistent CTA
+
+struct psi_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    // node table
+    node_t* d_nodes = nullptr;
+    int* d_level_off = nullptr;
+    int n_nodes = 0, max_m = 0;
+    double eps = 0;
+    size_t table_smem = 0;                 // bytes needed to stage the table in shared memory
+    bool table_in_smem = false;
+    // distributions
+    DistParams* d_dists = nullptr;
+    std::vector<DistParams> h_dists;
+    // work queue + statistics
+    unsigned long long* d_counter = nullptr;     // [0] queue head, [1] node evals (host entry points)
+    // staging for the *_host entry points
+    void* d_stage = nullptr;
+    size_t stage_bytes = 0;
+    long long launches = 0;
+};
+
+static NodeTableView table_view(const psi_ctx* c) {
+    NodeTableView t;
+    t.nodes = c->d_nodes; t.level_off = c->d_level_off; t.n_nodes = c->n_nodes; t.max_m = c->max_m;
+    t.eps = c->eps;
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void background_kernel(NodeTableView t, DistParams* dists, int id) {
+    DistParams d = dists[id];
+    unsigned long long nodes = 0;
+    background_warp<WarpCuda>(t, d, nodes);
+    if (threadIdx.x == 0) {
+        dists[id].j0 = d.j0; dists[id].j1 = d.j1; dists[id].denom = d.denom;
+        dists[id].vgx = d.vgx; dists[id].vgy = d.vgy;
+    }
+}
+
+template <bool SMEM_TABLE>
+__global__ void __launch_bounds__(kEvalThreads, 1)
+disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long long n, int broadcast,
+                 const int* __restrict__ dist, const double* __restrict__ kx,
+                 const double* __restrict__ kz, const double* __restrict__ alpha,
+                 const double2* __restrict__ w, double2* __restrict__ D, double2* __restrict__ M,
+                 unsigned long long* __restrict__ queue, unsigned long long* __restrict__ node_evals) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NodeTableView t = gt;
+    if (SMEM_TABLE) {
+        node_t* s_nodes = reinterpret_cast<node_t*>(smem_raw);
+        int* s_off = reinterpret_cast<int*>(smem_raw + sizeof(node_t) * (size_t)gt.n_nodes);
+        const double2* src = reinterpret_cast<const double2*>(gt.nodes);
+        double2* dst = reinterpret_cast<double2*>(s_nodes);
+        for (int i = threadIdx.x; i < gt.n_nodes; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < gt.max_m + 2; i += blockDim.x) s_off[i] = gt.level_off[i];
+        __syncthreads();
+        t.nodes = s_nodes;
+        t.level_off = s_off;
+    }
+    const int lane = threadIdx.x & 31;
+    unsigned long long nodes = 0;
+    while (true) {
+        unsigned long long idx = 0;
+        if (lane == 0) idx = atomicAdd(queue, 1ull);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= (unsigned long long)n) break;
+        const long long pi = broadcast ? 0 : (long long)idx;
+        const DistParams& d = dists[dist[pi]];
+        const double2 wv = w[idx];
+        cx m[7];
+        const cx val = disp_eval_warp<WarpCuda>(t, d, cx(wv.x, wv.y), kx[pi], kz[pi], alpha[pi], m, nodes);
+        if (lane == 0) D[idx] = make_double2(val.re, val.im);
+        if (M != nullptr && lane < 7) {
+            cx mv = m[0];
+#pragma unroll
+            for (int k = 1; k < 7; ++k) if (lane == k) mv = m[k];
+            M[idx * 7 + lane] = make_double2(mv.re, mv.im);
+        }
+    }
+    if (node_evals != nullptr && lane == 0 && nodes) atomicAdd(node_evals, nodes);
+}
+
+// DFMA-pipe peak: 8 independent FMA chains per thread, all in registers.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5,
+           a6 = seed + 6, a7 = seed + 7;
+    const double m = 1.0 + 1e-9 * threadIdx.x, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* psi_version(void) { return "psi_b200 0.1 (sm_100a)"; }
+const char* psi_last_error(void) { return g_err.c_str(); }
+
+int psi_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj, int n_nodes,
+                   int max_level, double eps) {
+    if (!out || !xj || !wj || n_nodes <= 0 || max_level < 1 || max_level > 20 || !(eps > 0))
+        return fail(PSI_ERR_ARG, "psi_ctx_create: bad argument");
+    int ndev = psi_device_count();
+    if (ndev <= 0)
+        return fail(PSI_ERR_NODEVICE, "no CUDA device visible; libpsi_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(PSI_ERR_ARG, "psi_ctx_create: bad device index");
+    CK(cudaSetDevice(device));
+    psi_ctx* c = new psi_ctx();
+    c->device = device;
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->n_nodes = n_nodes; c->max_m = max_level; c->eps = eps;
+    // level-major reordering of the caller's table
+    std::vector<node_t> lv;
+    std::vector<int> off;
+    if (!build_level_major(xj, wj, n_nodes, max_level, lv, off)) {
+        delete c;
+        return fail(PSI_ERR_ARG, "node table reorder failed");
+    }
+    CK(cudaMalloc(&c->d_nodes, sizeof(node_t) * n_nodes));
+    CK(cudaMalloc(&c->d_level_off, sizeof(int) * off.size()));
+    CK(cudaMemcpy(c->d_nodes, lv.data(), sizeof(node_t) * n_nodes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_level_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+    c->table_smem = sizeof(node_t) * (size_t)n_nodes + sizeof(int) * off.size();
+    c->table_in_smem = c->table_smem + 1024 <= (size_t)c->smem_optin;
+    if (c->table_in_smem)
+        CK(cudaFuncSetAttribute(disp_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)c->table_smem));
+    CK(cudaMalloc(&c->d_dists, sizeof(DistParams) * kMaxDists));
+    CK(cudaMalloc(&c->d_counter, sizeof(unsigned long long) * 8));
+    CK(cudaMemset(c->d_counter, 0, sizeof(unsigned long long) * 8));
+    *out = c;
+    return PSI_OK;
+}
+
+void psi_ctx_destroy(psi_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_nodes); cudaFree(c->d_level_off); cudaFree(c->d_dists); cudaFree(c->d_counter);
+    cudaFree(c->d_stage);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int psi_ctx_sm_count(psi_ctx* c) { return c ? c->sm_count : 0; }
+long long psi_ctx_launch_count(psi_ctx* c) { return c ? c->launches : 0; }
+
+int psi_ctx_synchronize(psi_ctx* c) {
+    if (!c) return fail(PSI_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return PSI_OK;
+}
+
+int psi_dist_add(psi_ctx* c, const psi_dist_desc* s) {
+    if (!c || !s) return fail(PSI_ERR_ARG, "psi_dist_add: null argument");
+    if (s->kind < 0 || s->kind > 2) return fail(PSI_ERR_ARG, "psi_dist_add: unknown kind");
+    if (s->n_poles < 0 || s->n_poles > PSI_MAX_POLES)
+        return fail(PSI_ERR_CAPACITY, "psi_dist_add: too many size-density poles");
+    if ((int)c->h_dists.size() >= kMaxDists) return fail(PSI_ERR_CAPACITY, "too many distributions");
+    if (!(s->tau_min > 0) || !(s->tau_max > 0) || !(s->rhod != 0))
+        return fail(PSI_ERR_ARG, "psi_dist_add: bad Stokes range or rhod");
+    CK(cudaSetDevice(c->device));
+    DistParams d = dist_from_desc(*s);
+    const int id = (int)c->h_dists.size();
+    CK(cudaMemcpyAsync(c->d_dists + id, &d, sizeof(d), cudaMemcpyHostToDevice, c->stream));
+    background_kernel<<<1, 32, 0, c->stream>>>(table_view(c), c->d_dists, id);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&d, c->d_dists + id, sizeof(d), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->h_dists.push_back(d);
+    return id;
+}
+
+int psi_dist_get_background(psi_ctx* c, int dist, double out[5]) {
+    if (!c || !out || dist < 0 || dist >= (int)c->h_dists.size())
+        return fail(PSI_ERR_ARG, "psi_dist_get_background: bad argument");
+    const DistParams& d = c->h_dists[dist];
+    out[0] = d.j0; out[1] = d.j1; out[2] = d.denom; out[3] = d.vgx; out[4] = d.vgy;
+    return PSI_OK;
+}
+
+static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* dist, const double* kx,
+                            const double* kz, const double* alpha, const double* w, double* D,
+                            double* M, unsigned long long* node_evals_dev, cudaStream_t st) {
+    if (n == 0) return PSI_OK;
+    const int warps = kEvalThreads / 32;
+    long long want = (n + warps - 1) / warps;
+    int grid = (int)(want < c->sm_count ? want : c->sm_count);
+    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+    NodeTableView t = table_view(c);
+    if (c->table_in_smem)
+        disp_eval_kernel<true><<<grid, kEvalThreads, c->table_smem, st>>>(
+            t, c->d_dists, n, broadcast, dist, kx, kz, alpha, (const double2*)w, (double2*)D,
+            (double2*)M, c->d_counter, node_evals_dev);
+    else
+        disp_eval_kernel<false><<<grid, kEvalThreads, 0, st>>>(
+            t, c->d_dists, n, broadcast, dist, kx, kz, alpha, (const double2*)w, (double2*)D,
+            (double2*)M, c->d_counter, node_evals_dev);
+    c->launches++;
+    CK(cudaGetLastError());
+    return PSI_OK;
+}
+
+int psi_disp_eval_dev(psi_ctx* c, long long n, int broadcast, const int* dist, const double* kx,
+                      const double* kz, const double* alpha, const double* w, double* D, double* M,
+                      unsigned long long* node_evals_dev, void* stream) {
+    if (!c || n < 0 || !dist || !kx || !kz || !alpha || (n > 0 && (!w || !D)))
+        return fail(PSI_ERR_ARG, "psi_disp_eval_dev: bad argument");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return launch_disp_eval(c, n, broadcast, dist, kx, kz, alpha, w, D, M, node_evals_dev, st);
+}
+
+static int ensure_stage(psi_ctx* c, size_t bytes) {
+    if (bytes <= c->stage_bytes) return PSI_OK;
+    if (c->d_stage) CK(cudaFree(c->d_stage));
+    c->d_stage = nullptr; c->stage_bytes = 0;
+    CK(cudaMalloc(&c->d_stage, bytes));
+    c->stage_bytes = bytes;
+    return PSI_OK;
+}
+
+int psi_disp_eval_host(psi_ctx* c, long long n, int broadcast, const int* dist, const double* kx,
+                       const double* kz, const double* alpha, const double* w, double* D, double* M,
+                       unsigned long long* node_evals) {
+    if (!c || n < 0 || !dist || !kx || !kz || !alpha || (n > 0 && (!w || !D)))
+        return fail(PSI_ERR_ARG, "psi_disp_eval_host: bad argument");
+    if (node_evals) *node_evals = 0;
+    if (n == 0) return PSI_OK;
+    CK(cudaSetDevice(c->device));
+    const long long np = broadcast ? 1 : n;
+    for (long long i = 0; i < np; ++i)
+        if (dist[i] < 0 || dist[i] >= (int)c->h_dists.size())
+            return fail(PSI_ERR_ARG, "psi_disp_eval_host: distribution id out of range");
+    // staging layout: w | D | M | kx | kz | alpha | dist   (all 16-byte aligned)
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_w = 0, o_D = al(o_w + 16 * n), o_M = al(o_D + 16 * n),
+                 o_kx = al(o_M + (M ? 112 * n : 0)), o_kz = al(o_kx + 8 * np),
+                 o_al = al(o_kz + 8 * np), o_ds = al(o_al + 8 * np), total = al(o_ds + 4 * np);
+    int rc = ensure_stage(c, total);
+    if (rc != PSI_OK) return rc;
+    char* base = (char*)c->d_stage;
+    cudaStream_t st = c->stream;
+    CK(cudaMemcpyAsync(base + o_w, w, 16 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_kx, kx, 8 * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_kz, kz, 8 * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_al, alpha, 8 * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_ds, dist, 4 * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->d_counter + 1, 0, sizeof(unsigned long long), st));
+    rc = launch_disp_eval(c, n, broadcast, (const int*)(base + o_ds), (const double*)(base + o_kx),
+                          (const double*)(base + o_kz), (const double*)(base + o_al),
+                          (const double*)(base + o_w), (double*)(base + o_D),
+                          M ? (double*)(base + o_M) : nullptr, c->d_counter + 1, st);
+    if (rc != PSI_OK) return rc;
+    CK(cudaMemcpyAsync(D, base + o_D, 16 * n, cudaMemcpyDeviceToHost, st));
+    if (M) CK(cudaMemcpyAsync(M, base + o_M, 112 * n, cudaMemcpyDeviceToHost, st));
+    unsigned long long ne = 0;
+    CK(cudaMemcpyAsync(&ne, c->d_counter + 1, sizeof(ne), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (node_evals) *node_evals = ne;
+    return PSI_OK;
+}
+
+int psi_measure_fp64_peak(psi_ctx* c, int reps, double* tflops) {
+    if (!c || !tflops || reps < 1) return fail(PSI_ERR_ARG, "psi_measure_fp64_peak: bad argument");
+    CK(cudaSetDevice(c->device));
+    const int threads = 256, blocks = c->sm_count * 8, iters = 4096;
+    double* buf = nullptr;
+    CK(cudaMalloc(&buf, sizeof(double) * threads * blocks));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int r = 0; r < reps + 2; ++r) {
+        CK(cudaEventRecord(e0, c->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, c->stream>>>(buf, iters, 1.0 + r);
+        c->launches++;
+        CK(cudaEventRecord(e1, c->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8 * 16 * (double)iters * threads * blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (r >= 2 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    *tflops = best;
+    return PSI_OK;
+}
+
+}  // extern "C"
