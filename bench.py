@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- D(omega) evaluations per second on BASELINE config 2.
+
+Workload ("config2"): the dispersion relation on a 1024x1024 complex-omega grid
+(Re in [-7.5, 7.5], Im in [-12.5, 2.5], ranges of psitools_examples/example_PSIModeMPIDispersion.py)
+at fixed (Kx, Kz) = (50, 100), MRN power law mu = 3, tau in [1e-8, 0.1], TanhSinh(15, 12).
+One step = one pass of kernel K1 over the whole grid (1,048,576 evaluations per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 is launched with torch.distributed.run (one rank per GPU); the grid is an independent shard
+per rank (rank r maps the same omega grid at its own (Kx, Kz)), no data-path collective, weak
+scaling.  Rank 0 prints ONE JSON line.  `--impl reference` times the CPU path (the oracle port of
+the reference's algorithm -- the Python reference itself cannot travel to the GPU box) on all host
+cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_NODE = 300.0          # nominal FP64 flops per joint node evaluation
+GRID = 1024
+K_BASE = (50.0, 100.0)
+MU, STOKES = 3.0, (1e-8, 0.1)
+
+
+def omega_grid(n=GRID):
+    re = np.linspace(-7.5, 7.5, n)
+    im = np.linspace(-12.5, 2.5, n)
+    return (re[None, :] + 1j*im[:, None]).ravel()
+
+
+def rank_wavenumbers(rank):
+    """Independent shard per rank: same omega grid, a different (Kx, Kz) pixel of a log K grid."""
+    return K_BASE[0]*(1.25**rank), K_BASE[1]*(1.25**rank)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: oracle port on the host cores
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import psi_oracle as po
+    w, kx, kz = args
+    disp = _cpu_worker.cache.get("d")
+    if disp is None:
+        disp = po.Dispersion(po.DustDist.power_law(MU, list(STOKES)), po.NodeTable())
+        _cpu_worker.cache["d"] = disp
+    return disp.calculate(w, kx, kz)
+
+
+_cpu_worker.cache = {}
+
+
+def cpu_sample_rate(n_points, cores, seed=0, pool=None):
+    """evals/s of the oracle port on `cores` processes over a seeded random subset of the grid."""
+    import multiprocessing as mp
+    w = omega_grid()
+    idx = np.random.RandomState(seed).choice(w.size, size=n_points, replace=False)
+    chunks = [c for c in np.array_split(w[idx], cores*4) if len(c)]
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores)
+        pool.map(_cpu_worker, [(w[:1], K_BASE[0], K_BASE[1])]*cores)      # warm the workers
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, [(c, K_BASE[0], K_BASE[1]) for c in chunks], chunksize=1)
+    dt = time.perf_counter() - t0
+    if own:
+        pool.close()
+        pool.join()
+    assert np.all(np.isfinite(np.concatenate(res)))
+    return n_points/dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = 96*cores
+    pool = mp.get_context("fork").Pool(cores)
+    pool.map(_cpu_worker, [(omega_grid()[:1], K_BASE[0], K_BASE[1])]*cores)
+    for i in range(args.warmup):
+        cpu_sample_rate(max(cores, per_step//8), cores, seed=100 + i, pool=pool)
+    t_total, n_total = 0.0, 0
+    for i in range(args.steps):
+        _, dt = cpu_sample_rate(per_step, cores, seed=i, pool=pool)
+        t_total += dt
+        n_total += per_step
+    pool.close()
+    pool.join()
+    value = n_total/t_total
+    sample = "%d random points of the 1024^2 omega grid per step, %d steps" % (per_step, args.steps)
+    line = {"impl": "reference", "metric": "D(omega) evals/s", "value": value, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3*t_total/args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "config2: D(omega) on a 1024x1024 complex-omega grid at fixed (Kx,Kz)=(50,100), "
+                        "MRN mu=3 tau in [1e-8,0.1], TanhSinh(15,12)",
+            "points_per_gpu": GRID*GRID, "sharding": "independent omega grid per rank (own Kx,Kz)",
+            "parallelism": "dp%d" % n_gpus,
+            "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    import __graft_entry__ as ge
+    if local == 0:
+        ge.build()                      # no-op when the in-tree libpsi_b200.so is up to date
+    if world > 1:
+        dist.barrier()
+    from psitools_public_b200 import PSIDispersion, TanhSinh
+
+    pd = PSIDispersion(MU, list(STOKES), tanhsinh_integrator=TanhSinh(), device=local)
+    ctx = pd.ctx
+    kx, kz = rank_wavenumbers(rank)
+    w_host = torch.from_numpy(omega_grid().view(np.float64).copy()).pin_memory()      # (2n,) pinned
+    n = GRID*GRID
+    # a dedicated (non-default) stream: the C ABI treats a NULL stream as "the context's own"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    # resident inputs/outputs in HBM
+    w_dev = w_host.to(dev, non_blocking=True)
+    D_dev = torch.empty(2*n, dtype=torch.float64, device=dev)
+    par = torch.tensor([kx, kz, 0.0], dtype=torch.float64, device=dev)
+    dist_dev = torch.tensor([pd.dist_id], dtype=torch.int32, device=dev)
+    nodes_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256*1024*1024, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        flush.fill_(1)
+        ctx.disp_eval_dev(n, 1, dist_dev.data_ptr(), par.data_ptr(), par.data_ptr() + 8,
+                          par.data_ptr() + 16, w_dev.data_ptr(), D_dev.data_ptr(), 0,
+                          nodes_dev.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = ctx.measure_fp64_peak(5) if rank == 0 else None
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    nodes_dev.zero_()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        flush.fill_(1)
+        kev[i][0].record(stream)
+        ctx.disp_eval_dev(n, 1, dist_dev.data_ptr(), par.data_ptr(), par.data_ptr() + 8,
+                          par.data_ptr() + 16, w_dev.data_ptr(), D_dev.data_ptr(), 0,
+                          nodes_dev.data_ptr(), stream.cuda_stream)
+        kev[i][1].record(stream)
+    ev[1].record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count - launches0
+    ms_total = ev[0].elapsed_time(ev[1])
+    ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    node_evals = int(nodes_dev.item())
+    D_resident = D_dev.cpu().numpy().view(np.complex128)
+
+    # end to end through the public API: host buffers, H2D + D2H inside the timed region
+    w_np = w_host.numpy().view(np.complex128)
+    out_pinned = torch.empty(2*n, dtype=torch.float64).pin_memory()
+    out_np = out_pinned.numpy().view(np.complex128)
+    for _ in range(min(args.warmup, 2)):
+        pd.ctx.disp_eval(pd.dist_id, kx, kz, 0.0, w_np, out=out_np)
+    barrier()
+    t0 = time.perf_counter()
+    e_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    e_ev[0].record(stream)
+    for _ in range(args.steps):
+        got = pd.ctx.disp_eval(pd.dist_id, kx, kz, 0.0, w_np, out=out_np)    # synchronous on return
+    e_ev[1].record(stream)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert np.array_equal(got, D_resident), "resident and end-to-end results differ"
+    assert np.all(np.isfinite(got))
+
+    t = torch.tensor([ms_total, ms_kernel, e2e_s], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(node_evals), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_total, ms_kernel, e2e_s = [float(x) for x in t.tolist()]
+    node_evals_all, launches_all = [float(x) for x in cnt.tolist()]
+
+    if rank == 0:
+        total_evals = float(n)*world*args.steps
+        value = total_evals/(ms_total*1e-3)
+        tf = FLOPS_PER_NODE*(node_evals/args.steps)/(ms_kernel*1e-3)/1e12     # rank 0's kernel
+        roof = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": tf/fp64_peak if fp64_peak else None, "traffic": None,
+                "kernel": "disp_eval_kernel", "kernel_ms": ms_kernel,
+                "node_evals_per_launch": node_evals/args.steps, "flops_per_node_eval": FLOPS_PER_NODE,
+                "peak_source": "measured live by dfma_peak_kernel (MEASURED_PEAKS.json has no FP64 entry)",
+                "hbm_gbs_algorithmic": 32.0*n/(ms_kernel*1e-3)/1e9}
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            n_cpu = min(n, 600*cores)
+            rate, dt = cpu_sample_rate(n_cpu, cores)
+            cpu = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                   "sample": "%d random points of the 1024^2 omega grid (%.1f s)" % (n_cpu, dt)}
+        line = {"metric": "D(omega) evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total/args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": total_evals/e2e_s, "unit": "evals/s",
+                        "h2d_bytes_per_step": 16*n + 28, "d2h_bytes_per_step": 16*n + 8},
+                "gpu_launches": int(launches_all), "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -150,8 +150,9 @@ class Context:
         check(self.lib.psi_dist_get_background(self.handle, dist_id, out), "psi_dist_get_background")
         return dict(j0=out[0], j1=out[1], denom=out[2], vgx=out[3], vgy=out[4])
 
-    def disp_eval(self, dist, kx, kz, alpha, w, want_M=False):
-        """Batch D(omega).  dist/kx/kz/alpha are scalars (broadcast) or arrays shaped like w."""
+    def disp_eval(self, dist, kx, kz, alpha, w, want_M=False, out=None):
+        """Batch D(omega).  dist/kx/kz/alpha are scalars (broadcast) or arrays shaped like w.
+        ``out`` may be a preallocated (e.g. pinned) complex128 array of the same length."""
         w = np.ascontiguousarray(np.ravel(w), dtype=np.complex128)
         n = len(w)
         bc = int(np.ndim(kx) == 0 and np.ndim(kz) == 0 and np.ndim(alpha) == 0 and np.ndim(dist) == 0)
@@ -160,7 +161,9 @@ class Context:
         kxa = np.ascontiguousarray(np.broadcast_to(np.asarray(kx, dtype=np.float64), (m,)))
         kza = np.ascontiguousarray(np.broadcast_to(np.asarray(kz, dtype=np.float64), (m,)))
         ala = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha, dtype=np.float64), (m,)))
-        D = np.empty(n, dtype=np.complex128)
+        D = np.empty(n, dtype=np.complex128) if out is None else out
+        if D.dtype != np.complex128 or D.size != n or not D.flags.c_contiguous:
+            raise ValueError("out must be a contiguous complex128 array with one entry per point")
         M = np.empty((n, 7), dtype=np.complex128) if want_M else None
         ne = C.c_ulonglong(0)
         check(self.lib.psi_disp_eval_host(self.handle, n, bc, _ptr(da), _ptr(kxa), _ptr(kza),
@@ -169,6 +172,15 @@ class Context:
               "psi_disp_eval_host")
         self.node_evals += ne.value
         return (D, M) if want_M else D
+
+    def disp_eval_dev(self, n, broadcast, dist_ptr, kx_ptr, kz_ptr, alpha_ptr, w_ptr, D_ptr, M_ptr=0,
+                      node_evals_ptr=0, stream=0):
+        """K1 on DEVICE pointers (ints), asynchronous on ``stream`` (a cudaStream_t as int; 0 = the
+        context's own stream).  Used when inputs are already resident in HBM."""
+        check(self.lib.psi_disp_eval_dev(self.handle, int(n), int(broadcast), dist_ptr, kx_ptr, kz_ptr,
+                                         alpha_ptr, w_ptr, D_ptr, M_ptr or None,
+                                         node_evals_ptr or None, stream or None),
+              "psi_disp_eval_dev")
 
     def measure_fp64_peak(self, reps=5):
         out = C.c_double(0)

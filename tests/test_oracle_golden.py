@@ -1,0 +1,106 @@
+"""Pin the oracle (oracle/psi_oracle.py) to fixtures produced by the unmodified reference
+(tests/golden/make_golden.py) and to the golden numbers in the reference's own tests."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from common import carr, cplx, load, oracle_dist
+from oracle import psi_oracle as po
+
+
+@pytest.fixture(scope="module")
+def tab():
+    return po.NodeTable()
+
+
+def test_node_tables_match_reference():
+    g = load("nodes.json")
+    for key in ("15_12", "15_10", "12_8"):
+        p, m = map(int, key.split("_"))
+        t = po.NodeTable(p, m)
+        assert len(t.xj) == g[key]["n"]
+        assert hashlib.sha256(t.xj.tobytes()).hexdigest() == g[key]["sha_x"]
+        assert hashlib.sha256(t.wj.tobytes()).hexdigest() == g[key]["sha_w"]
+    assert g["15_12"]["n"] == 12743            # N1
+
+
+def test_known_integrals(tab):
+    """psitools_examples/tanhsinh_example.ipynb known answers + the reference's own values."""
+    g = load("nodes.json")["known"]
+    eps = 1e-8
+    got = {
+        "xlog1px": po.integrate(lambda x: x*np.log(1 + x), 0.0, 1.0, tab),
+        "sqrtxlogx": po.integrate(lambda x: np.sqrt(x)*np.log(x), 0.0, 1.0, tab),
+        "log2x": po.integrate(lambda x: np.log(x)**2, 0.0, 1.0, tab),
+        "lorentz": po.integrate(lambda x: eps/(x*x + eps*eps), 0.0, 1.0, tab),
+    }
+    for k, v in got.items():
+        assert abs(v - g[k]) <= 1e-15*max(1.0, abs(g[k])), k
+    assert abs(got["xlog1px"] - 0.25) < 1e-14
+    assert abs(got["sqrtxlogx"] + 4.0/9.0) < 1e-14
+    assert abs(got["log2x"] - 2.0) < 1e-11
+    z = po.integrate(lambda x: np.exp((1 + 2j)*x), -1.0, 2.5, tab)
+    assert abs(z - cplx(g["cexp"])) < 1e-14*abs(z)
+
+
+def test_background_matches_reference(tab):
+    for name, g in load("background.json").items():
+        d = oracle_dist(g["spec"])
+        disp = po.Dispersion(d, tab)
+        assert abs(disp.vgx - g["vgx"]) <= 4e-16*abs(g["vgx"]), name
+        assert abs(disp.vgy - g["vgy"]) <= 4e-16*abs(g["vgy"]), name
+        assert abs(d.rhod - g["rhod"]) <= 1e-15*abs(g["rhod"]), name
+        s = np.array(g["s_probe"])
+        np.testing.assert_allclose(d.F(s), g["F_probe"], rtol=1e-14, err_msg=name)
+        assert np.allclose(d.poles, g["poles"], rtol=0, atol=0), name
+
+
+def test_dispersion_matches_reference(tab):
+    """D and the seven M entries at every fixture point (reference run with TanhSinh())."""
+    bg = load("background.json")
+    for case in load("disp.json")["cases"]:
+        disp = po.Dispersion(oracle_dist(bg[case["dist"]]["spec"]), tab)
+        w = carr(case["w"])
+        D, M = disp.calculate(w, case["kx"], case["kz"], case["alpha"], return_M=True)
+        ref = carr(case["D"])
+        Mref = np.array([carr(m) for m in case["M"]])
+        scale = np.median(np.abs(ref))
+        assert np.max(np.abs(D - ref)) <= 1e-12*scale, case["dist"]
+        assert np.max(np.abs(M - Mref)/np.max(np.abs(Mref), axis=1, keepdims=True)) <= 1e-11
+
+
+def test_reference_test_goldens_D(tab):
+    """test_psi_mode_mpi.py:157-171 (QUADPACK values pasted in the reference test) vs TanhSinh."""
+    disp = po.Dispersion(po.DustDist.power_law(3.0, [1e-8, 1.0]), tab)
+    w = np.array([-2 - 2j, 2 - 2j, -2 + 2j, 2 + 2j])
+    gold = np.array([-1.72733464670814e+08 + 5.32484293672187e+07j,
+                     -1.01104322248054e+08 + 1.70121606122589e+07j,
+                     -1.41025978843637e+08 + 1.08008841143562e+08j,
+                     -8.18797751107521e+07 + 8.84518043425989e+07j])
+    got = disp.calculate(w, 100.0, 10.0)
+    np.testing.assert_allclose(got.real, gold.real, rtol=1e-11)
+    np.testing.assert_allclose(got.imag, gold.imag, rtol=1e-11)
+    q = carr(load("disp.json")["quadpack_mrn_1_K100_10"]["D"])
+    assert np.max(np.abs(got - q)/np.abs(q)) < 5e-13     # TanhSinh vs QUADPACK path of the reference
+
+
+def test_mode_matches_reference(tab):
+    """PSIMode.calculate: same roots, same number of D evaluations, same AAA node mask as the
+    reference run (test_psi_mode.py:32-189 configurations, seed 0) and the pasted pins."""
+    bg = load("background.json")
+    for case in load("mode.json")["cases"]:
+        disp = po.Dispersion(oracle_dist(bg[case["dist"]]["spec"]), tab)
+        init = case["init"]
+        np.random.seed(case["seed"])
+        md = po.Mode(disp, init["real_range"], init["imag_range"], init.get("n_sample", 20),
+                     init.get("max_zoom_domains", 1))
+        roots = md.calculate(case["K"][0], case["K"][1], case["alpha"])
+        ref = carr(case["roots"])
+        assert len(roots) == len(ref) == 1, case["name"]
+        assert abs(roots[0] - ref[0]) <= 1e-9*abs(ref[0]), case["name"]
+        assert md.n_function_call == case["n_function_call"], case["name"]
+        assert list(md.ra.mask.astype(int)) == case["mask"], case["name"]
+        pin = cplx(case["pin"])                       # golden pasted in test_psi_mode.py, rtol 1e-7
+        np.testing.assert_allclose(roots[0].real, pin.real, rtol=1e-7)
+        np.testing.assert_allclose(roots[0].imag, pin.imag, rtol=1e-7)
