@@ -217,11 +217,13 @@ def run_b200(args):
     flush = torch.empty(256*1024*1024, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
+    cmask = 1 << ctx.point_class(pd.dist_id, 0.0)
+
     def step_resident():
         flush.fill_(1)
         ctx.disp_eval_dev(n, 1, dist_dev.data_ptr(), par.data_ptr(), par.data_ptr() + 8,
                           par.data_ptr() + 16, w_dev.data_ptr(), D_dev.data_ptr(), 0,
-                          nodes_dev.data_ptr(), stream.cuda_stream)
+                          nodes_dev.data_ptr(), cmask, stream.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -249,7 +251,7 @@ def run_b200(args):
         kev[i][0].record(stream)
         ctx.disp_eval_dev(n, 1, dist_dev.data_ptr(), par.data_ptr(), par.data_ptr() + 8,
                           par.data_ptr() + 16, w_dev.data_ptr(), D_dev.data_ptr(), 0,
-                          nodes_dev.data_ptr(), stream.cuda_stream)
+                          nodes_dev.data_ptr(), cmask, stream.cuda_stream)
         kev[i][1].record(stream)
     ev[1].record(stream)
     barrier()

@@ -81,10 +81,15 @@ int psi_dist_get_background(psi_ctx* ctx, int dist, double out[5]);
 int psi_disp_eval_host(psi_ctx* ctx, long long n, int broadcast, const int* dist, const double* kx,
                        const double* kz, const double* alpha, const double* w, double* D, double* M,
                        unsigned long long* node_evals);
-/* Same with device pointers; node_evals_dev (optional) is a device counter that is INCREMENTED. */
+/* Same with device pointers; node_evals_dev (optional) is a device counter that is INCREMENTED.
+ * K1 is compiled once per work class (size-density family x viscous/inviscid, psi_point_class);
+ * class_mask has bit c set when the batch may contain points of class c (0 = all classes, i.e. one
+ * launch per class, each skipping foreign points). */
 int psi_disp_eval_dev(psi_ctx* ctx, long long n, int broadcast, const int* dist, const double* kx,
                       const double* kz, const double* alpha, const double* w, double* D, double* M,
-                      unsigned long long* node_evals_dev, void* stream);
+                      unsigned long long* node_evals_dev, unsigned class_mask, void* stream);
+/* Work class (0..7) of a point of distribution `dist` at viscosity parameter alpha. */
+int psi_point_class(psi_ctx* ctx, int dist, double alpha);
 
 /* FP64 FMA-pipe peak of the device (roofline denominator; MEASURED_PEAKS.json has no FP64 entry):
  * runs a register-resident DFMA chain kernel `reps` times and returns the best TFLOP/s. */

@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpsi_b200.so")
+LIB_PATH = os.environ.get("PSI_B200_LIB", os.path.join(_HERE, "libpsi_b200.so"))   # override: experiments only
 
 PSI_MAX_POLES = 4
 KIND_POWERLAW, KIND_POWERBUMP, KIND_POWERBUMPTAIL = 0, 1, 2
@@ -56,7 +56,8 @@ _SIGNATURES = {
     "psi_disp_eval_host": (C.c_int, [_vp, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      C.POINTER(C.c_ulonglong)]),
     "psi_disp_eval_dev": (C.c_int, [_vp, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                    _vp, _vp]),
+                                    _vp, C.c_uint, _vp]),
+    "psi_point_class": (C.c_int, [_vp, C.c_int, C.c_double]),
     "psi_measure_fp64_peak": (C.c_int, [_vp, C.c_int, _dp]),
 }
 
@@ -173,13 +174,16 @@ class Context:
         self.node_evals += ne.value
         return (D, M) if want_M else D
 
+    def point_class(self, dist_id, alpha):
+        return check(self.lib.psi_point_class(self.handle, int(dist_id), float(alpha)), "psi_point_class")
+
     def disp_eval_dev(self, n, broadcast, dist_ptr, kx_ptr, kz_ptr, alpha_ptr, w_ptr, D_ptr, M_ptr=0,
-                      node_evals_ptr=0, stream=0):
+                      node_evals_ptr=0, class_mask=0, stream=0):
         """K1 on DEVICE pointers (ints), asynchronous on ``stream`` (a cudaStream_t as int; 0 = the
         context's own stream).  Used when inputs are already resident in HBM."""
         check(self.lib.psi_disp_eval_dev(self.handle, int(n), int(broadcast), dist_ptr, kx_ptr, kz_ptr,
                                          alpha_ptr, w_ptr, D_ptr, M_ptr or None,
-                                         node_evals_ptr or None, stream or None),
+                                         node_evals_ptr or None, int(class_mask), stream or None),
               "psi_disp_eval_dev")
 
     def measure_fp64_peak(self, reps=5):

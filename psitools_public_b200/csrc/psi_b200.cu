@@ -46,7 +46,10 @@ struct WarpCuda {
 // context
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxDists = 4096;
-constexpr int kEvalThreads = 384;          // 12 warps per persistent CTA
+#ifndef PSI_EVAL_THREADS
+#define PSI_EVAL_THREADS 384
+#endif
+constexpr int kEvalThreads = PSI_EVAL_THREADS;   // warps*32 per persistent CTA (one CTA per SM)
 
 struct psi_ctx {
     int device = 0;
@@ -91,7 +94,9 @@ __global__ void background_kernel(NodeTableView t, DistParams* dists, int id) {
     }
 }
 
-template <bool SMEM_TABLE>
+// K1.  One specialisation per work class (NK, VISC); a launch handles the points of ITS class and
+// skips the others (a batch normally holds a single class, see launch_disp_eval).
+template <bool SMEM_TABLE, int NK, bool VISC>
 __global__ void __launch_bounds__(kEvalThreads, 1)
 disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long long n, int broadcast,
                  const int* __restrict__ dist, const double* __restrict__ kx,
@@ -120,9 +125,12 @@ disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long lo
         if (idx >= (unsigned long long)n) break;
         const long long pi = broadcast ? 0 : (long long)idx;
         const DistParams& d = dists[dist[pi]];
+        const double al = alpha[pi];
+        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
         const double2 wv = w[idx];
         cx m[7];
-        const cx val = disp_eval_warp<WarpCuda>(t, d, cx(wv.x, wv.y), kx[pi], kz[pi], alpha[pi], m, nodes);
+        const cx val = disp_eval_warp<WarpCuda, NK, VISC>(t, d, cx(wv.x, wv.y), kx[pi], kz[pi], al,
+                                                          M != nullptr ? m : nullptr, nodes);
         if (lane == 0) D[idx] = make_double2(val.re, val.im);
         if (M != nullptr && lane < 7) {
             cx mv = m[0];
@@ -132,6 +140,24 @@ disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long lo
         }
     }
     if (node_evals != nullptr && lane == 0 && nodes) atomicAdd(node_evals, nodes);
+}
+
+typedef void (*eval_kernel_t)(NodeTableView, const DistParams*, long long, int, const int*, const double*,
+                              const double*, const double*, const double2*, double2*, double2*,
+                              unsigned long long*, unsigned long long*);
+
+template <bool SMEM>
+static eval_kernel_t eval_kernel_for(int cls) {
+    switch (cls) {
+    case 0: return disp_eval_kernel<SMEM, 0, false>;
+    case 1: return disp_eval_kernel<SMEM, 0, true>;
+    case 2: return disp_eval_kernel<SMEM, 1, false>;
+    case 3: return disp_eval_kernel<SMEM, 1, true>;
+    case 4: return disp_eval_kernel<SMEM, 2, false>;
+    case 5: return disp_eval_kernel<SMEM, 2, true>;
+    case 6: return disp_eval_kernel<SMEM, 3, false>;
+    default: return disp_eval_kernel<SMEM, 3, true>;
+    }
 }
 
 // DFMA-pipe peak: 8 independent FMA chains per thread, all in registers.
@@ -192,8 +218,9 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
     c->table_smem = sizeof(node_t) * (size_t)n_nodes + sizeof(int) * off.size();
     c->table_in_smem = c->table_smem + 1024 <= (size_t)c->smem_optin;
     if (c->table_in_smem)
-        CK(cudaFuncSetAttribute(disp_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)c->table_smem));
+        for (int cls = 0; cls < kNumClasses; ++cls)
+            CK(cudaFuncSetAttribute(eval_kernel_for<true>(cls),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
     CK(cudaMalloc(&c->d_dists, sizeof(DistParams) * kMaxDists));
     CK(cudaMalloc(&c->d_counter, sizeof(unsigned long long) * 8));
     CK(cudaMemset(c->d_counter, 0, sizeof(unsigned long long) * 8));
@@ -242,6 +269,12 @@ int psi_dist_add(psi_ctx* c, const psi_dist_desc* s) {
     return id;
 }
 
+int psi_point_class(psi_ctx* c, int dist, double alpha) {
+    if (!c || dist < 0 || dist >= (int)c->h_dists.size())
+        return fail(PSI_ERR_ARG, "psi_point_class: bad argument");
+    return point_class(c->h_dists[dist], alpha);
+}
+
 int psi_dist_get_background(psi_ctx* c, int dist, double out[5]) {
     if (!c || !out || dist < 0 || dist >= (int)c->h_dists.size())
         return fail(PSI_ERR_ARG, "psi_dist_get_background: bad argument");
@@ -250,36 +283,39 @@ int psi_dist_get_background(psi_ctx* c, int dist, double out[5]) {
     return PSI_OK;
 }
 
+// class_mask: bit c set = the batch may contain points of work class c (see point_class()).
 static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* dist, const double* kx,
                             const double* kz, const double* alpha, const double* w, double* D,
-                            double* M, unsigned long long* node_evals_dev, cudaStream_t st) {
+                            double* M, unsigned long long* node_evals_dev, unsigned class_mask,
+                            cudaStream_t st) {
     if (n == 0) return PSI_OK;
     const int warps = kEvalThreads / 32;
     long long want = (n + warps - 1) / warps;
     int grid = (int)(want < c->sm_count ? want : c->sm_count);
-    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
     NodeTableView t = table_view(c);
-    if (c->table_in_smem)
-        disp_eval_kernel<true><<<grid, kEvalThreads, c->table_smem, st>>>(
+    if ((class_mask & 0xffu) == 0) class_mask = 0xffu;
+    for (int cls = 0; cls < kNumClasses; ++cls) {
+        if (!(class_mask & (1u << cls))) continue;
+        CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+        eval_kernel_t k = c->table_in_smem ? eval_kernel_for<true>(cls) : eval_kernel_for<false>(cls);
+        k<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
             t, c->d_dists, n, broadcast, dist, kx, kz, alpha, (const double2*)w, (double2*)D,
             (double2*)M, c->d_counter, node_evals_dev);
-    else
-        disp_eval_kernel<false><<<grid, kEvalThreads, 0, st>>>(
-            t, c->d_dists, n, broadcast, dist, kx, kz, alpha, (const double2*)w, (double2*)D,
-            (double2*)M, c->d_counter, node_evals_dev);
-    c->launches++;
-    CK(cudaGetLastError());
+        c->launches++;
+        CK(cudaGetLastError());
+    }
     return PSI_OK;
 }
 
 int psi_disp_eval_dev(psi_ctx* c, long long n, int broadcast, const int* dist, const double* kx,
                       const double* kz, const double* alpha, const double* w, double* D, double* M,
-                      unsigned long long* node_evals_dev, void* stream) {
+                      unsigned long long* node_evals_dev, unsigned class_mask, void* stream) {
     if (!c || n < 0 || !dist || !kx || !kz || !alpha || (n > 0 && (!w || !D)))
         return fail(PSI_ERR_ARG, "psi_disp_eval_dev: bad argument");
     CK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    return launch_disp_eval(c, n, broadcast, dist, kx, kz, alpha, w, D, M, node_evals_dev, st);
+    return launch_disp_eval(c, n, broadcast, dist, kx, kz, alpha, w, D, M, node_evals_dev, class_mask,
+                            st);
 }
 
 static int ensure_stage(psi_ctx* c, size_t bytes) {
@@ -300,9 +336,12 @@ int psi_disp_eval_host(psi_ctx* c, long long n, int broadcast, const int* dist, 
     if (n == 0) return PSI_OK;
     CK(cudaSetDevice(c->device));
     const long long np = broadcast ? 1 : n;
-    for (long long i = 0; i < np; ++i)
+    unsigned class_mask = 0;
+    for (long long i = 0; i < np; ++i) {
         if (dist[i] < 0 || dist[i] >= (int)c->h_dists.size())
             return fail(PSI_ERR_ARG, "psi_disp_eval_host: distribution id out of range");
+        class_mask |= 1u << point_class(c->h_dists[dist[i]], alpha[i]);
+    }
     // staging layout: w | D | M | kx | kz | alpha | dist   (all 16-byte aligned)
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t o_w = 0, o_D = al(o_w + 16 * n), o_M = al(o_D + 16 * n),
@@ -321,7 +360,7 @@ int psi_disp_eval_host(psi_ctx* c, long long n, int broadcast, const int* dist, 
     rc = launch_disp_eval(c, n, broadcast, (const int*)(base + o_ds), (const double*)(base + o_kx),
                           (const double*)(base + o_kz), (const double*)(base + o_al),
                           (const double*)(base + o_w), (double*)(base + o_D),
-                          M ? (double*)(base + o_M) : nullptr, c->d_counter + 1, st);
+                          M ? (double*)(base + o_M) : nullptr, c->d_counter + 1, class_mask, st);
     if (rc != PSI_OK) return rc;
     CK(cudaMemcpyAsync(D, base + o_D, 16 * n, cudaMemcpyDeviceToHost, st));
     if (M) CK(cudaMemcpyAsync(M, base + o_M, 112 * n, cudaMemcpyDeviceToHost, st));

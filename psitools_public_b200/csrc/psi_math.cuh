@@ -88,7 +88,34 @@ struct DistParams {
     double calc_poles[kMaxPoles];
 };
 
-// sigma(a) of the analytic families
+// ---- fast reciprocal / reciprocal square root (MUFU seed + Newton, ~1 ulp) ---------------------------
+PSI_HD double fast_rcp(double a) {
+#if defined(__CUDA_ARCH__)
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));     // ~20 bits (MUFU.RCP64H)
+    double e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    return fma(x, e, x);
+#else
+    return 1.0 / a;
+#endif
+}
+PSI_HD double fast_rsqrt(double a) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));   // ~20 bits (MUFU.RSQ64H)
+    const double ha = 0.5 * a;
+    y = y * fma(-ha * y, y, 1.5);
+    y = y * fma(-ha * y, y, 1.5);
+    return y;
+#else
+    return 1.0 / sqrt(a);
+#endif
+}
+PSI_HD cx fast_recip(cx a) { const double s = fast_rcp(norm2(a)); return cx(a.re * s, -a.im * s); }
+
+// sigma(a) of the analytic families (straightforward form; the quadrature uses NodeGen below)
 PSI_HD double sigma_of(const DistParams& d, double a) {
     if (d.kind == kPowerLaw) return pow(a, d.q);
     // PowerBump.mnn (power_bump.py:97-123) / PowerBumpTail.fnn (:193-212)
@@ -106,11 +133,86 @@ PSI_HD double F_of(const DistParams& d, double s) {
     return d.taumax * sigma_of(d, d.taumax * s) / d.rhod;
 }
 
+// ---- quadrature nodes of one sub-interval ------------------------------------------------------------
+// For the abscissa pair +-x of the tanh-sinh rule on [a, b] (in u = ln s, psi_dispersion.py:135-145)
+// the quadrature needs, per node:  tau = taumax*e^u,  1/tau,  and the weight e^u * F(e^u).
+// With mid = (a+b)/2, half = (b-a)/2:  e^{u(+-x)} = e^{mid} * E^{+-1},  E = exp(half*x), so ONE exp and
+// one reciprocal serve both nodes of the pair, and 1/tau comes for free.  For a power law
+// e^u F(e^u) = taumax^(q+1)/rhod * e^{(q+1)u}  (psi_dispersion.py:57-66), i.e. a second exp pair --
+// or a square root when q + 1 = 1/2 (MRN).  For the bump families e^u F(e^u) = tau^4 v(tau) scale/rhod
+// with v the piecewise max(power law, Gaussian) of power_bump.py:97-123.
+enum NodeKind { kNodePowerSqrt = 0, kNodePowerGen = 1, kNodeBump = 2, kNodeBumpTail = 3 };
+
+PSI_HD int node_kind_of(const DistParams& d) {
+    if (d.kind == kPowerLaw) return (d.q == -0.5) ? kNodePowerSqrt : kNodePowerGen;
+    return d.kind == kPowerBump ? kNodeBump : kNodeBumpTail;
+}
+
+struct NodeVals { double tau, it, wt; };      // stopping time, 1/tau, e^u F(e^u)
+
+template <int NK>
+struct NodeGen {
+    double half, tm, itm, cw, qe, plm, tailc;
+    const DistParams* d;
+    PSI_HD void begin(const DistParams& dd, double a, double b) {
+        d = &dd;
+        half = 0.5 * (b - a);
+        const double mid = 0.5 * (b + a);
+        const double em = exp(mid);
+        tm = dd.taumax * em;                    // tau at x = 0
+        itm = 1.0 / tm;
+        if (NK == kNodePowerSqrt || NK == kNodePowerGen) {
+            qe = dd.q + 1.0;
+            cw = pow(dd.taumax, qe) / dd.rhod * exp(qe * mid);
+        } else {
+            cw = dd.scale / dd.rhod;
+            plm = dd.norm_pl * pow(tm, dd.beta);                         // power law at x = 0
+            tailc = dd.norm_pl * pow(dd.aBT > 0 ? dd.aBT : 1.0, dd.beta);  // value at aBT
+        }
+    }
+    PSI_HD double bump_weight(double tau, double pl) const {
+        const DistParams& dd = *d;
+        if (NK == kNodeBumpTail && !(tau > dd.aBT)) pl = tailc * sqrt(tau * fast_rcp(dd.aBT));
+        const double t = tau - dd.aP;
+        const double bb = dd.amp * exp(dd.curv * (t * t));
+        double v = pl;
+        if (tau > dd.aL) v = fmax(pl, bb);
+        if (tau > dd.aP) v = bb;
+        const double t2 = tau * tau;
+        return cw * v * (t2 * t2);
+    }
+    // nodes at +x (p) and -x (n)
+    PSI_HD void pair(double x, NodeVals& p, NodeVals& n) const {
+        const double h = half * x;
+        const double E = exp(h), Ei = fast_rcp(E);
+        p.tau = tm * E;  p.it = itm * Ei;
+        n.tau = tm * Ei; n.it = itm * E;
+        if (NK == kNodePowerSqrt) {
+            const double rs = fast_rsqrt(E);
+            p.wt = cw * (E * rs); n.wt = cw * rs;
+        } else if (NK == kNodePowerGen) {
+            const double G = exp(qe * h);
+            p.wt = cw * G; n.wt = cw * fast_rcp(G);
+        } else {
+            const double B = exp(d->beta * h);
+            p.wt = bump_weight(p.tau, plm * B);
+            n.wt = bump_weight(n.tau, plm * fast_rcp(B));
+        }
+    }
+    PSI_HD NodeVals centre() const {            // x = 0
+        NodeVals c; c.tau = tm; c.it = itm;
+        if (NK == kNodePowerSqrt || NK == kNodePowerGen) c.wt = cw; else c.wt = bump_weight(tm, plm);
+        return c;
+    }
+};
+
 // ---- per-point constants ----------------------------------------------------------------------------
 struct PointConst {
-    double kx, kz, k2, nu;
+    double kx, kz, k2, nu, kappa;   // kappa = kz/kx
     cx w;            // omega
     cx c0;           // 1/(omega - kx*vgx)
+    cx ic0;          // i*c0
+    double c1;       // Im(w)^2 + 1
     double A2;       // 2*denom
     double j0p;      // 1 + J0
     double j1, dn, vgx, vgy;
@@ -118,81 +220,99 @@ struct PointConst {
 
 PSI_HD PointConst make_point(const DistParams& d, cx w, double kx, double kz, double alpha) {
     PointConst p;
-    p.kx = kx; p.kz = kz; p.k2 = kx * kx + kz * kz;
+    p.kx = kx; p.kz = kz; p.k2 = kx * kx + kz * kz; p.kappa = kz / kx;
     p.nu = alpha * d.c * d.c;                       // psi_dispersion.py:389
     p.w = w;
     p.c0 = recip(cx(w.re - kx * d.vgx, w.im));
+    p.ic0 = mul_i(p.c0);
+    p.c1 = w.im * w.im + 1.0;
     p.A2 = 2 * d.denom; p.j0p = 1 + d.j0; p.j1 = d.j1; p.dn = d.denom; p.vgx = d.vgx; p.vgy = d.vgy;
     return p;
 }
 
-// The seven integrands (V A^-1 D + W)_ij * i/tau, ij in {11,12,13,21,22,23,33}, at stopping time tau,
-// from shared sub-expressions (psi_dispersion.py:212-373; expansion in SURVEY.md section 8 a6).
-// out[k] += wt * integrand_k.
-template <bool VISC>
-PSI_HD void m_integrands_acc(const PointConst& p, double tau, double wt, cx* acc) {
-    const double r1 = 1.0 / (1.0 + tau * tau);
-    const double ux = p.A2 * (p.j1 - tau * p.j0p) * r1;            // :80
-    const double uy = -p.dn * (p.j0p + tau * p.j1) * r1;           // :81
-    const double dux = ux - p.vgx, duy = uy - p.vgy;
-    const double it = 1.0 / tau;                                    // K = i/tau
-    const double s1 = dux * p.kx, s2 = dux * p.kz, s3 = duy * p.kx, s4 = duy * p.kz;
-    // d = kx*ux - w - i/tau                                           (:214)
-    const cx d(p.kx * ux - p.w.re, -p.w.im - it);
-    // den = 1/(1 - d^2)                                               (:215)
-    const cx den = recip(cx(1.0 - (d.re * d.re - d.im * d.im), -2.0 * d.re * d.im));
-    const cx dden = d * den;
-    const cx a11 = -dden;                       // = a22
-    const cx a12(-2.0 * den.im, 2.0 * den.re);  // 2i*den
-    const cx a21(0.5 * den.im, -0.5 * den.re);  // -0.5i*den
-    const cx rd = recip(d);                     // a33
-    // E = (i/tau)*c0 ; D-matrix entries                               (:238-246)
-    const cx E(-it * p.c0.im, it * p.c0.re);
-    const cx d11(s1 * E.re, s1 * E.im - it);
-    const cx d13 = s2 * E, d21 = s3 * E, d23 = s4 * E;
-    // A^-1 D                                                          (:249-275)
-    const cx ad11 = a11 * d11 + a12 * d21;
-    const cx ad12 = (2.0 * it) * den;                    // a12*(-i/tau)
-    const cx ad13 = a11 * d13 + a12 * d23;
-    const cx ad21 = a21 * d11 + a11 * d21;
-    const cx ad22(-it * dden.im, it * dden.re);          // a11*(-i/tau) = (i/tau)*d*den
-    const cx ad23 = a21 * d13 + a11 * d23;
-    const cx ad33(it * rd.im, -it * rd.re);              // (1/d)*(-i/tau)
-    // dv = 1/(w - kx*ux + i*(k2*Dtau + 1e-10))                        (:288-289)
-    double dif = 0.0;
-    if (VISC) {
-        const double r2 = r1 * r1;
-        dif = (1.0 + tau + 4.0 * tau * tau) * p.nu * r2;              // :390
-    }
-    const cx dv = recip(cx(-d.re, p.w.im + (p.k2 * dif + 1.0e-10)));
-    const cx v11(1.0 + s1 * dv.re, s1 * dv.im);
-    const cx v13 = s2 * dv, v21 = s3 * dv, v23 = s4 * dv;
-    cx o0 = v11 * ad11, o1 = v11 * ad12, o2 = v11 * ad13 + v13 * ad33;
-    cx o3 = v21 * ad11 + ad21, o4 = v21 * ad12 + ad22, o5 = v21 * ad13 + ad23 + v23 * ad33;
-    cx o6 = ad33;
-    if (VISC) {
-        // W - (-I) part: q = i*Dtau*k2*dv*c0                           (:338-345)
-        const cx q = mul_i((dif * p.k2) * (dv * p.c0));
-        o0 = o0 + s1 * q; o2 = o2 + s2 * q; o3 = o3 + s3 * q; o5 = o5 + s4 * q;
-    }
-    o0.re -= 1.0; o4.re -= 1.0; o6.re -= 1.0;           // W11 = W22 = W33 = -1
-    // times K = i/tau, times the quadrature weight
-    const double g = wt * it;
-    acc[0].re -= g * o0.im; acc[0].im += g * o0.re;
-    acc[1].re -= g * o1.im; acc[1].im += g * o1.re;
-    acc[2].re -= g * o2.im; acc[2].im += g * o2.re;
-    acc[3].re -= g * o3.im; acc[3].im += g * o3.re;
-    acc[4].re -= g * o4.im; acc[4].im += g * o4.re;
-    acc[5].re -= g * o5.im; acc[5].im += g * o5.re;
-    acc[6].re -= g * o6.im; acc[6].im += g * o6.re;
+// Scale factors deferred out of the node loop: M12 = 2*int(...), M13 = kappa*int(...), M23 likewise.
+PSI_HD void m_scales(const PointConst& p, double* sc) {
+    sc[0] = 1.0; sc[1] = 2.0; sc[2] = fabs(p.kappa); sc[3] = 1.0; sc[4] = 1.0; sc[5] = fabs(p.kappa); sc[6] = 1.0;
+}
+PSI_HD void m_apply_scales(const PointConst& p, cx* m) {
+    m[1] = 2.0 * m[1]; m[2] = p.kappa * m[2]; m[5] = p.kappa * m[5];
 }
 
-// J_alpha integrands tau^alpha/(1+tau^2), alpha = 0, 1              (psi_dispersion.py:183-187)
-PSI_HD void j_integrands_acc(double tau, double wt, cx* acc) {
-    const double r1 = wt / (1.0 + tau * tau);
-    acc[0].re += r1;
-    acc[1].re += tau * r1;
+// The seven integrands (V A^-1 D + W)_ij * i/tau, ij in {11,12,13,21,22,23,33}, at one node
+// (psi_dispersion.py:212-373).  Notation: delta = kx*ux - w, d = delta - i/tau, den = 1/(1-d^2),
+// rd = 1/d, dv = 1/(w - kx*ux + i(k^2 Dtau + 1e-10)), s1 = dux*kx, s3 = duy*kx, kappa = kz/kx.
+// Algebra used (all exact identities of the reference's expressions):
+//   A^-1 D columns 1 and 3 are E*(p, r) - (i/tau)(a11, a21) and kappa*E*(p, r) with
+//     E = (i/tau) c0,  p = den*(-d s1 + 2i s3),  r = den*(-d s3 - i s1/2);
+//   the "-1" of W11, W22, W33 is absorbed without cancellation:
+//     -(i/tau) a11 - 1 = (delta^2 - (i/tau) delta - 1) den =: N den,   A33D33 - 1 = -delta*rd;
+//   v11 = 1 + s1 dv, v21 = s3 dv, v13 = kappa s1 dv, v23 = kappa s3 dv.
+// acc[k] += wt * (i/tau) * integrand_k, with the constant factors of m_scales() left out.
+template <bool VISC>
+PSI_HD void m_node(const PointConst& p, const NodeVals& nv, double wq, cx* acc) {
+    const double tau = nv.tau, it = nv.it;
+    const double r1 = fast_rcp(fma(tau, tau, 1.0));
+    const double ux = p.A2 * (p.j1 - tau * p.j0p) * r1;            // :80
+    const double uy = -p.dn * (p.j0p + tau * p.j1) * r1;           // :81
+    const double s1 = (ux - p.vgx) * p.kx, s3 = (uy - p.vgy) * p.kx;
+    const double dr = fma(p.kx, ux, -p.w.re);                      // Re delta = Re d
+    const double di = -p.w.im - it;                                // Im d
+    const cx den = fast_recip(cx(1.0 - (dr * dr - di * di), -2.0 * dr * di));
+    const cx rd = fast_recip(cx(dr, di));
+    double dif = 0.0;
+    if (VISC) dif = (1.0 + tau + 4.0 * tau * tau) * p.nu * (r1 * r1);   // :390
+    const cx dv = fast_recip(cx(-dr, p.w.im + (p.k2 * dif + 1.0e-10)));
+    // N = delta^2 - (i/tau) delta - 1, delta = (dr, -w.im)
+    const cx N(dr * dr - p.c1 - it * p.w.im, -dr * (2.0 * p.w.im + it));
+    const cx Nden = N * den;
+    const cx P0(-dr * s1, 2.0 * s3 - di * s1);
+    const cx R0(-dr * s3, -di * s3 - 0.5 * s1);
+    const cx cden = p.ic0 * den;
+    const cx Ep = cden * P0, Er = cden * R0;           // E p / (1/tau), E r / (1/tau)
+    const cx X(fma(it, Ep.re, Nden.re), fma(it, Ep.im, Nden.im));         // A11D11... - 1
+    const cx T1 = dv * cx(X.re + 1.0, X.im);
+    const cx Y = dv * den;
+    const cx dvEp = dv * Ep, dvrd = dv * rd;
+    const cx S(dvEp.re + dvrd.im, dvEp.im - dvrd.re);                     // dv*Ep - i dv*rd
+    cx o0(fma(s1, T1.re, X.re), fma(s1, T1.im, X.im));
+    const cx o1(it * fma(s1, Y.re, den.re), it * fma(s1, Y.im, den.im));
+    cx o2(it * fma(s1, S.re, Ep.re), it * fma(s1, S.im, Ep.im));
+    cx o3(fma(it, fma(-0.5, den.re, Er.re), s3 * T1.re), fma(it, fma(-0.5, den.im, Er.im), s3 * T1.im));
+    const double its3 = 2.0 * it * s3;
+    const cx o4(fma(its3, Y.re, Nden.re), fma(its3, Y.im, Nden.im));
+    cx o5(it * fma(s3, S.re, Er.re), it * fma(s3, S.im, Er.im));
+    const cx o6(-(dr * rd.re + p.w.im * rd.im), -(dr * rd.im - p.w.im * rd.re));   // -delta*rd
+    if (VISC) {
+        // W + I: q = i*Dtau*k2*dv*c0                                       (:338-345)
+        const cx q = (dif * p.k2) * (dv * p.ic0);
+        o0 = o0 + s1 * q; o3 = o3 + s3 * q;
+        // columns 3 carry kz = kappa*kx; with kappa deferred the W13/W23 terms are s1 q, s3 q
+        o2 = o2 + s1 * q; o5 = o5 + s3 * q;
+    }
+    const double g = wq * nv.wt * it;
+    acc[0].re = fma(-g, o0.im, acc[0].re); acc[0].im = fma(g, o0.re, acc[0].im);
+    acc[1].re = fma(-g, o1.im, acc[1].re); acc[1].im = fma(g, o1.re, acc[1].im);
+    acc[2].re = fma(-g, o2.im, acc[2].re); acc[2].im = fma(g, o2.re, acc[2].im);
+    acc[3].re = fma(-g, o3.im, acc[3].re); acc[3].im = fma(g, o3.re, acc[3].im);
+    acc[4].re = fma(-g, o4.im, acc[4].re); acc[4].im = fma(g, o4.re, acc[4].im);
+    acc[5].re = fma(-g, o5.im, acc[5].re); acc[5].im = fma(g, o5.re, acc[5].im);
+    acc[6].re = fma(-g, o6.im, acc[6].re); acc[6].im = fma(g, o6.re, acc[6].im);
 }
+
+template <bool VISC>
+struct MNode {
+    const PointConst* p;
+    PSI_HD void operator()(const NodeVals& nv, double wq, cx* acc) const { m_node<VISC>(*p, nv, wq, acc); }
+};
+
+// J_alpha integrands tau^alpha/(1+tau^2), alpha = 0, 1              (psi_dispersion.py:183-187)
+struct JNode {
+    PSI_HD void operator()(const NodeVals& nv, double wq, cx* acc) const {
+        const double r1 = wq * nv.wt / fma(nv.tau, nv.tau, 1.0);
+        acc[0].re += r1;
+        acc[1].re = fma(nv.tau, r1, acc[1].re);
+    }
+};
 
 // ---- resonance poles ---------------------------------------------------------------------------------
 // Real roots of c0 + c1*tau + c2*tau^2 = 0 strictly inside (taumin, taumax), divided by taumax, merged

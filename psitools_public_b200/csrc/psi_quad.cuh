@@ -62,16 +62,18 @@ PSI_HD int kept_nodes(const NodeTableView& t, double a, double b) {
 }
 
 // Generic joint tanh-sinh over [a, b] of NC complex components.
-//   f(u, wt, acc) must do acc[k] += wt * integrand_k(u).
+//   gen  : NodeGen<..> already begin()'ed on [a, b]: turns an abscissa pair +-x into (tau, 1/tau, weight)
+//   fn   : fn(node, wq, acc) does acc[k] += wq * node.wt * integrand_k(node.tau)
+//   cscale[k] : constant factor the caller applies to component k afterwards (the exit test sees it)
 // Each component keeps the reference's own early exit: it stops, WITHOUT adding the last
 // increment, once |increment| < tol (tanhsinh.py:120-126).  `res` receives the NC results and
 // `nodes_done` is increased by the number of integrand evaluations this warp performed.
-template <class W, int NC, class F>
-PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol, F f, cx* res,
+template <class W, int NC, class GEN, class FN>
+PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol, const GEN& gen,
+                          const FN& fn, const double* cscale, cx* res,
                           unsigned long long& nodes_done) {
     const int lane = W::lane();
-    const double bma = b - a;
-    const double half = 0.5 * bma;
+    const double half = 0.5 * (b - a);
     const int nsel = kept_nodes(t, a, b);
     unsigned active = (1u << NC) - 1u;
     unsigned long long evals = 0;
@@ -84,8 +86,14 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
         const int cnt = nsel > 0 ? ((nsel - 1) >> t.max_m) + 1 : 0;     // j = k << max_m < nsel
         for (int k = lane; k < cnt; k += W::width) {
             const node_t nd = t.nodes[k];
-            f(abscissa(nd.x, bma, a, b), nd.y, acc);
-            if (k > 0) f(abscissa(-nd.x, bma, a, b), nd.y, acc);
+            if (k == 0) {
+                fn(gen.centre(), nd.y, acc);
+            } else {
+                NodeVals np, nn;
+                gen.pair(nd.x, np, nn);
+                fn(np, nd.y, acc);
+                fn(nn, nd.y, acc);
+            }
         }
         evals += cnt > 0 ? 2 * cnt - 1 : 0;
     }
@@ -106,8 +114,10 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
         for (int k = 0; k < NC; ++k) acc[k] = cx(0.0, 0.0);
         for (int i = lane; i < cnt; i += W::width) {
             const node_t nd = lv[i];
-            f(abscissa(nd.x, bma, a, b), nd.y, acc);
-            f(abscissa(-nd.x, bma, a, b), nd.y, acc);
+            NodeVals np, nn;
+            gen.pair(nd.x, np, nn);
+            fn(np, nd.y, acc);
+            fn(nn, nd.y, acc);
         }
         evals += 2ull * cnt;
         const double hh = h * half;
@@ -116,7 +126,7 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
             if (active & (1u << k)) {
                 cx dres(-0.5 * res[k].re + hh * W::sum(acc[k].re),
                         -0.5 * res[k].im + hh * W::sum(acc[k].im));
-                if (cabs(dres) < tol) active &= ~(1u << k);
+                if (cabs(dres) * cscale[k] < tol) active &= ~(1u << k);
                 else { res[k].re += dres.re; res[k].im += dres.im; }
             }
         }
@@ -127,21 +137,18 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
 
 // mu * sum over sub-intervals [ln smin, ln p1], [ln p1, ln p2], ..., [ln pn, 0] of the joint
 // integral of g(taumax*e^u) * e^u * F(e^u) du                      (psi_dispersion.py:135-157)
-template <class W, int NC, class G>
-PSI_HD void average_warp(const NodeTableView& t, const DistParams& d, const double* poles, int npoles,
-                         G g, cx* out, unsigned long long& nodes_done) {
+template <class W, int NC, int NK, class FN>
+PSI_HD void average_kind(const NodeTableView& t, const DistParams& d, const double* poles, int npoles,
+                         const FN& fn, const double* cscale, cx* out, unsigned long long& nodes_done) {
 #pragma unroll
     for (int k = 0; k < NC; ++k) out[k] = cx(0.0, 0.0);
-    const double a0 = log(d.taumin / d.taumax);
-    auto f = [&](double u, double wq, cx* acc) {
-        const double e = exp(u);
-        g(d.taumax * e, wq * (e * F_of(d, e)), acc);
-    };
-    double lo = a0;
+    double lo = log(d.taumin / d.taumax);
+    NodeGen<NK> gen;
     for (int s = 0; s <= npoles; ++s) {
         const double hi = (s < npoles) ? log(poles[s]) : 0.0;
         cx r[NC];
-        tanhsinh_warp<W, NC>(t, lo, hi, t.eps, f, r, nodes_done);
+        gen.begin(d, lo, hi);
+        tanhsinh_warp<W, NC>(t, lo, hi, t.eps, gen, fn, cscale, r, nodes_done);
 #pragma unroll
         for (int k = 0; k < NC; ++k) { out[k].re += r[k].re; out[k].im += r[k].im; }
         lo = hi;
@@ -160,9 +167,13 @@ PSI_HD void background_warp(const NodeTableView& t, DistParams& d, unsigned long
         j[0] = cx(d.mu * r1, 0.0);
         j[1] = cx(d.mu * d.taumax * r1, 0.0);
     } else {
-        average_warp<W, 2>(t, d, d.init_poles, d.n_init_poles,
-                           [](double tau, double wt, cx* acc) { j_integrands_acc(tau, wt, acc); }, j,
-                           nodes_done);
+        const double one[2] = {1.0, 1.0};
+        switch (node_kind_of(d)) {            // warp-uniform
+        case kNodePowerSqrt: average_kind<W, 2, kNodePowerSqrt>(t, d, d.init_poles, d.n_init_poles, JNode(), one, j, nodes_done); break;
+        case kNodePowerGen:  average_kind<W, 2, kNodePowerGen>(t, d, d.init_poles, d.n_init_poles, JNode(), one, j, nodes_done); break;
+        case kNodeBump:      average_kind<W, 2, kNodeBump>(t, d, d.init_poles, d.n_init_poles, JNode(), one, j, nodes_done); break;
+        default:             average_kind<W, 2, kNodeBumpTail>(t, d, d.init_poles, d.n_init_poles, JNode(), one, j, nodes_done); break;
+        }
     }
     d.j0 = j[0].re;
     d.j1 = j[1].re;
@@ -171,8 +182,16 @@ PSI_HD void background_warp(const NodeTableView& t, DistParams& d, unsigned long
     d.vgy = -(1.0 + d.j0) * d.denom;
 }
 
-// K1 body: one D(omega; Kx, Kz, alpha) evaluation by one warp.  Returns D; m_out (7 entries) gets M.
-template <class W>
+// Work class of a point: which specialisation of K1 evaluates it (kernels are compiled per class so
+// that each keeps its own, smaller register footprint).  class = node kind * 2 + (viscous ? 1 : 0).
+constexpr int kNumClasses = 8;
+PSI_HD int point_class(const DistParams& d, double alpha) {
+    return node_kind_of(d) * 2 + ((alpha * d.c * d.c) != 0.0 ? 1 : 0);
+}
+
+// K1 body: one D(omega; Kx, Kz, alpha) evaluation by one warp, for a point of class (NK, VISC).
+// Returns D; m_out (7 entries, may be null) gets M.
+template <class W, int NK, bool VISC>
 PSI_HD cx disp_eval_warp(const NodeTableView& t, const DistParams& d, cx w, double kx, double kz,
                          double alpha, cx* m_out, unsigned long long& nodes_done) {
     const PointConst p = make_point(d, w, kx, kz, alpha);
@@ -181,25 +200,38 @@ PSI_HD cx disp_eval_warp(const NodeTableView& t, const DistParams& d, cx w, doub
         // average() shortcut: mu * g(taumax)                       (psi_dispersion.py:130-131)
 #pragma unroll
         for (int k = 0; k < 7; ++k) m[k] = cx(0.0, 0.0);
-        if (p.nu != 0.0) m_integrands_acc<true>(p, d.taumax, d.mu, m);
-        else m_integrands_acc<false>(p, d.taumax, d.mu, m);
+        NodeVals nv; nv.tau = d.taumax; nv.it = 1.0 / d.taumax; nv.wt = d.mu;
+        m_node<VISC>(p, nv, 1.0, m);
     } else {
         double poles[2 * kMaxPoles];
         const int np = resonance_poles(d, w.re, kx, poles);
-        if (p.nu != 0.0)
-            average_warp<W, 7>(t, d, poles, np,
-                               [&](double tau, double wt, cx* acc) { m_integrands_acc<true>(p, tau, wt, acc); },
-                               m, nodes_done);
-        else
-            average_warp<W, 7>(t, d, poles, np,
-                               [&](double tau, double wt, cx* acc) { m_integrands_acc<false>(p, tau, wt, acc); },
-                               m, nodes_done);
+        double sc[7];
+        m_scales(p, sc);
+        MNode<VISC> fn; fn.p = &p;
+        average_kind<W, 7, NK>(t, d, poles, np, fn, sc, m, nodes_done);
     }
+    m_apply_scales(p, m);
     if (m_out) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) m_out[k] = m[k];
     }
     return det_P_plus_M(d, p, m);
+}
+
+// run-time dispatch over the classes (host harness, small kernels)
+template <class W>
+PSI_HD cx disp_eval_any(const NodeTableView& t, const DistParams& d, cx w, double kx, double kz,
+                        double alpha, cx* m_out, unsigned long long& nodes_done) {
+    switch (point_class(d, alpha)) {
+    case 0: return disp_eval_warp<W, 0, false>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    case 1: return disp_eval_warp<W, 0, true>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    case 2: return disp_eval_warp<W, 1, false>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    case 3: return disp_eval_warp<W, 1, true>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    case 4: return disp_eval_warp<W, 2, false>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    case 5: return disp_eval_warp<W, 2, true>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    case 6: return disp_eval_warp<W, 3, false>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    default: return disp_eval_warp<W, 3, true>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    }
 }
 
 }  // namespace psi

@@ -56,7 +56,7 @@ int hs_disp_eval(const psi_dist_desc* desc, const double* xj, const double* wj, 
     nodes = 0;
     for (long long i = 0; i < npts; ++i) {
         cx m[7];
-        cx v = disp_eval_warp<WarpOne>(t.view, d, cx(w[2 * i], w[2 * i + 1]), kx[i], kz[i], alpha[i], m,
+        cx v = disp_eval_any<WarpOne>(t.view, d, cx(w[2 * i], w[2 * i + 1]), kx[i], kz[i], alpha[i], m,
                                        nodes);
         D[2 * i] = v.re; D[2 * i + 1] = v.im;
         if (M) for (int k = 0; k < 7; ++k) { M[14 * i + 2 * k] = m[k].re; M[14 * i + 2 * k + 1] = m[k].im; }
