@@ -69,6 +69,13 @@ def load():
     return ns
 
 
+_ITEMS = []     # arg list shared with forked workers (arg dicts hold unpicklable lambdas)
+
+
+def _run_index(i):
+    return _run_item(_ITEMS[i])
+
+
 def _run_item(args):
     """Worker body: one scheduler item through the reference's own runcompute."""
     kind, item = args
@@ -106,8 +113,10 @@ class SerialScheduler:
         items = [(self.kind, copy.deepcopy(a)) for a in arglist]
         if self.procs > 1:
             import multiprocessing as mp
+            global _ITEMS
+            _ITEMS = items
             with mp.get_context("fork").Pool(self.procs) as pool:
-                res = pool.map(_run_item, items, chunksize=1)
+                res = pool.map(_run_index, range(len(items)), chunksize=1)
         else:
             res = [_run_item(it) for it in items]
         return {i: r for i, r in enumerate(res)}
