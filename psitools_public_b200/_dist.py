@@ -1,0 +1,76 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), work items interleaved across ranks, results
+exchanged with ONE all-gather of fixed-slot float64 records per phase (NCCL over NVLink on GPUs,
+gloo in the CPU test-suite).  There is no data-path collective inside the kernels: every (Kx, Kz,
+omega) item is independent; this replaces the reference's pickled MPI
+point-to-point traffic (psi_mode_mpi.py:57-160) and the per-sweep bcast of psi_grid_refine.py:325-326.
+"""
+import numpy as np
+
+
+def _td():
+    try:
+        import torch.distributed as td
+    except Exception:
+        return None
+    return td if td.is_available() and td.is_initialized() else None
+
+
+def world_size():
+    td = _td()
+    return td.get_world_size() if td else 1
+
+
+def rank():
+    td = _td()
+    return td.get_rank() if td else 0
+
+
+def my_items(n_items):
+    """Indices owned by this rank: interleaved (i mod world == rank) so that the strongly
+    K-dependent cost of neighbouring pixels is spread over all GPUs."""
+    return list(range(rank(), n_items, world_size()))
+
+
+def _device_for_collectives():
+    import torch
+    td = _td()
+    if td is not None and td.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def all_gather_records(local):
+    """``local``: dict {global index: 1-D float64 array}.  Returns the union over all ranks.
+
+    Records are packed as rows [index, length, payload..., padding] of a common width (one
+    all-reduce MAX for the width and the row count, one all-gather for the data)."""
+    td = _td()
+    if td is None or td.get_world_size() == 1:
+        return dict(local)
+    import torch
+    dev = _device_for_collectives()
+    width = max([len(v) for v in local.values()] + [0])
+    shape = torch.tensor([len(local), width], dtype=torch.int64, device=dev)
+    td.all_reduce(shape, op=td.ReduceOp.MAX)
+    rows, width = int(shape[0]), int(shape[1])
+    buf = np.full((rows, width + 2), -1.0)
+    for r, (idx, v) in enumerate(sorted(local.items())):
+        buf[r, 0] = idx
+        buf[r, 1] = len(v)
+        buf[r, 2:2 + len(v)] = v
+    mine = torch.from_numpy(buf).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(td.get_world_size())]
+    td.all_gather(parts, mine)
+    out = {}
+    for p in parts:
+        a = p.cpu().numpy()
+        for row in a:
+            if row[0] >= 0:
+                out[int(row[0])] = row[2:2 + int(row[1])].copy()
+    return out
+
+
+def barrier():
+    td = _td()
+    if td is not None:
+        td.barrier()

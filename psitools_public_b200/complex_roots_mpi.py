@@ -1,0 +1,73 @@
+"""Root-count maps with the interface of psitools.complex_roots_mpi.MpiScheduler (reference
+complex_roots_mpi.py:32-175): items {'PSIDispersion.__init__': ..., 'dispersion': {wave numbers},
+'z_list': contour, 'count_roots': kwargs} -> number of roots inside the contour, or the sentinel
+-666 when the count did not converge (:171-174).  All contours of a rank are refined in lock-step,
+one K1 launch per refinement pass."""
+import numpy as np
+
+from . import _dist
+from ._engine import Job, run_lockstep
+from .complex_roots import contour_machine
+from .psi_dispersion import PSIDispersion
+from .psi_mode_mpi import _same_init
+
+FAILED_COUNT = -666
+
+
+class MpiScheduler:
+    def __init__(self, wall_start, wall_limit_total, verbose=True):
+        self.verbose = verbose
+        self.rank = _dist.rank()
+        self.nranks = _dist.world_size()
+        self.wall_start = wall_start
+        self.wall_limit_total = wall_limit_total
+        self._disp = []
+
+    def _dispersion(self, init):
+        for known, pd in self._disp:
+            if _same_init(known, init):
+                return pd
+        pd = PSIDispersion(**init)
+        self._disp.append((init, pd))
+        return pd
+
+    def _job(self, args):
+        pd = self._dispersion(args['PSIDispersion.__init__'])
+        kw = dict(args.get('count_roots', {}))
+        kw.pop('verbose', None)
+        d = args['dispersion']
+        job = Job(contour_machine(args['z_list'], **kw), pd.dist_id, d['wave_number_x'],
+                  d['wave_number_z'], d.get('viscous_alpha', 0))
+        return job, pd
+
+    def runcompute(self, args):
+        job, pd = self._job(args)
+        run_lockstep(pd.ctx, [job], capture_errors=True)
+        return self._value(job)
+
+    @staticmethod
+    def _value(job):
+        if job.error is None:
+            return int(job.result)
+        if isinstance(job.error, RuntimeError):
+            print('complex_roots_mpi caught RuntimeError in count_roots', job.error)
+            print('Likely means the max iterations was exceeded.')
+            return FAILED_COUNT
+        raise job.error
+
+    def run_all(self, arglist):
+        mine = _dist.my_items(len(arglist))
+        jobs, ctx = [], None
+        for i in mine:
+            job, pd = self._job(arglist[i])
+            jobs.append((i, job))
+            ctx = pd.ctx
+        if jobs:
+            run_lockstep(ctx, [j for _, j in jobs], capture_errors=True)
+        local = {i: np.array([float(self._value(j))]) for i, j in jobs}
+        merged = _dist.all_gather_records(local)
+        return {i: int(merged[i][0]) for i in sorted(merged)}
+
+    def run(self, arglist):
+        res = self.run_all(arglist)
+        return res if self.rank == 0 else None

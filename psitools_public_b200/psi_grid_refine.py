@@ -1,0 +1,247 @@
+"""Adaptive growth-rate maps -- drop-in for psitools.psi_grid_refine.PSIGridRefiner (reference
+psi_grid_refine.py:36-386).
+
+A base (Kx, Kz) log grid is solved, pixels without roots are re-run with the roots of their eight
+neighbours as guesses until nothing new is found, then the grid is refined to 2n-1 points per axis
+(log mid-points) and the sweeps repeat.  Every batch of runs goes through ``MpiScheduler.run_all``:
+the runs of a sweep are interleaved over the GPUs, advanced in lock-step on each, and the new roots
+are all-gathered so that every rank keeps the same replicated root map for the next sweep (this is
+the single exchange step per sweep that replaces the reference's bcast, :325-326).
+
+Kept bug-for-bug (results must match the reference's): the upper pad cell is Kaxis[1]+dK (:155,159),
+and the first run of every sweep re-uses the largest existing run id (offset = max(results), :226,
+:276, :321), overwriting that run's roots.
+Out of scope: prune_kmeans (dead code in the reference, :87-98, :272-273).
+"""
+import copy
+import time
+
+import numpy as np
+
+from . import _dist
+from . import psi_mode_mpi
+from .psi_mode import guess_domain_size  # noqa: F401  (re-exported like the reference)
+
+
+def spreadgrid(old, const_axis=0):
+    """Stretch a meshgrid array to 2n-1 points per axis, inserting log10 mid-points along the
+    varying axis.  For ``A, B = meshgrid(a, b, indexing='ij')``: A has const_axis=1, B const_axis=0."""
+    new = np.zeros([2*n - 1 for n in old.shape])
+    new[::2, ::2] = old
+    if const_axis == 0:
+        new[1:-1:2, ::2] = new[:-1:2, ::2]
+        new[:, 1:-1:2] = 10**(0.5*(np.log10(new[:, :-2:2]) + np.log10(new[:, 2::2])))
+    elif const_axis == 1:
+        new[::2, 1:-1:2] = new[::2, :-1:2]
+        new[1:-1:2, :] = 10**(0.5*(np.log10(new[:-2:2, :]) + np.log10(new[2::2, :])))
+    else:
+        raise ValueError('Bad const_axis')
+    return new
+
+
+def get_if(finishedruns, runkey):
+    """Roots of run ``runkey`` as a list; the key -1 (no run yet) gives an empty list."""
+    return list(finishedruns[runkey]) if runkey >= 0 else []
+
+
+def prune_eps(values, epsilon=1e-5):
+    """Crude pruning of root guesses: drop values within ``epsilon`` of an earlier kept one."""
+    if values is None or len(values) <= 1:
+        return values
+    kept = [values[0]]
+    for v in values[1:]:
+        if not any(np.abs(v - u) < epsilon for u in kept):
+            kept.append(v)
+    return np.array(kept)
+
+
+_NEIGHBOURS = ((-1, -1), (0, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (0, 1), (1, 1))   # (diz, dix)
+
+
+class PSIGridRefiner:
+    def __init__(self, batchname, baseargs=None, nbase=(16, 16), reruns=3, verbose=False,
+                 krange=(-1.0, 3.0), scheduler=None):
+        if baseargs:
+            self.baseargs = baseargs
+        else:
+            # defaults for testing (the reference's default Stokes range reads (1-8, 1e-1), an
+            # obvious typo for 1e-8 that would make every run fail)
+            self.baseargs = {'__init__': {'stokes_range': (1e-8, 1e-1), 'dust_to_gas_ratio': 10.0,
+                                          'size_distribution_power': 3.5,
+                                          'real_range': [-2.0, 2.0], 'imag_range': [1e-8, 1.0],
+                                          'n_sample': 30, 'max_zoom_domains': 1, 'tol': 1.0e-13,
+                                          'clean_tol': 1e-4},
+                             'calculate': {'wave_number_x': None, 'wave_number_z': None,
+                                           'guess_roots': []},
+                             'random_seed': 2}
+        self.nbase = nbase
+        self.krange = krange
+        self.reruns = reruns
+        self.batchname = batchname
+        self.datafile_hdf5 = batchname + '.hdf5'
+        self.verbose = verbose
+        self.wall_start = time.time()
+        self.wall_limit_total = 70*60*60
+        self.rank = _dist.rank()
+        self.root = self.rank == 0
+        self.ms = scheduler if scheduler is not None else \
+            psi_mode_mpi.MpiScheduler(self.wall_start, self.wall_limit_total, verbose=self.verbose)
+        self.grids = []
+        self.sweep_log = []          # (grid index, runs launched, new roots) per sweep
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _run(self, arglist):
+        """All results on all ranks (scheduler shards, solves and all-gathers)."""
+        if hasattr(self.ms, "run_all"):
+            return self.ms.run_all(arglist)
+        return self.ms.run(arglist)
+
+    def _padded_axis(self, n):
+        axis = np.logspace(self.krange[0], self.krange[1], n)
+        dk = axis[1] - axis[0]
+        return np.hstack(([axis[0] - dk], axis, [axis[1] + dk]))
+
+    def _sweep_until_quiet(self, max_sweep=32):
+        for _ in range(max_sweep):
+            if self.sweep_last_grid() == 0:
+                break
+
+    # -- public API ----------------------------------------------------------------------------
+    def run_basegrid(self):
+        kx_axis = self._padded_axis(self.nbase[1])
+        kz_axis = self._padded_axis(self.nbase[0])
+        kz_grid, kx_grid = np.meshgrid(kz_axis, kx_axis, indexing='ij')
+        runs = np.arange(kx_grid.size, dtype=int).reshape(kx_grid.shape)
+        arglist = []
+        for kx, kz in zip(kx_grid.ravel(), kz_grid.ravel()):
+            args = copy.deepcopy(self.baseargs)
+            args['__init__']['max_zoom_domains'] = 1
+            args['calculate']['wave_number_x'] = kx
+            args['calculate']['wave_number_z'] = kz
+            arglist.append(args)
+        results = self._run(arglist)
+        self.grids.append({'Kx': kx_grid, 'Kz': kz_grid, 'runs': runs, 'results': results,
+                           'nguess': np.zeros(kx_grid.shape, dtype=int)})
+        self._sweep_until_quiet()
+
+    def fill_in_grid(self):
+        old = self.grids[-1]
+        kx_grid = spreadgrid(old['Kx'], const_axis=0)
+        kz_grid = spreadgrid(old['Kz'], const_axis=1)
+        runs = -1*np.ones(kx_grid.shape, dtype=int)
+        runs[::2, ::2] = old['runs']
+        self.grids.append({'Kx': kx_grid, 'Kz': kz_grid, 'runs': runs,
+                           'results': copy.deepcopy(old['results']),
+                           'nguess': np.zeros(kx_grid.shape, dtype=int)})
+        if self.root:
+            print(' running grid sweeps')
+        self._sweep_until_quiet()
+
+    def sweep_last_grid(self):
+        """Re-run every root-less pixel that has gained neighbour roots; returns #new roots."""
+        grid = self.grids[-1]
+        kx_grid, kz_grid = grid['Kx'], grid['Kz']
+        runs, nguess, results = grid['runs'], grid['nguess'], grid['results']
+        offset = max(results)
+        nz, nx = kz_grid.shape
+        for key in runs.ravel():
+            get_if(results, key)                      # validity of the mapping
+
+        arglist = []
+        bump = np.zeros_like(runs)
+        for iz in range(nz):
+            for ix in range(nx):
+                if len(get_if(results, runs[iz, ix])) > 0:
+                    continue                          # never re-run a pixel that has roots
+                near = []
+                for diz, dix in _NEIGHBOURS:
+                    jz, jx = iz + diz, ix + dix
+                    if 0 <= jz < nz and 0 <= jx < nx:
+                        near += get_if(results, runs[jz, jx])
+                if len(near) > 0:
+                    near = prune_eps(near, epsilon=np.array(near).imag.mean()*1e-4)
+                if len(near) > nguess[iz, ix]:        # only when more guesses than last time
+                    nguess[iz, ix] = len(near)
+                    args = copy.deepcopy(self.baseargs)
+                    args['__init__']['max_zoom_domains'] = 0
+                    args['calculate']['wave_number_x'] = kx_grid[iz, ix]
+                    args['calculate']['wave_number_z'] = kz_grid[iz, ix]
+                    args['calculate']['guess_roots'] = near
+                    first = len(arglist)
+                    bump[iz, ix] = offset + first - runs[iz, ix]
+                    arglist.append(args)
+                    for _ in range(self.reruns):
+                        args = copy.deepcopy(args)
+                        args['random_seed'] += 1
+                        args['is_rerun'] = first      # its roots are appended to the first run's
+                        arglist.append(args)
+        if self.root:
+            print('Will run ', len(arglist), ' new points')
+
+        newroots = 0
+        if arglist:
+            fresh = self._run(arglist)
+            for irun in sorted(fresh):
+                if 'is_rerun' in arglist[irun]:
+                    key = offset + arglist[irun]['is_rerun']
+                    if len(results[key]) == 0 and len(fresh[irun]) > 0 and self.root:
+                        print('combined ', results[key], fresh[irun])
+                    results[key] = np.append(results[key], fresh[irun])
+                else:
+                    results[offset + irun] = fresh[irun]
+                newroots += len(fresh[irun])
+            runs += bump
+            for key in runs.ravel():
+                get_if(results, key)
+            grid['runs'], grid['results'] = runs, results
+        self.sweep_log.append((len(self.grids) - 1, len(arglist), newroots))
+        return newroots
+
+    # -- output ("next" row: HDF5 writer, reference psi_grid_refine.py:336-386) -----------------
+    def grid_arrays(self, grid):
+        """Dense arrays of one grid: Kxgrid, Kzgrid, root_real, root_imag (depth = largest root
+        multiplicity) and error (= number of roots per pixel)."""
+        depth = max([1] + [len(grid['results'][r]) for r in grid['runs'].ravel() if r >= 0])
+        shape = list(grid['runs'].shape) + [depth]
+        re, im = np.zeros(shape), np.zeros(shape)
+        err = -1*np.ones_like(grid['runs'], dtype=int)
+        for (iz, ix), _ in np.ndenumerate(grid['Kz']):
+            roots = get_if(grid['results'], grid['runs'][iz, ix])
+            err[iz, ix] = len(roots)
+            for k, r in enumerate(roots):
+                re[iz, ix, k], im[iz, ix, k] = r.real, r.imag
+        return {'Kxgrid': np.array(grid['Kx']), 'Kzgrid': np.array(grid['Kz']),
+                'root_real': re, 'root_imag': im, 'error': err}
+
+    def to_hdf5(self):
+        """Write all grids to ``batchname.hdf5`` (groups batchname/<igrid> with the datasets of
+        grid_arrays and the run attributes).  Without h5py the same arrays go to ``batchname.npz``
+        under the keys '<igrid>/<dataset>'."""
+        if not self.root:
+            return None
+        print('Writing ', len(self.grids), 'grids to hdf5')
+        init = self.baseargs['__init__']
+        try:
+            import h5py
+        except ImportError:
+            flat = {}
+            for i, g in enumerate(self.grids):
+                for name, arr in self.grid_arrays(g).items():
+                    flat['%d/%s' % (i, name)] = arr
+            path = self.batchname + '.npz'
+            np.savez(path, run_walltime=time.time() - self.wall_start, **flat)
+            return path
+        with h5py.File(self.datafile_hdf5, 'w') as h5f:
+            top = h5f.create_group(self.batchname)
+            top.attrs['run_walltime'] = time.time() - self.wall_start
+            for i, g in enumerate(self.grids):
+                grp = h5f.create_group(self.batchname + '/' + str(i))
+                grp.attrs['stokes_range'] = init['stokes_range']
+                grp.attrs['dust_to_gas_ratio'] = init['dust_to_gas_ratio']
+                if 'viscous_alpha' in self.baseargs['calculate']:
+                    grp.attrs['viscous_alpha'] = self.baseargs['calculate']['viscous_alpha']
+                grp.attrs['real_range'] = init['real_range']
+                grp.attrs['imag_range'] = init['imag_range']
+                for name, arr in self.grid_arrays(g).items():
+                    grp.create_dataset(name, data=arr)
+        return self.datafile_hdf5

@@ -1,0 +1,279 @@
+"""PSIMode -- drop-in for psitools.psi_mode.PSIMode (reference psi_mode.py:40-491).
+
+The root search (random samples -> AAA rational approximation -> zeros -> zoom domains -> secant
+polish on the exact dispersion relation) is written once as the generator ``mode_machine``: it
+yields batches of frequencies and receives D there.  ``PSIMode.calculate`` drives one machine;
+``solve_modes`` drives thousands of them in lock-step (one K1 launch per pass, see _engine.py), which
+is what ``MpiScheduler.run`` and ``PSIGridRefiner`` use for maps.
+
+Out of scope: find_minimum (unused), plot_dispersion (matplotlib).
+"""
+import numpy as np
+
+from . import complex_roots as cr
+from . import psi_dispersion as psid
+from ._engine import Job, run_lockstep
+
+
+def guess_domain_size(x):
+    """Size of the zoom box put around a guessed root (may be used from other modules)."""
+    return min((1e-3, np.abs(x.imag)*4))
+
+
+class ModeSettings:
+    """The PSIMode constructor knobs that steer the search."""
+
+    def __init__(self, real_range, imag_range, n_sample=20, max_zoom_domains=1, tol=1.0e-13,
+                 clean_tol=1.0e-4, max_secant_iterations=100):
+        self.domain = cr.Rectangle(real_range, imag_range)
+        self.n_sample = n_sample
+        self.max_zoom_level = max_zoom_domains
+        self.max_zoom_domains_per_level = 4
+        self.max_secant_iterations = max_secant_iterations
+        self.minimum_interpolation_nodes = 4
+        self.force_at_least_one_root = True
+        self.tol = tol
+        self.clean_tol = clean_tol
+
+
+class ModeTrace:
+    """What PSIMode exposes after a call: counters, samples and the rational approximation."""
+
+    def __init__(self):
+        self.n_function_call = 0
+        self.max_convergence_iterations = 0
+        self.z_sample = None
+        self.f_sample = None
+        self.ra = None
+        self.n_roots = None
+
+
+def _boxed_centre(dom, centre, size):
+    """Shift a zoom box centre so that the whole box lies inside the search domain."""
+    re, im = np.real(centre), np.imag(centre)
+    if re < dom.xmin + 0.5*size[0]:
+        re = dom.xmin + 0.5*size[0]
+    if re > dom.xmax - 0.5*size[0]:
+        re = dom.xmax - 0.5*size[0]
+    if im < dom.ymin + 0.5*size[1]:
+        im = dom.ymin + 0.5*size[1]
+    if im > dom.ymax - 0.5*size[1]:
+        im = dom.ymax - 0.5*size[1]
+    return re + 1j*im
+
+
+def mode_machine(cfg, guess_roots=(), count_roots=False, rng=None, trace=None, log=None):
+    """Generator implementing PSIMode.calculate for one (Kx, Kz, alpha).
+
+    Yields arrays of complex frequencies, receives the dispersion relation there, returns the
+    array of roots inside the search rectangle (reference psi_mode.py:106-333).  ``rng`` supplies
+    ``uniform`` (numpy's global legacy state by default, a per-item RandomState in batched runs).
+    """
+    trace = ModeTrace() if trace is None else trace
+    say = (lambda *a: None) if log is None else log
+    dom = cfg.domain
+    ra = cr.RationalApproximation(dom, tol=cfg.tol, clean_tol=cfg.clean_tol)
+    trace.ra = ra
+
+    zs = dom.generate_random_sample_points(cfg.n_sample, rng)
+    fs = yield zs
+    trace.n_function_call = cfg.n_sample
+
+    if count_roots:
+        st = {}
+        trace.n_roots = yield from cr.contour_machine(dom.corners(), state=st)
+        say('Number of roots: {}'.format(trace.n_roots))
+        zs = np.concatenate((zs, st["points"]))
+        fs = np.concatenate((fs, st["f_points"]))
+
+    def extra_domain(zs, fs, size, centre):
+        centre = _boxed_centre(dom, centre, size)
+        say('Adding zoom domain around {}'.format(centre))
+        box = cr.Rectangle([centre.real - 0.5*size[0], centre.real + 0.5*size[0]],
+                           [centre.imag - 0.5*size[1], centre.imag + 0.5*size[1]])
+        zn = box.generate_random_sample_points(cfg.n_sample, rng)
+        fn = yield zn
+        trace.n_function_call += cfg.n_sample
+        return np.concatenate((zs, zn)), np.concatenate((fs, fn))
+
+    for centre in guess_roots:
+        side = guess_domain_size(centre)
+        zs, fs = yield from extra_domain(zs, fs, [side, side], centre)
+
+    roots = np.zeros(0, dtype=complex)
+    for level in range(0, cfg.max_zoom_level + 1):
+        trace.z_sample, trace.f_sample = zs, fs
+        ra.calculate(fs, zs)
+        zeros = ra.find_zeros()
+        zeros = zeros[np.asarray(dom.is_in(zeros)).nonzero()]
+
+        # too few support points or no growing zero: halve clean_tol and redo (down to tol)
+        need = cfg.minimum_interpolation_nodes*(1 + level + len(guess_roots))
+        saved = ra.clean_tol
+        while (np.sum(ra.maskF) < need or
+               (not np.any(np.imag(zeros) > 0.0) and cfg.force_at_least_one_root)):
+            ra.clean_tol = 0.5*ra.clean_tol
+            if ra.clean_tol < ra.tol:
+                break
+            say('Reducing clean_tol to {}'.format(ra.clean_tol))
+            ra.calculate(fs, zs)
+            zeros = ra.find_zeros()
+            zeros = zeros[np.asarray(dom.is_in(zeros)).nonzero()]
+        ra.clean_tol = saved
+        say('Number of nodes used: {}'.format(np.sum(ra.maskF)))
+
+        zeros = ra.find_zeros()
+        say('All zeros: {}'.format(zeros))
+        # zoom candidates: anything below the top of the box and inside in Re (may be damped)
+        cand = zeros[np.asarray((zeros.imag < dom.ymax) & (zeros.real < dom.xmax) &
+                                (zeros.real > dom.xmin)).nonzero()]
+        box_dx = np.power(10.0, -1 - 0.5*level)
+        if len(cand) > 0:
+            cand = cand[np.argsort(cand.imag)]
+            zoom = [cand[-1]]
+            for z in cand[-2::-1]:
+                if not any(np.abs(z.real - q.real) < box_dx for q in zoom):
+                    zoom.append(z)
+            zoom = zoom[:cfg.max_zoom_domains_per_level]
+            least_damped = zoom[0]
+        else:
+            zoom, least_damped = [], None
+
+        zeros = np.asarray(zeros[np.asarray(dom.is_in(zeros)).nonzero()])
+        say('All zeros in domain: {}'.format(zeros))
+        max_iter = cfg.max_secant_iterations
+        if level < cfg.max_zoom_level:
+            max_iter = cfg.n_sample
+        if len(zeros) == 0 and least_damped is not None:
+            zeros = np.asarray([least_damped])
+            max_iter = 5
+
+        roots = yield from polish_machine(cfg, zeros, max_iter, trace, say)
+        if np.any(roots.imag > 0.0) or level == cfg.max_zoom_level or len(zoom) == 0:
+            return roots
+        for centre in zoom:
+            zs, fs = yield from extra_domain(zs, fs, [box_dx, np.min([0.1, np.abs(centre.imag)])],
+                                             centre)
+    return roots
+
+
+def polish_machine(cfg, starts, max_iter, trace, say=lambda *a: None, initial_iterations=5,
+                   select_inside_domain=True):
+    """Secant polish of every start value on the exact dispersion relation, one after the other
+    (reference psi_mode.py:340-352, 411-491): five iterations first; if that has not converged but
+    stayed within |start| of the start, continue from there for up to ``max_iter``.  Failed or
+    outside-domain results are dropped.  The step tolerance min(1.48e-8, 1e-5*min|Im start|) looks
+    at ALL current start values, including restart points of earlier ones."""
+    w0 = np.atleast_1d(np.asarray(starts, dtype=complex)).ravel().copy()
+    out = np.zeros(len(w0), dtype=complex)
+    eps = 1.0e-6
+    for i in range(len(w0)):
+        say('Starting iteration at z = {}'.format(w0[i]))
+        xtol = np.min(np.hstack([[1.48e-8], np.abs(w0.imag*1e-5)]))
+        res = yield from cr.secant_machine(w0[i], cr.second_point(w0[i], eps), initial_iterations, xtol)
+        trace.n_function_call += res.function_calls
+        if (not res.converged and np.abs(res.root - w0[i])/np.abs(w0[i]) < 1
+                and max_iter > initial_iterations):
+            say("Starting further iteration")
+            w0[i] = res.root
+            xtol = np.min(np.hstack([[1.48e-8], np.abs(w0.imag*1e-5)]))
+            res = yield from cr.secant_machine(w0[i], cr.second_point(w0[i], eps), max_iter, xtol)
+            trace.n_function_call += res.function_calls
+        elif not res.converged:
+            say("Secant is running away; no further iterations")
+        inside = bool(cfg.domain.is_in(res.root)) or not select_inside_domain
+        if res.converged and inside:
+            trace.max_convergence_iterations = max(trace.max_convergence_iterations, res.iterations)
+            out[i] = res.root
+        else:
+            out[i] = -1j                      # sentinel, outside every search rectangle
+    return out[np.asarray(cfg.domain.is_in(out)).nonzero()]
+
+
+class PSIMode:
+    """Calculates PSI modes (complex frequencies of the polydisperse streaming instability).
+
+    Args: as psitools.psi_mode.PSIMode -- dust_to_gas_ratio, stokes_range, real_range, imag_range,
+    sound_speed_over_eta=1/0.05, size_distribution_power=3.5, single_size_flag=False, n_sample=20,
+    max_zoom_domains=1, verbose_flag=False, size_density=None, tol=1e-13, clean_tol=1e-4,
+    max_secant_iterations=100, tanhsinh_integrator=None.
+    """
+
+    def __init__(self, dust_to_gas_ratio, stokes_range, real_range, imag_range,
+                 sound_speed_over_eta=1/0.05, size_distribution_power=3.5, single_size_flag=False,
+                 n_sample=20, max_zoom_domains=1, verbose_flag=False, size_density=None,
+                 tol=1.0e-13, clean_tol=1.0e-4, max_secant_iterations=100,
+                 tanhsinh_integrator=None, device=None):
+        self.psi_dispersion = psid.PSIDispersion(dust_to_gas_ratio, stokes_range, sound_speed_over_eta,
+                                                 size_distribution_power, single_size_flag,
+                                                 size_density, tanhsinh_integrator, device=device)
+        self.dispersion = self.psi_dispersion.calculate
+        self.cfg = ModeSettings(real_range, imag_range, n_sample, max_zoom_domains, tol, clean_tol,
+                                max_secant_iterations)
+        self.domain = self.cfg.domain
+        self.n_sample = n_sample
+        self.max_zoom_level = max_zoom_domains
+        self.max_zoom_domains_per_level = self.cfg.max_zoom_domains_per_level
+        self.max_secant_iterations = max_secant_iterations
+        self.verbose_flag = verbose_flag
+        self.max_convergence_iterations = 0
+        self.minimum_interpolation_nodes = self.cfg.minimum_interpolation_nodes
+        self.force_at_least_one_root = True
+        self.n_function_call = 0
+        self.guess_domain_size = guess_domain_size
+        self.ra = cr.RationalApproximation(self.domain, tol=tol, clean_tol=clean_tol)
+
+    def log_print(self, arg):
+        if self.verbose_flag:
+            print(arg)
+
+    def _sync_cfg(self):
+        c = self.cfg
+        c.n_sample, c.max_zoom_level = self.n_sample, self.max_zoom_level
+        c.max_zoom_domains_per_level = self.max_zoom_domains_per_level
+        c.max_secant_iterations = self.max_secant_iterations
+        c.minimum_interpolation_nodes = self.minimum_interpolation_nodes
+        c.force_at_least_one_root = self.force_at_least_one_root
+        c.tol, c.clean_tol = self.ra.tol, self.ra.clean_tol
+
+    def make_job(self, wave_number_x, wave_number_z, viscous_alpha=0, guess_roots=(),
+                 count_roots=False, rng=None, trace=None):
+        """A lock-step job for this mode search (used by the batched drivers)."""
+        self._sync_cfg()
+        mach = mode_machine(self.cfg, guess_roots, count_roots, rng, trace,
+                            self.log_print if self.verbose_flag else None)
+        return Job(mach, self.psi_dispersion.dist_id, wave_number_x, wave_number_z, viscous_alpha)
+
+    def calculate(self, wave_number_x, wave_number_z, viscous_alpha=0, guess_roots=[],
+                  count_roots=False):
+        """Complex mode frequencies at (Kx, Kz) and viscosity parameter viscous_alpha."""
+        self.disp = lambda z: self.dispersion(z, wave_number_x, wave_number_z, viscous_alpha)
+        trace = ModeTrace()
+        job = self.make_job(wave_number_x, wave_number_z, viscous_alpha, guess_roots, count_roots,
+                            None, trace)
+        try:
+            run_lockstep(self.psi_dispersion.ctx, [job])
+        except Exception:
+            print(('Root search failed at Kx = {}, Kz = {}, alpha = {}, guess_roots = {}')
+                  .format(wave_number_x, wave_number_z, viscous_alpha, guess_roots))
+            raise
+        finally:
+            self.n_function_call = trace.n_function_call
+            self.max_convergence_iterations = max(self.max_convergence_iterations,
+                                                  trace.max_convergence_iterations)
+            self.z_sample, self.f_sample = trace.z_sample, trace.f_sample
+            if trace.ra is not None:
+                self.ra = trace.ra
+            if trace.n_roots is not None:
+                self.n_roots = trace.n_roots
+        return job.result
+
+    def find_dispersion_roots(self, zeros, max_iter):
+        trace = ModeTrace()
+        self._sync_cfg()
+        job = Job(polish_machine(self.cfg, zeros, max_iter, trace), self.psi_dispersion.dist_id,
+                  self.psi_dispersion.kx, self.psi_dispersion.kz,
+                  self.psi_dispersion.nu/self.psi_dispersion.c**2)
+        run_lockstep(self.psi_dispersion.ctx, [job])
+        self.n_function_call += trace.n_function_call
+        return job.result

@@ -1,0 +1,126 @@
+"""Batch drivers with the interface of psitools.psi_mode_mpi (reference psi_mode_mpi.py:33-192).
+
+``MpiScheduler(wall_start, wall_limit_total, verbose).run(arglist)`` keeps its meaning -- a list of
+arg-dicts {'__init__': PSIMode kwargs, 'calculate': PSIMode.calculate kwargs, 'random_seed': int}
+in, {index: roots} out on rank 0 (None on the other ranks) -- but instead of a master handing
+single items to MPI workers, every rank (one per GPU under torchrun) takes the items
+i = rank (mod world), advances all their root searches in lock-step on its GPU (one K1 launch per
+pass, _engine.py) and the results are exchanged with a single all-gather (_dist.py).  Work items
+re-seed their own random stream exactly like the reference's runcompute (:162-167), so results do
+not depend on the schedule.
+"""
+import time
+
+import numpy as np
+
+from . import _dist
+from ._engine import run_lockstep
+from .psi_mode import ModeTrace, PSIMode
+
+
+def _same_init(a, b):
+    try:
+        return a == b
+    except Exception:
+        return a is b
+
+
+class _ModeCache:
+    """PSIMode objects keyed by '__init__' dict equality (reference psi_mode_mpi.py:168-171)."""
+
+    def __init__(self):
+        self.entries = []
+
+    def get(self, init):
+        for known, pm in self.entries:
+            if _same_init(known, init):
+                return pm
+        pm = PSIMode(**init)
+        self.entries.append((init, pm))
+        return pm
+
+
+class MpiScheduler:
+    """Execute a set of PSIMode runs given as a list of arg-dicts."""
+
+    def __init__(self, wall_start, wall_limit_total, verbose=True):
+        self.verbose = verbose
+        self.exitFlag = False
+        self.rank = _dist.rank()
+        self.nranks = _dist.world_size()
+        self.wall_start = wall_start
+        self.wall_limit_total = wall_limit_total
+        self._cache = _ModeCache()
+        self.last_stats = {}
+
+    # -- per-item body ------------------------------------------------------------------------
+    def _job(self, args):
+        pm = self._cache.get(args['__init__'])
+        rng = np.random.RandomState(args.get('random_seed', 0))
+        trace = ModeTrace()
+        job = pm.make_job(rng=rng, trace=trace, **args['calculate'])
+        return job, trace, pm
+
+    def runcompute(self, args):
+        """One work item on its own (kept for callers that used the reference's method)."""
+        job, _, pm = self._job(args)
+        run_lockstep(pm.psi_dispersion.ctx, [job])
+        return job.result.copy()
+
+    def _encode(self, result):
+        return np.asarray(result, dtype=np.complex128).view(np.float64)
+
+    def _decode(self, rec):
+        return np.asarray(rec, dtype=np.float64).view(np.complex128).copy()
+
+    def run_all(self, arglist):
+        """Results of every item, on every rank."""
+        t0 = time.time()
+        mine = _dist.my_items(len(arglist))
+        jobs, ctx = [], None
+        for i in mine:
+            job, trace, pm = self._job(arglist[i])
+            jobs.append((i, job, trace))
+            ctx = pm.psi_dispersion.ctx
+        stats = {}
+        if jobs:
+            run_lockstep(ctx, [j for _, j, _ in jobs], stats=stats)
+        local = {i: self._encode(j.result) for i, j, _ in jobs}
+        if self.verbose:
+            for i, j, _ in jobs:
+                print(i, 'result ', j.result)
+        self.last_stats = dict(items=len(jobs), passes=stats.get("passes", 0),
+                               function_calls=sum(t.n_function_call for _, _, t in jobs),
+                               seconds=time.time() - t0)
+        merged = _dist.all_gather_records(local)
+        return {i: self._decode(merged[i]) for i in sorted(merged)}
+
+    def run(self, arglist):
+        res = self.run_all(arglist)
+        return res if self.rank == 0 else None
+
+
+class DispersionRelationMpiScheduler(MpiScheduler):
+    """Values of the dispersion relation for items {'__init__': ..., 'dispersion': {'w', 'wave_number_x',
+    'wave_number_z', 'viscous_alpha'}} (reference psi_mode_mpi.py:181-192): all items of a rank go
+    through ONE K1 launch."""
+
+    def runcompute(self, args):
+        pm = self._cache.get(args['__init__'])
+        return pm.dispersion(**args['dispersion'])
+
+    def run_all(self, arglist):
+        mine = _dist.my_items(len(arglist))
+        local = {}
+        if mine:
+            pms = [self._cache.get(arglist[i]['__init__']) for i in mine]
+            d = [arglist[i]['dispersion'] for i in mine]
+            ctx = pms[0].psi_dispersion.ctx
+            vals = ctx.disp_eval(np.array([p.psi_dispersion.dist_id for p in pms], dtype=np.int32),
+                                 np.array([float(x['wave_number_x']) for x in d]),
+                                 np.array([float(x['wave_number_z']) for x in d]),
+                                 np.array([float(x.get('viscous_alpha', 0)) for x in d]),
+                                 np.array([complex(x['w']) for x in d]))
+            local = {i: np.array([v.real, v.imag]) for i, v in zip(mine, vals)}
+        merged = _dist.all_gather_records(local)
+        return {i: np.squeeze(np.array([complex(merged[i][0], merged[i][1])])) for i in sorted(merged)}

@@ -62,3 +62,43 @@ def disp_eval(desc, integ, w, kx, kz, alpha, want_M=False):
                        C.c_double(float(integ.eps)), C.c_longlong(n), _p(kx), _p(kz), _p(al), _p(w),
                        _p(D), _p(M), C.byref(ne))
     return (D, M, ne.value) if want_M else D
+
+
+class HostsimContext:
+    """Test double with the interface of psitools_public_b200._device.Context, backed by the
+    lane-emulation harness.  Lets the CPU suite run the product's host-side state machines
+    (lock-step engine, PSIMode, contours, grid refinement) end to end without a GPU."""
+
+    def __init__(self, integ):
+        self.integ = integ
+        self.descs = []
+        self.node_evals = 0
+        self.launch_count = 0
+
+    def add_dist(self, desc):
+        for i, d in enumerate(self.descs):
+            if d.key() == desc.key():
+                return i
+        self.descs.append(desc)
+        return len(self.descs) - 1
+
+    def background(self, dist_id):
+        return background(self.descs[dist_id], self.integ)
+
+    def disp_eval(self, dist, kx, kz, alpha, w, want_M=False, out=None):
+        w = np.ascontiguousarray(np.ravel(w), dtype=np.complex128)
+        n = len(w)
+        dist = np.broadcast_to(np.asarray(dist, dtype=np.int32), (n,))
+        kx = np.broadcast_to(np.asarray(kx, dtype=float), (n,))
+        kz = np.broadcast_to(np.asarray(kz, dtype=float), (n,))
+        al = np.broadcast_to(np.asarray(alpha, dtype=float), (n,))
+        D = np.empty(n, dtype=np.complex128) if out is None else out
+        M = np.empty((n, 7), dtype=np.complex128)
+        self.launch_count += 1
+        for d in np.unique(dist):
+            sel = (dist == d).nonzero()[0]
+            Dd, Md, ne = disp_eval(self.descs[int(d)], self.integ, w[sel], kx[sel], kz[sel], al[sel], True)
+            D[sel] = Dd
+            M[sel] = Md
+            self.node_evals += ne
+        return (D, M) if want_M else D

@@ -1,0 +1,141 @@
+"""The product's PSIMode / ClosedPath / scheduler classes end to end against fixtures produced by the
+unmodified reference.  Every test runs on the CPU lane-emulation backend (conftest.hostsim_backend,
+for the GPU-less container) and, under ``-m gpu``, through the real CUDA library."""
+import numpy as np
+import pytest
+
+from common import carr, cplx, load, product_kwargs
+
+
+def mode_cases():
+    return load("mode.json")["cases"]
+
+
+@pytest.mark.parametrize("case", mode_cases(), ids=lambda c: c["name"])
+def test_psimode_reference_cases(backend, case):
+    """test_psi_mode.py:32-189: same root (rtol 1e-7 as in the reference test, in fact ~1e-9) and
+    same number of dispersion evaluations as the reference run."""
+    from psitools_public_b200 import PSIMode, TanhSinh
+    spec = load("background.json")[case["dist"]]["spec"]
+    kw = product_kwargs(spec)
+    kw.update(case["init"])
+    np.random.seed(case["seed"])
+    pm = PSIMode(tanhsinh_integrator=TanhSinh(), **kw)
+    roots = pm.calculate(wave_number_x=case["K"][0], wave_number_z=case["K"][1],
+                         viscous_alpha=case["alpha"])
+    ref = carr(case["roots"])
+    assert len(roots) == len(ref) == 1
+    assert abs(roots[0] - ref[0]) <= 1e-8*abs(ref[0])
+    pin = cplx(case["pin"])
+    np.testing.assert_allclose(roots[0].real, pin.real, rtol=1e-7)
+    np.testing.assert_allclose(roots[0].imag, pin.imag, rtol=1e-7)
+    assert pm.n_function_call == case["n_function_call"]
+    assert len(pm.z_sample) == len(case["z_sample"])
+    np.testing.assert_array_equal(pm.z_sample, carr(case["z_sample"]))   # same random stream
+
+
+def same_root_sets(got, ref, rtol=1e-8):
+    got = sorted(got, key=lambda z: (z.real, z.imag))
+    ref = sorted(ref, key=lambda z: (z.real, z.imag))
+    if len(got) != len(ref):
+        return False
+    return all(abs(a - b) <= rtol*abs(b) for a, b in zip(got, ref))
+
+
+def grid_arglist(n_axis, ts):
+    ax = np.logspace(-1, 3, n_axis)
+    kxg, kzg = np.meshgrid(ax, ax)
+    return [{'__init__': {'stokes_range': [1e-8, 1.0], 'dust_to_gas_ratio': 3.0,
+                          'size_distribution_power': 3.5, 'real_range': [-2.0, 2.0],
+                          'imag_range': [1e-8, 1.0], 'n_sample': 20, 'max_zoom_domains': 1,
+                          'tol': 1.0e-13, 'clean_tol': 1e-4, 'tanhsinh_integrator': ts},
+             'calculate': {'wave_number_x': kx, 'wave_number_z': kz}, 'random_seed': 2}
+            for kx, kz in zip(kxg.flatten(), kzg.flatten())]
+
+
+@pytest.mark.parametrize("n_axis", [3, 6])
+def test_mpischeduler_mode_grid(backend, n_axis):
+    """test_psi_mode_mpi.py:38-104 (3x3) and a 6x6 grid of the same family: root sets per pixel
+    equal to the reference's (count exact, values to 1e-8 |omega|)."""
+    import time
+    from psitools_public_b200 import TanhSinhNoDeepCopy, psi_mode_mpi
+    g = load("modegrid.json")["grid%d" % n_axis]
+    ms = psi_mode_mpi.MpiScheduler(time.time(), 3600, verbose=False)
+    res = ms.run(grid_arglist(n_axis, TanhSinhNoDeepCopy()))
+    assert sorted(res) == list(range(n_axis*n_axis))
+    for i, case in enumerate(g["cases"]):
+        assert same_root_sets(list(res[i]), list(carr(case["roots"]))), (i, res[i], case["roots"])
+    if n_axis == 3:                              # goldens pasted in the reference test
+        np.testing.assert_allclose(res[3].real, [-1.00487970465063e+00], rtol=1e-7)
+        np.testing.assert_allclose(res[3].imag, [+8.94632567125043e-04], rtol=1e-7)
+        np.testing.assert_allclose(res[6].real, [-1.00492431244162e+00], rtol=1e-7)
+        np.testing.assert_allclose(res[6].imag, [+9.03855503901244e-04], rtol=1e-7)
+    assert ms.last_stats["items"] == n_axis*n_axis and ms.last_stats["passes"] > 0
+
+
+def test_dispersion_scheduler(backend):
+    """test_psi_mode_mpi.py:108-171."""
+    import time
+    from psitools_public_b200 import psi_mode_mpi
+    items = [{'__init__': {'stokes_range': [1e-8, 1.0], 'dust_to_gas_ratio': 3.0,
+                           'real_range': [-2.0, 2.0], 'imag_range': [-2.0, 2.0]},
+              'dispersion': {'w': re + 1j*im, 'wave_number_x': 1e2, 'wave_number_z': 1e1,
+                             'viscous_alpha': 0.0}}
+             for im in (-2.0, 2.0) for re in (-2.0, 2.0)]
+    res = psi_mode_mpi.DispersionRelationMpiScheduler(time.time(), 3600, verbose=False).run(items)
+    np.testing.assert_allclose(res[0].real, -1.72733464670814e+08, rtol=1e-7)
+    np.testing.assert_allclose(res[0].imag, +5.32484293672187e+07, rtol=1e-7)
+    np.testing.assert_allclose(res[3].real, -8.18797751107521e+07, rtol=1e-7)
+    np.testing.assert_allclose(res[3].imag, +8.84518043425989e+07, rtol=1e-7)
+    assert res[1].shape == ()
+
+
+def count_arglist(ts):
+    z_list = [-2.0 + 2e-7j, 2.0 + 2e-7j, 2.0 + 2.0j, -2.0 + 2.0j]
+    ax = np.logspace(-1, 3, 3)
+    kxg, kzg = np.meshgrid(ax, ax)
+    return [{'PSIDispersion.__init__': {'stokes_range': [1e-8, 1.0], 'dust_to_gas_ratio': 3.0,
+                                        'size_distribution_power': 3.5, 'tanhsinh_integrator': ts},
+             'dispersion': {'wave_number_x': kx, 'wave_number_z': kz, 'viscous_alpha': 0.0},
+             'z_list': z_list, 'count_roots': {'tol': 0.1}}
+            for kx, kz in zip(kxg.flatten(), kzg.flatten())]
+
+
+def test_root_count_map(backend):
+    """test_complex_roots_mpi.py:32-102: counts [0,0,0,1,0,0,1,0,0] exactly."""
+    import time
+    from psitools_public_b200 import TanhSinhNoDeepCopy, complex_roots_mpi
+    res = complex_roots_mpi.MpiScheduler(time.time(), 3600, verbose=False).run(
+        count_arglist(TanhSinhNoDeepCopy()))
+    assert [res[i] for i in range(9)] == [0, 0, 0, 1, 0, 0, 1, 0, 0]
+    gold = load("contour.json")["cases"]
+    assert [c["count"] for c in gold] == [res[i] for i in range(9)]
+
+
+def test_closedpath_dropin(backend):
+    """ClosedPath driven by an arbitrary callable: same refinement history as the reference
+    (number of points added per pass) on the contour with one root."""
+    from psitools_public_b200 import ClosedPath, PSIDispersion, TanhSinh
+    gold = load("contour.json")["cases"][3]
+    pd = PSIDispersion(3.0, [1e-8, 1.0], tanhsinh_integrator=TanhSinh())
+    cp = ClosedPath(lambda z: pd.calculate(z, gold["kx"], gold["kz"]),
+                    [-2.0 + 2e-7j, 2.0 + 2e-7j, 2.0 + 2.0j, -2.0 + 2.0j])
+    assert cp.count_roots(tol=0.1) == gold["count"] == 1
+    assert cp.success
+    # the refinement is driven by arg(D) jumps > 0.1: the point count follows the reference closely
+    assert abs(len(cp.points) - gold["n_points"]) <= 0.05*gold["n_points"]
+    with pytest.raises(RuntimeError):
+        ClosedPath(lambda z: pd.calculate(z, gold["kx"], gold["kz"]),
+                   [-2.0 + 2e-7j, 2.0 + 2e-7j, 2.0 + 2.0j, -2.0 + 2.0j]).count_roots(max_iter=3)
+
+
+def test_mode_with_count_and_guess(backend):
+    """count_roots=True joins the contour points to the samples (psi_mode.py:127-138); a guessed
+    root adds a zoom domain (psi_mode.py:141-145)."""
+    from psitools_public_b200 import PSIMode, TanhSinh
+    np.random.seed(0)
+    pm = PSIMode(3.0, [1e-8, 1.0], [-2, 2], [1e-8, 1], tanhsinh_integrator=TanhSinh())
+    roots = pm.calculate(0.1, 10.0, guess_roots=[-1.0048797 + 8.9463e-4j])
+    assert len(roots) >= 1
+    assert min(abs(r - (-1.004879704650626 + 0.0008946325671658642j)) for r in roots) < 1e-9
+    assert pm.n_function_call >= 40
