@@ -114,6 +114,48 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------
+# secondary workload: BASELINE config 3, (Kx,Kz) modes solved per second
+# ---------------------------------------------------------------------------------------------
+MODE_INIT = dict(stokes_range=[1e-8, 1.0], dust_to_gas_ratio=3.0, size_distribution_power=3.5,
+                 real_range=[-2.0, 2.0], imag_range=[1e-8, 1.0], n_sample=20, max_zoom_domains=1,
+                 tol=1.0e-13, clean_tol=1e-4)
+
+
+def mode_grid(n_axis, rank=0, world=1):
+    """Kx, Kz of the n_axis^2 log-spaced map of test_psi_mode_mpi.py:51-53; rank r owns the pixels
+    i = r (mod world) of the flattened map."""
+    ax = np.logspace(-1, 3, n_axis)
+    kxg, kzg = np.meshgrid(ax, ax)
+    return kxg.ravel()[rank::world], kzg.ravel()[rank::world]
+
+
+def _cpu_mode_worker(k):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import psi_oracle as po
+    item = {'__init__': dict(MODE_INIT), 'calculate': {'wave_number_x': k[0], 'wave_number_z': k[1]},
+            'random_seed': 2}
+    tab = _cpu_mode_worker.cache.setdefault("t", po.NodeTable())
+    return len(po.run_mode_item(item, tab))
+
+
+_cpu_mode_worker.cache = {}
+
+
+def cpu_mode_rate(n_axis, cores):
+    """modes/s of the oracle port of PSIMode.calculate on `cores` processes over a strided subset of
+    the map (2 pixels per core)."""
+    import multiprocessing as mp
+    kx, kz = mode_grid(n_axis)
+    want = min(len(kx), 2*cores)
+    idx = np.linspace(0, len(kx) - 1, want).astype(int)
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        pool.map(_cpu_mode_worker, [(float(kx[i]), float(kz[i])) for i in idx], chunksize=1)
+        dt = time.perf_counter() - t0
+    return want/dt, dt, want
+
+
 def workload_config(n_gpus):
     return {"workload": "config2: D(omega) on a 1024x1024 complex-omega grid at fixed (Kx,Kz)=(50,100), "
                         "MRN mu=3 tau in [1e-8,0.1], TanhSinh(15,12)",
@@ -280,12 +322,46 @@ def run_b200(args):
     assert np.array_equal(got, D_resident), "resident and end-to-end results differ"
     assert np.all(np.isfinite(got))
 
-    t = torch.tensor([ms_total, ms_kernel, e2e_s], dtype=torch.float64, device=dev)
+    # ---- secondary: PSIMode growth-rate map (BASELINE config 3), native lock-step engine ----
+    modes = None
+    if args.modes_grid > 0:
+        from psitools_public_b200 import psi_mode_mpi
+        from psitools_public_b200.tanhsinh import TanhSinhNoDeepCopy
+        ts2 = TanhSinhNoDeepCopy()
+        init = dict(MODE_INIT, tanhsinh_integrator=ts2)
+
+        def arglist(n_axis):
+            ax = np.logspace(-1, 3, n_axis)
+            kxg, kzg = np.meshgrid(ax, ax)
+            return [{'__init__': init, 'calculate': {'wave_number_x': float(a), 'wave_number_z': float(b)},
+                     'random_seed': 2} for a, b in zip(kxg.ravel(), kzg.ravel())]
+
+        ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False)
+        ms.run_all(arglist(min(32, args.modes_grid)))            # warm-up (LAPACK binding, staging buffers)
+        items = arglist(args.modes_grid)
+        barrier()
+        l0 = ctx.launch_count
+        t0 = time.perf_counter()
+        res = ms.run_all(items)                                   # the call a user makes; all ranks share the map
+        barrier()
+        m_s = time.perf_counter() - t0
+        st = ms.last_stats
+        modes = {"metric": "(Kx,Kz) modes solved/s", "unit": "modes/s", "seconds": m_s,
+                 "workload": "config3: PSIMode on a %dx%d logspace(-1,3) (Kx,Kz) map, MRN mu=3 tau in "
+                             "[1e-8,1], n_sample 20, max_zoom 1, seed 2; pixels interleaved over ranks, "
+                             "one all-gather of the roots" % (args.modes_grid, args.modes_grid),
+                 "pixels": len(items), "pixels_with_roots": int(sum(len(v) > 0 for v in res.values())),
+                 "rank0_passes": st.get("passes"), "rank0_D_evals": st.get("evals"),
+                 "rank0_engine_seconds": st.get("seconds"), "rank0_launches": ctx.launch_count - l0,
+                 "engine": st.get("engine")}
+
+    t = torch.tensor([ms_total, ms_kernel, e2e_s, modes["seconds"] if modes else 0.0],
+                     dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(node_evals), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total, ms_kernel, e2e_s = [float(x) for x in t.tolist()]
+    ms_total, ms_kernel, e2e_s, modes_s = [float(x) for x in t.tolist()]
     node_evals_all, launches_all = [float(x) for x in cnt.tolist()]
 
     if rank == 0:
@@ -305,6 +381,13 @@ def run_b200(args):
             rate, dt = cpu_sample_rate(n_cpu, cores)
             cpu = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                    "sample": "%d random points of the 1024^2 omega grid (%.1f s)" % (n_cpu, dt)}
+        if modes:
+            modes["seconds"] = modes_s
+            modes["value"] = modes["pixels"]/modes_s
+            if cpu is not None:
+                rate, dt, npx = cpu_mode_rate(args.modes_grid, cores)
+                modes["cpu_baseline"] = {"value": rate, "unit": "modes/s", "cores": cores, "kind": "port",
+                                         "sample": "%d pixels strided over the map (%.1f s)" % (npx, dt)}
         line = {"metric": "D(omega) evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total/args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -312,7 +395,7 @@ def run_b200(args):
                 "e2e": {"value": total_evals/e2e_s, "unit": "evals/s",
                         "h2d_bytes_per_step": 16*n + 28, "d2h_bytes_per_step": 16*n + 8},
                 "gpu_launches": int(launches_all), "roofline": roof, "cpu_baseline": cpu,
-                "clocks": clocks}
+                "clocks": clocks, "modes": modes}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -325,6 +408,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--modes-grid", type=int, default=256,
+                    help="axis length of the secondary PSIMode map (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -91,6 +91,38 @@ int psi_disp_eval_dev(psi_ctx* ctx, long long n, int broadcast, const int* dist,
 /* Work class (0..7) of a point of distribution `dist` at viscosity parameter alpha. */
 int psi_point_class(psi_ctx* ctx, int dist, double alpha);
 
+/* ---- native lock-step engine (csrc/psi_engine.cu): whole batches of root searches / contour counts,
+ * one K1 launch per pass over the union of all points the items need.  Host pointers throughout. ---- */
+
+/* Bind LAPACK (zgesdd for the AAA Loewner SVD, zggev for the arrowhead pencils) from the OpenBLAS
+ * shared objects that numpy (ILP64, symbol scipy_zgesdd_64_) and scipy (LP64, scipy_zggev_) load, so
+ * that the engine reproduces numpy.linalg.svd / scipy.linalg.eig of the same interpreter. */
+int psi_engine_bind_lapack(const char* numpy_openblas64, const char* scipy_openblas32);
+
+/* n_items PSIMode.calculate searches (psi_mode.py:106-333) in lock-step.
+ *   dist, kx, kz, alpha : per item (PSIMode(...).dispersion of the item, wave numbers, viscous_alpha)
+ *   domain   : 4 doubles per item {real_range[0], real_range[1], imag_range[0], imag_range[1]}
+ *   iparams  : 3 ints per item {n_sample, max_zoom_domains, max_secant_iterations}
+ *   dparams  : 2 doubles per item {tol, clean_tol}
+ *   seeds    : per item random_seed (numpy legacy MT19937 stream, psi_mode_mpi.py:164-167)
+ *   guess_off: n_items+1 offsets into guesses (interleaved complex) = guess_roots of each item
+ *   roots    : max_roots complex slots per item; n_roots = roots found (may exceed max_roots ->
+ *              status 2, truncated); n_calls = PSIMode.n_function_call; status 0 ok / 1 failed
+ *   stats    : 5 values {passes, D evaluations, failed items, host-logic us, K1+copies us} (optional) */
+int psi_mode_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
+                        const double* alpha, const double* domain, const int* iparams, const double* dparams,
+                        const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,
+                        double* roots, int* n_roots, int* n_calls, int* status, long long* stats);
+
+/* n_items ClosedPath(...).count_roots(max_iter, tol, max_step) (complex_roots.py:517-625) in lock-step.
+ *   z_off: n_items+1 offsets into z_list (interleaved complex contour corners, counter-clockwise)
+ *   counts: winding number, or -666 when it did not converge (complex_roots_mpi.py:171-174)
+ *   status: 0 ok, 1 RuntimeError (no integer / max_iter exceeded), 2 ValueError (non-finite f) */
+int psi_contour_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
+                           const double* alpha, const int* z_off, const double* z_list, const double* tol,
+                           const double* max_step, const int* max_iter, int* counts, int* status,
+                           int* n_points, long long* stats);
+
 /* FP64 FMA-pipe peak of the device (roofline denominator; MEASURED_PEAKS.json has no FP64 entry):
  * runs a register-resident DFMA chain kernel `reps` times and returns the best TFLOP/s. */
 int psi_measure_fp64_peak(psi_ctx* ctx, int reps, double* tflops);

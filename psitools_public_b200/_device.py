@@ -59,6 +59,9 @@ _SIGNATURES = {
                                     _vp, C.c_uint, _vp]),
     "psi_point_class": (C.c_int, [_vp, C.c_int, C.c_double]),
     "psi_measure_fp64_peak": (C.c_int, [_vp, C.c_int, _dp]),
+    "psi_engine_bind_lapack": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "psi_mode_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*10 + [C.c_int] + [_vp]*5),
+    "psi_contour_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*13),
 }
 
 
@@ -101,7 +104,110 @@ def _ptr(a):
     return a.ctypes.data_as(_vp)
 
 
-class Context:
+def openblas_paths():
+    """The OpenBLAS shared objects numpy (ILP64) and scipy (LP64) ship and load themselves."""
+    import glob
+    import numpy
+    import scipy
+    out = []
+    for mod, pat in ((numpy, "libscipy_openblas64_*.so"), (scipy, "libscipy_openblas-*.so")):
+        base = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(mod.__file__))),
+                            mod.__name__ + ".libs")
+        hits = sorted(glob.glob(os.path.join(base, pat)))
+        if not hits:
+            raise PsiError("OpenBLAS library %s not found under %s" % (pat, base))
+        out.append(hits[0])
+    return out
+
+
+class EngineAPI:
+    """Python face of the native lock-step engine (csrc/psi_engine.cu); mixed into Context.  Needs
+    ``self.lib`` (a CDLL exporting the psi_* engine entry points) and ``self.handle``."""
+
+    _lapack_bound = False
+
+    def _bind_lapack(self):
+        if not self._lapack_bound:
+            a, b = openblas_paths()
+            fn = self.lib.psi_engine_bind_lapack
+            fn.restype, fn.argtypes = C.c_int, [C.c_char_p, C.c_char_p]
+            self._check(fn(a.encode(), b.encode()), "psi_engine_bind_lapack")
+            type(self)._lapack_bound = True
+
+    def _check(self, rc, what):
+        return check(rc, what)
+
+    def mode_batch(self, dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
+                   seeds, guesses, max_roots=8):
+        """Run len(dist) PSIMode.calculate searches in lock-step.  Per-item arrays; ``guesses`` is a
+        list of complex sequences.  Returns (list of root arrays, n_function_call array, stats)."""
+        self._bind_lapack()
+        n = len(dist)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        dist, kx, kz, alpha = i32(dist), f64(kx), f64(kz), f64(alpha)
+        domain = f64(domain).reshape(n, 4)
+        ip = i32(np.stack([np.broadcast_to(n_sample, (n,)), np.broadcast_to(max_zoom, (n,)),
+                           np.broadcast_to(max_secant, (n,))], axis=1))
+        dp = f64(np.stack([np.broadcast_to(tol, (n,)), np.broadcast_to(clean_tol, (n,))], axis=1))
+        seeds = np.ascontiguousarray(np.broadcast_to(seeds, (n,)), dtype=np.uint32)
+        goff = np.zeros(n + 1, dtype=np.int32)
+        goff[1:] = np.cumsum([len(g) for g in guesses])
+        flat = [complex(z) for g in guesses for z in g]
+        gz = np.ascontiguousarray(np.array(flat, dtype=np.complex128)) if flat else np.zeros(1, np.complex128)
+        fn = self.lib.psi_mode_batch_host
+        fn.restype = C.c_int
+        while True:
+            roots = np.zeros((n, max_roots), dtype=np.complex128)
+            nr = np.zeros(n, dtype=np.int32)
+            nc = np.zeros(n, dtype=np.int32)
+            st = np.zeros(n, dtype=np.int32)
+            stats = np.zeros(5, dtype=np.int64)
+            self._check(fn(self.handle, C.c_int(n), _ptr(dist), _ptr(kx), _ptr(kz), _ptr(alpha),
+                           _ptr(domain), _ptr(ip), _ptr(dp), _ptr(seeds), _ptr(goff), _ptr(gz),
+                           C.c_int(max_roots), _ptr(roots), _ptr(nr), _ptr(nc), _ptr(st), _ptr(stats)),
+                        "psi_mode_batch_host")
+            if n and nr.max() > max_roots:           # rare: more roots than slots, redo with room
+                max_roots = int(nr.max())
+                continue
+            break
+        if np.any(st == 1):
+            bad = int(np.flatnonzero(st == 1)[0])
+            raise PsiError("root search failed for item %d (Kx=%g, Kz=%g): %s"
+                           % (bad, kx[bad], kz[bad], self._last_error()))
+        out = [roots[i, :nr[i]].copy() for i in range(n)]
+        return out, nc, dict(passes=int(stats[0]), evals=int(stats[1]), logic_s=stats[3]*1e-6,
+                             eval_s=stats[4]*1e-6)
+
+    def contour_batch(self, dist, kx, kz, alpha, z_lists, tol, max_step, max_iter):
+        """Root counts of len(dist) closed contours in lock-step.  Returns (counts, status, n_points,
+        stats); counts are -666 where the count did not converge (status 1) ."""
+        n = len(dist)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        dist, kx, kz, alpha = i32(dist), f64(kx), f64(kz), f64(alpha)
+        zoff = np.zeros(n + 1, dtype=np.int32)
+        zoff[1:] = np.cumsum([len(z) for z in z_lists])
+        zz = np.ascontiguousarray(np.array([complex(v) for z in z_lists for v in z], dtype=np.complex128))
+        tol = f64(np.broadcast_to(tol, (n,)))
+        ms = f64(np.broadcast_to(max_step, (n,)))
+        mi = i32(np.broadcast_to(max_iter, (n,)))
+        counts = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        npts = np.zeros(n, dtype=np.int32)
+        stats = np.zeros(2, dtype=np.int64)
+        fn = self.lib.psi_contour_batch_host
+        fn.restype = C.c_int
+        self._check(fn(self.handle, C.c_int(n), _ptr(dist), _ptr(kx), _ptr(kz), _ptr(alpha), _ptr(zoff),
+                       _ptr(zz), _ptr(tol), _ptr(ms), _ptr(mi), _ptr(counts), _ptr(st), _ptr(npts),
+                       _ptr(stats)), "psi_contour_batch_host")
+        return counts, st, npts, dict(passes=int(stats[0]), evals=int(stats[1]))
+
+    def _last_error(self):
+        return load_library().psi_last_error().decode()
+
+
+class Context(EngineAPI):
     """One device + one node table (``psi_ctx``).  Distributions are registered once and cached by
     the bytes of their descriptor."""
 

@@ -15,7 +15,9 @@ FAILED_COUNT = -666
 
 
 class MpiScheduler:
-    def __init__(self, wall_start, wall_limit_total, verbose=True):
+    def __init__(self, wall_start, wall_limit_total, verbose=True, native_engine=True):
+        self.native_engine = native_engine
+        self.last_stats = {}
         self.verbose = verbose
         self.rank = _dist.rank()
         self.nranks = _dist.world_size()
@@ -55,8 +57,36 @@ class MpiScheduler:
             return FAILED_COUNT
         raise job.error
 
+    def _run_native(self, arglist, mine):
+        pds = [self._dispersion(arglist[i]['PSIDispersion.__init__']) for i in mine]
+        if not pds:
+            return {}
+        ctx = pds[0].ctx
+        if any(pd.ctx is not ctx for pd in pds) or not hasattr(ctx, "contour_batch"):
+            return None
+        kw = [dict(arglist[i].get('count_roots', {})) for i in mine]
+        d = [arglist[i]['dispersion'] for i in mine]
+        counts, status, npts, st = ctx.contour_batch(
+            [pd.dist_id for pd in pds], [float(x['wave_number_x']) for x in d],
+            [float(x['wave_number_z']) for x in d], [float(x.get('viscous_alpha', 0)) for x in d],
+            [arglist[i]['z_list'] for i in mine], [k.get('tol', 0.1) for k in kw],
+            [k.get('max_step', 0.1) for k in kw], [k.get('max_iter', 100) for k in kw])
+        if np.any(status == 2):
+            raise ValueError("Infinite value in f_add")
+        for s_ in status:
+            if s_ == 1:
+                print('complex_roots_mpi caught RuntimeError in count_roots')
+                print('Likely means the max iterations was exceeded.')
+        self.last_stats = dict(st, items=len(mine), points=int(np.sum(npts)), engine="native")
+        return {i: np.array([float(c)]) for i, c in zip(mine, counts)}
+
     def run_all(self, arglist):
         mine = _dist.my_items(len(arglist))
+        if self.native_engine:
+            local = self._run_native(arglist, mine)
+            if local is not None:
+                merged = _dist.all_gather_records(local)
+                return {i: int(merged[i][0]) for i in sorted(merged)}
         jobs, ctx = [], None
         for i in mine:
             job, pd = self._job(arglist[i])

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/psi_b200.h"
+#include "psi_internal.hpp"
 #include "psi_table.hpp"
 
 using namespace psi;
@@ -22,6 +23,7 @@ using namespace psi;
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int psi_internal_fail(int code, const std::string& msg) { return fail(code, msg); }
 #define CK(call)                                                                              \
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \
@@ -74,6 +76,8 @@ struct psi_ctx {
     long long launches = 0;
 };
 
+extern "C" { static int ensure_stage(psi_ctx* c, size_t bytes); }
+
 static NodeTableView table_view(const psi_ctx* c) {
     NodeTableView t;
     t.nodes = c->d_nodes; t.level_off = c->d_level_off; t.n_nodes = c->n_nodes; t.max_m = c->max_m;
@@ -101,8 +105,9 @@ __global__ void __launch_bounds__(kEvalThreads, 1)
 disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long long n, int broadcast,
                  const int* __restrict__ dist, const double* __restrict__ kx,
                  const double* __restrict__ kz, const double* __restrict__ alpha,
-                 const double2* __restrict__ w, double2* __restrict__ D, double2* __restrict__ M,
-                 unsigned long long* __restrict__ queue, unsigned long long* __restrict__ node_evals) {
+                 const int* __restrict__ pidx, const double2* __restrict__ w, double2* __restrict__ D,
+                 double2* __restrict__ M, unsigned long long* __restrict__ queue,
+                 unsigned long long* __restrict__ node_evals) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NodeTableView t = gt;
     if (SMEM_TABLE) {
@@ -123,7 +128,7 @@ disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long lo
         if (lane == 0) idx = atomicAdd(queue, 1ull);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= (unsigned long long)n) break;
-        const long long pi = broadcast ? 0 : (long long)idx;
+        const long long pi = pidx != nullptr ? (long long)pidx[idx] : (broadcast ? 0 : (long long)idx);
         const DistParams& d = dists[dist[pi]];
         const double al = alpha[pi];
         if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
@@ -143,7 +148,7 @@ disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long lo
 }
 
 typedef void (*eval_kernel_t)(NodeTableView, const DistParams*, long long, int, const int*, const double*,
-                              const double*, const double*, const double2*, double2*, double2*,
+                              const double*, const double*, const int*, const double2*, double2*, double2*,
                               unsigned long long*, unsigned long long*);
 
 template <bool SMEM>
@@ -287,7 +292,7 @@ int psi_dist_get_background(psi_ctx* c, int dist, double out[5]) {
 static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* dist, const double* kx,
                             const double* kz, const double* alpha, const double* w, double* D,
                             double* M, unsigned long long* node_evals_dev, unsigned class_mask,
-                            cudaStream_t st) {
+                            cudaStream_t st, const int* pidx = nullptr) {
     if (n == 0) return PSI_OK;
     const int warps = kEvalThreads / 32;
     long long want = (n + warps - 1) / warps;
@@ -299,7 +304,7 @@ static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* d
         CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
         eval_kernel_t k = c->table_in_smem ? eval_kernel_for<true>(cls) : eval_kernel_for<false>(cls);
         k<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
-            t, c->d_dists, n, broadcast, dist, kx, kz, alpha, (const double2*)w, (double2*)D,
+            t, c->d_dists, n, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w, (double2*)D,
             (double2*)M, c->d_counter, node_evals_dev);
         c->launches++;
         CK(cudaGetLastError());
@@ -370,6 +375,46 @@ int psi_disp_eval_host(psi_ctx* c, long long n, int broadcast, const int* dist, 
     if (node_evals) *node_evals = ne;
     return PSI_OK;
 }
+
+}  // extern "C"
+
+int psi_internal_eval_indexed(psi_ctx* c, long long n, const int* pidx, int n_params, const int* dist,
+                              const double* kx, const double* kz, const double* alpha, const double* w,
+                              double* D) {
+    if (n == 0) return PSI_OK;
+    CK(cudaSetDevice(c->device));
+    unsigned class_mask = 0;
+    for (int i = 0; i < n_params; ++i) {
+        if (dist[i] < 0 || dist[i] >= (int)c->h_dists.size())
+            return fail(PSI_ERR_ARG, "distribution id out of range");
+        class_mask |= 1u << point_class(c->h_dists[dist[i]], alpha[i]);
+    }
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t np = (size_t)n_params;
+    const size_t o_w = 0, o_D = al(16 * (size_t)n), o_px = al(o_D + 16 * (size_t)n), o_kx = al(o_px + 4 * (size_t)n),
+                 o_kz = al(o_kx + 8 * np), o_al = al(o_kz + 8 * np), o_ds = al(o_al + 8 * np),
+                 total = al(o_ds + 4 * np);
+    int rc = ensure_stage(c, total);
+    if (rc != PSI_OK) return rc;
+    char* base = (char*)c->d_stage;
+    cudaStream_t st = c->stream;
+    CK(cudaMemcpyAsync(base + o_w, w, 16 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_px, pidx, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_kx, kx, 8 * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_kz, kz, 8 * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_al, alpha, 8 * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_ds, dist, 4 * np, cudaMemcpyHostToDevice, st));
+    rc = launch_disp_eval(c, n, 0, (const int*)(base + o_ds), (const double*)(base + o_kx),
+                          (const double*)(base + o_kz), (const double*)(base + o_al),
+                          (const double*)(base + o_w), (double*)(base + o_D), nullptr, c->d_counter + 2,
+                          class_mask, st, (const int*)(base + o_px));
+    if (rc != PSI_OK) return rc;
+    CK(cudaMemcpyAsync(D, base + o_D, 16 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSI_OK;
+}
+
+extern "C" {
 
 int psi_measure_fp64_peak(psi_ctx* c, int reps, double* tflops) {
     if (!c || !tflops || reps < 1) return fail(PSI_ERR_ARG, "psi_measure_fp64_peak: bad argument");

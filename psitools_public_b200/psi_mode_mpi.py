@@ -43,7 +43,7 @@ class _ModeCache:
 class MpiScheduler:
     """Execute a set of PSIMode runs given as a list of arg-dicts."""
 
-    def __init__(self, wall_start, wall_limit_total, verbose=True):
+    def __init__(self, wall_start, wall_limit_total, verbose=True, native_engine=True):
         self.verbose = verbose
         self.exitFlag = False
         self.rank = _dist.rank()
@@ -52,6 +52,9 @@ class MpiScheduler:
         self.wall_limit_total = wall_limit_total
         self._cache = _ModeCache()
         self.last_stats = {}
+        # True: the C++ lock-step engine of libpsi_b200 (csrc/psi_engine.cu) drives the searches;
+        # False: the Python generators of psi_mode.py do (same logic, same LAPACK, ~100x more host time)
+        self.native_engine = native_engine
 
     # -- per-item body ------------------------------------------------------------------------
     def _job(self, args):
@@ -73,10 +76,55 @@ class MpiScheduler:
     def _decode(self, rec):
         return np.asarray(rec, dtype=np.float64).view(np.complex128).copy()
 
+    def _run_native(self, arglist, mine):
+        """All of this rank's items through psi_mode_batch_host; None if an item needs the general
+        (Python) path."""
+        pms, calc = [], []
+        for i in mine:
+            a = arglist[i]
+            c = a['calculate']
+            pm = self._cache.get(a['__init__'])
+            if c.get('count_roots', False) or pm.verbose_flag:
+                return None
+            pms.append(pm)
+            calc.append(c)
+        if not pms:
+            return {}, {}
+        ctx = pms[0].psi_dispersion.ctx
+        if any(pm.psi_dispersion.ctx is not ctx for pm in pms) or not hasattr(ctx, "mode_batch"):
+            return None
+        for pm in pms:
+            pm._sync_cfg()
+        dom = [[pm.domain.xmin, pm.domain.xmax, pm.domain.ymin, pm.domain.ymax] for pm in pms]
+        roots, ncalls, st = ctx.mode_batch(
+            [pm.psi_dispersion.dist_id for pm in pms],
+            [float(c['wave_number_x']) for c in calc], [float(c['wave_number_z']) for c in calc],
+            [float(c.get('viscous_alpha', 0)) for c in calc], dom,
+            [pm.cfg.n_sample for pm in pms], [pm.cfg.max_zoom_level for pm in pms],
+            [pm.cfg.max_secant_iterations for pm in pms], [pm.cfg.tol for pm in pms],
+            [pm.cfg.clean_tol for pm in pms],
+            [int(arglist[i].get('random_seed', 0)) for i in mine],
+            [list(c.get('guess_roots', ())) for c in calc])
+        st["function_calls"] = int(np.sum(ncalls))
+        return {i: r for i, r in zip(mine, roots)}, st
+
     def run_all(self, arglist):
         """Results of every item, on every rank."""
         t0 = time.time()
         mine = _dist.my_items(len(arglist))
+        if self.native_engine:
+            done = self._run_native(arglist, mine)
+            if done is not None:
+                res, st = done
+                if self.verbose:
+                    for i in mine:
+                        print(i, 'result ', res[i])
+                self.last_stats = dict(items=len(mine), passes=st.get("passes", 0),
+                                       function_calls=st.get("function_calls", 0),
+                                       evals=st.get("evals", 0), seconds=time.time() - t0,
+                                       engine="native")
+                merged = _dist.all_gather_records({i: self._encode(r) for i, r in res.items()})
+                return {i: self._decode(merged[i]) for i in sorted(merged)}
         jobs, ctx = [], None
         for i in mine:
             job, trace, pm = self._job(arglist[i])
@@ -91,7 +139,7 @@ class MpiScheduler:
                 print(i, 'result ', j.result)
         self.last_stats = dict(items=len(jobs), passes=stats.get("passes", 0),
                                function_calls=sum(t.n_function_call for _, _, t in jobs),
-                               seconds=time.time() - t0)
+                               seconds=time.time() - t0, engine="python")
         merged = _dist.all_gather_records(local)
         return {i: self._decode(merged[i]) for i in sorted(merged)}
 
