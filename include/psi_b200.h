@@ -99,6 +99,9 @@ int psi_point_class(psi_ctx* ctx, int dist, double alpha);
  * that the engine reproduces numpy.linalg.svd / scipy.linalg.eig of the same interpreter. */
 int psi_engine_bind_lapack(const char* numpy_openblas64, const char* scipy_openblas32);
 
+/* profiling aid: {zgesdd calls, zgesdd ns, zggev calls, zggev ns} accumulated since load */
+void psi_engine_counters(long long out[4]);
+
 /* n_items PSIMode.calculate searches (psi_mode.py:106-333) in lock-step.
  *   dist, kx, kz, alpha : per item (PSIMode(...).dispersion of the item, wave numbers, viscous_alpha)
  *   domain   : 4 doubles per item {real_range[0], real_range[1], imag_range[0], imag_range[1]}

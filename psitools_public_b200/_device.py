@@ -60,6 +60,7 @@ _SIGNATURES = {
     "psi_point_class": (C.c_int, [_vp, C.c_int, C.c_double]),
     "psi_measure_fp64_peak": (C.c_int, [_vp, C.c_int, _dp]),
     "psi_engine_bind_lapack": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "psi_engine_counters": (None, [_vp]),
     "psi_mode_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*10 + [C.c_int] + [_vp]*5),
     "psi_contour_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*13),
 }

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <complex>
 #include <map>
@@ -38,6 +39,18 @@ typedef void (*zgesdd64_t)(const char*, const int64_t*, const int64_t*, cd*, con
 typedef void (*zggev32_t)(const char*, const char*, const int*, cd*, const int*, cd*, const int*, cd*, cd*,
                           cd*, const int*, cd*, const int*, cd*, const int*, double*, int*, size_t, size_t);
 typedef void (*setthreads_t)(int);
+
+// call counters / time (microseconds) of the LAPACK drivers, for profiling the host side
+std::atomic<long long> g_cnt_svd(0), g_us_svd(0), g_cnt_eig(0), g_us_eig(0);
+struct ScopedTimer {
+    std::atomic<long long>& cnt; std::atomic<long long>& us;
+    std::chrono::steady_clock::time_point t0;
+    ScopedTimer(std::atomic<long long>& c, std::atomic<long long>& u) : cnt(c), us(u), t0(std::chrono::steady_clock::now()) {}
+    ~ScopedTimer() {
+        us += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        cnt += 1;
+    }
+};
 
 struct Lapack {
     void* h_np = nullptr;
@@ -243,6 +256,7 @@ struct AAA {
             std::vector<double> s(mn), rwork((size_t)std::max<int64_t>(1, mn * std::max(5 * mn + 7, 2 * mx + 2 * mn + 1)));
             std::vector<cd> U((size_t)r * r), VT((size_t)m * m), work(1);
             std::vector<int64_t> iwork(8 * mn);
+            ScopedTimer tm(g_cnt_svd, g_us_svd);
             int64_t lwork = -1, info = 0, lda = r, ldu = r, ldvt = m;
             g_lapack.zgesdd("A", &r, &m, A.data(), &lda, s.data(), U.data(), &ldu, VT.data(), &ldvt,
                             work.data(), &lwork, rwork.data(), iwork.data(), &info, 1);
@@ -331,6 +345,7 @@ struct AAA {
         }
         std::vector<cd> alpha(n), beta(n), vr((size_t)n * n), work(1), vl(1);
         std::vector<double> rwork(8 * n);
+        ScopedTimer tm(g_cnt_eig, g_us_eig);
         int lwork = -1, info = 0, ldvl = 1;
         g_lapack.zggev("N", "V", &n, A.data(), &n, B.data(), &n, alpha.data(), beta.data(), vl.data(), &ldvl,
                        vr.data(), &n, work.data(), &lwork, rwork.data(), &info, 1, 1);
@@ -800,6 +815,11 @@ int psi_engine_bind_lapack(const char* numpy_openblas64, const char* scipy_openb
     if (setthreads_t f = (setthreads_t)dlsym(g_lapack.h_np, "scipy_openblas_set_num_threads64_")) f(1);
     if (setthreads_t f = (setthreads_t)dlsym(g_lapack.h_sp, "scipy_openblas_set_num_threads")) f(1);
     return PSI_OK;
+}
+
+/* profiling aid: {svd calls, svd ns, eig calls, eig ns} accumulated since load */
+void psi_engine_counters(long long out[4]) {
+    out[0] = g_cnt_svd; out[1] = g_us_svd; out[2] = g_cnt_eig; out[3] = g_us_eig;
 }
 
 int psi_mode_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,

@@ -1,0 +1,124 @@
+"""PSIGridRefiner against the reference's run of test_psi_grid_refine.py:35-77 (tiny configuration:
+PowerBump, krange (1, 1.1), nbase (2, 2), reruns 0, seed 2; fixture tests/golden/refine.json).
+
+What is compared and why: the reference pins the per-run root lists of one particular numpy/LAPACK
+build; SURVEY.md section 7 shows that even the reference does not reproduce those multiplicities
+across builds (root-less pixels re-run with neighbour guesses sit on a knife edge of the rational
+approximation).  The deterministic part is checked exactly -- grids, run-id bookkeeping (including
+the reference's re-use of the largest run id), the base map and the first sweep -- and the final
+map is checked on de-duplicated root sets per pixel."""
+import time
+
+import numpy as np
+import pytest
+
+from common import carr, load
+from test_host_logic import same_root_sets
+
+
+def make_refiner(engine):
+    from psitools_public_b200 import (PowerBump, PSIGridRefiner, SizeDensity, TanhSinhNoDeepCopy,
+                                      psi_mode_mpi)
+    pb = PowerBump(amin=1e-8, aP=0.1, aL=2.0/3.0*0.1, aR=0.156, bumpfac=2.0)
+    sd = SizeDensity(pb.sigma0, [1e-8, 0.156])
+    sd.poles = [pb.get_discontinuity()]
+    baseargs = {'__init__': {'stokes_range': [1e-8, 0.156], 'dust_to_gas_ratio': 10.0,
+                             'size_density': sd, 'real_range': [-2.0, 2.0], 'imag_range': [1e-7, 1.0],
+                             'n_sample': 20, 'max_zoom_domains': 1, 'tol': 1.0e-13, 'clean_tol': 1e-4,
+                             'tanhsinh_integrator': TanhSinhNoDeepCopy()},
+                'calculate': {'wave_number_x': None, 'wave_number_z': None, 'guess_roots': []},
+                'random_seed': 2}
+    ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False, native_engine=engine == "native")
+    log = []
+    inner = ms.run_all
+
+    def logged(arglist):
+        res = inner(arglist)
+        log.append([(a['calculate']['wave_number_x'], a['calculate']['wave_number_z'],
+                     list(a['calculate']['guess_roots']), res[i]) for i, a in enumerate(arglist)])
+        return res
+    ms.run_all = logged
+    return PSIGridRefiner('golden', baseargs=baseargs, nbase=(2, 2), reruns=0, krange=(1, 1.1),
+                          scheduler=ms), log
+
+
+def distinct(roots):
+    from psitools_public_b200.psi_grid_refine import prune_eps
+    roots = list(roots)
+    if not roots:
+        return []
+    return list(prune_eps(roots, epsilon=1e-6*max(abs(r) for r in roots)))
+
+
+@pytest.mark.parametrize("engine", ["native", "python"])
+def test_refiner_against_reference(backend, engine, tmp_path):
+    from psitools_public_b200.psi_grid_refine import get_if
+    gold = load("refine.json")
+    gr, log = make_refiner(engine)
+    gr.run_basegrid()
+    assert gr.grids[0]['Kx'].shape == (4, 4)                      # nbase + one pad cell per side
+    gr.fill_in_grid()
+    final, gfin = gr.grids[-1], gold["final"]
+    np.testing.assert_allclose(final['Kx'], gfin['Kx'], rtol=1e-15)
+    np.testing.assert_allclose(final['Kz'], gfin['Kz'], rtol=1e-15)
+    assert final['runs'].shape == (7, 7)
+    # same pixels never ran (-1) and the reference's run-id collision is reproduced
+    assert np.array_equal(final['runs'] < 0, np.array(gfin['runs']) < 0)
+    assert (final['runs'] == 19).sum() == (np.array(gfin['runs']) == 19).sum() == 2
+    # base map and first sweep: identical work lists and identical root sets
+    for mine, ref in zip(log[:2], gold["batches"][:2]):
+        assert len(mine) == len(ref)
+        for (kx, kz, guess, roots), r in zip(mine, ref):
+            assert abs(kx - r["kx"]) < 1e-12*kx and abs(kz - r["kz"]) < 1e-12*kz
+            assert same_root_sets(list(guess), list(carr(r["guess"])))
+            assert same_root_sets(list(roots), list(carr(r["roots"]))), (kx, kz)
+    # second sweep (after fill-in): same pixels are scheduled with the same guesses
+    assert [(round(a[0], 9), round(a[1], 9), len(a[2])) for a in log[2]] == \
+        [(round(r["kx"], 9), round(r["kz"], 9), len(r["guess"])) for r in gold["batches"][2]]
+    # final map: distinct roots per pixel agree on all but the knife-edge pixels
+    ref_results = {int(k): carr(v) for k, v in gfin["results"].items()}
+    ref_runs = np.array(gfin["runs"])
+    agree = 0
+    for iz in range(7):
+        for ix in range(7):
+            a = distinct(get_if(final['results'], final['runs'][iz, ix]))
+            b = distinct(get_if(ref_results, ref_runs[iz, ix]))
+            agree += same_root_sets(a, b)
+    assert agree >= 45, agree                                     # measured: 47 of 49
+    # every reported root is a root of the dispersion relation
+    from psitools_public_b200 import PSIDispersion
+    init = gr.baseargs['__init__']
+    pd = PSIDispersion(init['dust_to_gas_ratio'], init['stokes_range'], size_density=init['size_density'],
+                       tanhsinh_integrator=init['tanhsinh_integrator'])
+    # (checked per scheduler call: the map itself inherits the reference's run-id collision, which
+    # makes a few pixels display another pixel's roots)
+    for batch in log:
+        for kx, kz, _, roots in batch:
+            for root in distinct(roots):
+                d0 = pd.calculate(root, kx, kz)
+                d1 = pd.calculate(root + 1e-4, kx, kz)
+                assert abs(d0) < 1e-3*abs(d1 - d0)                # |D| << |D'| * 1e-4  => |dw| < 1e-7
+    # output writer ("next" row f1): npz fallback when h5py is absent
+    gr.batchname = str(tmp_path / "map")
+    gr.datafile_hdf5 = gr.batchname + ".hdf5"
+    path = gr.to_hdf5()
+    if path.endswith(".npz"):
+        z = np.load(path)
+        assert z["1/Kxgrid"].shape == (7, 7) and z["1/root_real"].shape[:2] == (7, 7)
+        assert np.array_equal(z["1/error"] > 0, np.array([[len(get_if(final['results'], r)) > 0
+                                                           for r in row] for row in final['runs']]))
+
+
+def test_spreadgrid_and_prune():
+    from psitools_public_b200.psi_grid_refine import prune_eps, spreadgrid
+    kz, kx = np.meshgrid(np.logspace(0, 1, 3), np.logspace(0, 2, 4), indexing='ij')
+    nx = spreadgrid(kx, const_axis=0)
+    nz = spreadgrid(kz, const_axis=1)
+    assert nx.shape == nz.shape == (5, 7)
+    np.testing.assert_allclose(nx[0], np.logspace(0, 2, 7))
+    np.testing.assert_allclose(nz[:, 0], np.logspace(0, 1, 5))
+    assert np.all(nx[1] == nx[0]) and np.all(nz[:, 1] == nz[:, 0])
+    vals = [1 + 1j, 1 + 1.0000001j, 2 + 0j]
+    assert len(prune_eps(vals, 1e-5)) == 2 and prune_eps([], 1e-5) == []
+    with pytest.raises(ValueError):
+        spreadgrid(kx, const_axis=2)
