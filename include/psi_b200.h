@@ -99,6 +99,11 @@ int psi_point_class(psi_ctx* ctx, int dist, double alpha);
  * that the engine reproduces numpy.linalg.svd / scipy.linalg.eig of the same interpreter. */
 int psi_engine_bind_lapack(const char* numpy_openblas64, const char* scipy_openblas32);
 
+/* Host threads the engine uses for the per-item logic between kernel launches (AAA, state machines).
+ * n <= 0: OpenMP default.  Under torchrun (OMP_NUM_THREADS=1) the Python layer sets
+ * cpu_count / LOCAL_WORLD_SIZE. */
+void psi_engine_set_threads(int n);
+
 /* profiling aid: {zgesdd calls, zgesdd ns, zggev calls, zggev ns} accumulated since load */
 void psi_engine_counters(long long out[4]);
 
@@ -111,20 +116,36 @@ void psi_engine_counters(long long out[4]);
  *   guess_off: n_items+1 offsets into guesses (interleaved complex) = guess_roots of each item
  *   roots    : max_roots complex slots per item; n_roots = roots found (may exceed max_roots ->
  *              status 2, truncated); n_calls = PSIMode.n_function_call; status 0 ok / 1 failed
- *   stats    : 5 values {passes, D evaluations, failed items, host-logic us, K1+copies us} (optional) */
+ *   stats    : 7 values {rounds, D evaluations, failed items, host-logic us, device us, kernel
+ *              launches, D evaluations inside K3} (optional) */
 int psi_mode_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
                         const double* alpha, const double* domain, const int* iparams, const double* dparams,
                         const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,
                         double* roots, int* n_roots, int* n_calls, int* status, long long* stats);
 
-/* n_items ClosedPath(...).count_roots(max_iter, tol, max_step) (complex_roots.py:517-625) in lock-step.
- *   z_off: n_items+1 offsets into z_list (interleaved complex contour corners, counter-clockwise)
+/* Kernel K2 -- n_items ClosedPath(f, z_list).count_roots(max_iter, tol, max_step)
+ * (complex_roots.py:517-625) in ONE launch: one warp per contour runs every refinement pass and the
+ * winding sum on the device.
+ *   z_off : n_items+1 offsets into z_list (interleaved complex contour corners, counter-clockwise)
  *   counts: winding number, or -666 when it did not converge (complex_roots_mpi.py:171-174)
- *   status: 0 ok, 1 RuntimeError (no integer / max_iter exceeded), 2 ValueError (non-finite f) */
+ *   status: 0 ok, 1 no integer winding number, 2 max_iter exceeded (both RuntimeError in the
+ *           reference), 3 non-finite D (ValueError), 4 more than 4096 contour points
+ *   stats : {launches, D evaluations} (optional) */
 int psi_contour_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
                            const double* alpha, const int* z_off, const double* z_list, const double* tol,
                            const double* max_step, const int* max_iter, int* counts, int* status,
                            int* n_points, long long* stats);
+
+/* Kernel K3 -- n_items PSIMode.find_dispersion_roots(zeros, max_iter) (psi_mode.py:340-352, 411-491) in
+ * ONE launch: one warp per item polishes its start values one after the other with the two-stage secant
+ * iteration (scipy newton's rule), every D evaluated on the device.
+ *   domain : 4 doubles per item; w0_off: n_items+1 offsets into w0 (interleaved complex start values)
+ *   roots  : one complex per start value: the root, or the sentinel -1j (failed / left the domain)
+ *   n_calls: D evaluations as PSIMode.n_function_call counts them; max_conv: largest iteration count of
+ *            a converged start; status 1 = a start value on the real axis (ValueError in the reference) */
+int psi_polish_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
+                          const double* alpha, const double* domain, const int* w0_off, const double* w0,
+                          const int* max_iter, double* roots, int* n_calls, int* max_conv, int* status);
 
 /* FP64 FMA-pipe peak of the device (roofline denominator; MEASURED_PEAKS.json has no FP64 entry):
  * runs a register-resident DFMA chain kernel `reps` times and returns the best TFLOP/s. */

@@ -61,8 +61,10 @@ _SIGNATURES = {
     "psi_measure_fp64_peak": (C.c_int, [_vp, C.c_int, _dp]),
     "psi_engine_bind_lapack": (C.c_int, [C.c_char_p, C.c_char_p]),
     "psi_engine_counters": (None, [_vp]),
+    "psi_engine_set_threads": (None, [C.c_int]),
     "psi_mode_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*10 + [C.c_int] + [_vp]*5),
     "psi_contour_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*13),
+    "psi_polish_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*12),
 }
 
 
@@ -127,8 +129,18 @@ class EngineAPI:
 
     _lapack_bound = False
 
+    @staticmethod
+    def default_engine_threads():
+        """Host threads per process: all cores, shared fairly between the ranks of one node (torchrun
+        sets OMP_NUM_THREADS=1, which would serialise the engine's AAA phase)."""
+        if "PSI_B200_THREADS" in os.environ:
+            return max(1, int(os.environ["PSI_B200_THREADS"]))
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        return max(1, (os.cpu_count() or 1)//ranks)
+
     def _bind_lapack(self):
         if not self._lapack_bound:
+            self.lib.psi_engine_set_threads(C.c_int(self.default_engine_threads()))
             a, b = openblas_paths()
             fn = self.lib.psi_engine_bind_lapack
             fn.restype, fn.argtypes = C.c_int, [C.c_char_p, C.c_char_p]
@@ -163,7 +175,7 @@ class EngineAPI:
             nr = np.zeros(n, dtype=np.int32)
             nc = np.zeros(n, dtype=np.int32)
             st = np.zeros(n, dtype=np.int32)
-            stats = np.zeros(5, dtype=np.int64)
+            stats = np.zeros(8, dtype=np.int64)
             self._check(fn(self.handle, C.c_int(n), _ptr(dist), _ptr(kx), _ptr(kz), _ptr(alpha),
                            _ptr(domain), _ptr(ip), _ptr(dp), _ptr(seeds), _ptr(goff), _ptr(gz),
                            C.c_int(max_roots), _ptr(roots), _ptr(nr), _ptr(nc), _ptr(st), _ptr(stats)),
@@ -178,11 +190,12 @@ class EngineAPI:
                            % (bad, kx[bad], kz[bad], self._last_error()))
         out = [roots[i, :nr[i]].copy() for i in range(n)]
         return out, nc, dict(passes=int(stats[0]), evals=int(stats[1]), logic_s=stats[3]*1e-6,
-                             eval_s=stats[4]*1e-6)
+                             eval_s=stats[4]*1e-6, launches=int(stats[5]), polish_evals=int(stats[6]))
 
     def contour_batch(self, dist, kx, kz, alpha, z_lists, tol, max_step, max_iter):
-        """Root counts of len(dist) closed contours in lock-step.  Returns (counts, status, n_points,
-        stats); counts are -666 where the count did not converge (status 1) ."""
+        """Root counts of len(dist) closed contours with ONE launch of kernel K2.  Returns (counts,
+        status, n_points, stats); counts are -666 where the count did not converge (status 1/2: the
+        reference's RuntimeError; 3: non-finite D, its ValueError; 4: contour buffer exhausted)."""
         n = len(dist)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -203,6 +216,30 @@ class EngineAPI:
                        _ptr(zz), _ptr(tol), _ptr(ms), _ptr(mi), _ptr(counts), _ptr(st), _ptr(npts),
                        _ptr(stats)), "psi_contour_batch_host")
         return counts, st, npts, dict(passes=int(stats[0]), evals=int(stats[1]))
+
+    def polish_batch(self, dist, kx, kz, alpha, domain, starts, max_iter):
+        """Kernel K3: secant polish of every list of start values in ``starts`` (one list per item).
+        Returns (list of arrays with the roots or the sentinel -1j, n_calls, max_conv, status)."""
+        n = len(dist)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        dist, kx, kz, alpha = i32(dist), f64(kx), f64(kz), f64(alpha)
+        domain = f64(domain).reshape(n, 4)
+        off = np.zeros(n + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(s) for s in starts])
+        flat = [complex(z) for s in starts for z in s]
+        w0 = np.ascontiguousarray(np.array(flat, dtype=np.complex128)) if flat else np.zeros(1, np.complex128)
+        mi = i32(np.broadcast_to(max_iter, (n,)))
+        roots = np.zeros(max(1, int(off[-1])), dtype=np.complex128)
+        nc = np.zeros(n, dtype=np.int32)
+        mc = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        fn = self.lib.psi_polish_batch_host
+        fn.restype = C.c_int
+        self._check(fn(self.handle, C.c_int(n), _ptr(dist), _ptr(kx), _ptr(kz), _ptr(alpha), _ptr(domain),
+                       _ptr(off), _ptr(w0), _ptr(mi), _ptr(roots), _ptr(nc), _ptr(mc), _ptr(st)),
+                    "psi_polish_batch_host")
+        return [roots[off[i]:off[i + 1]].copy() for i in range(n)], nc, mc, st
 
     def _last_error(self):
         return load_library().psi_last_error().decode()

@@ -71,10 +71,12 @@ class MpiScheduler:
             [float(x['wave_number_z']) for x in d], [float(x.get('viscous_alpha', 0)) for x in d],
             [arglist[i]['z_list'] for i in mine], [k.get('tol', 0.1) for k in kw],
             [k.get('max_step', 0.1) for k in kw], [k.get('max_iter', 100) for k in kw])
-        if np.any(status == 2):
+        if np.any(status == 3):
             raise ValueError("Infinite value in f_add")
+        if np.any(status == 4):
+            raise RuntimeError("contour needs more than 4096 points")
         for s_ in status:
-            if s_ == 1:
+            if s_ in (1, 2):
                 print('complex_roots_mpi caught RuntimeError in count_roots')
                 print('Likely means the max iterations was exceeded.')
         self.last_stats = dict(st, items=len(mine), points=int(np.sum(npts)), engine="native")

@@ -9,11 +9,13 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "../../include/psi_b200.h"
 #include "psi_internal.hpp"
+#include "psi_batch.cuh"
 #include "psi_table.hpp"
 
 using namespace psi;
@@ -48,6 +50,7 @@ struct WarpCuda {
 // context
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxDists = 4096;
+constexpr int kContourCap = 4096;          // points per contour buffer of K2 (the reference's runs stay < 1000)
 #ifndef PSI_EVAL_THREADS
 #define PSI_EVAL_THREADS 384
 #endif
@@ -73,6 +76,8 @@ struct psi_ctx {
     // staging for the *_host entry points
     void* d_stage = nullptr;
     size_t stage_bytes = 0;
+    // per-warp ping-pong point buffers of the contour kernel (K2)
+    void* d_contour_scratch = nullptr;
     long long launches = 0;
 };
 
@@ -98,16 +103,9 @@ __global__ void background_kernel(NodeTableView t, DistParams* dists, int id) {
     }
 }
 
-// K1.  One specialisation per work class (NK, VISC); a launch handles the points of ITS class and
-// skips the others (a batch normally holds a single class, see launch_disp_eval).
-template <bool SMEM_TABLE, int NK, bool VISC>
-__global__ void __launch_bounds__(kEvalThreads, 1)
-disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long long n, int broadcast,
-                 const int* __restrict__ dist, const double* __restrict__ kx,
-                 const double* __restrict__ kz, const double* __restrict__ alpha,
-                 const int* __restrict__ pidx, const double2* __restrict__ w, double2* __restrict__ D,
-                 double2* __restrict__ M, unsigned long long* __restrict__ queue,
-                 unsigned long long* __restrict__ node_evals) {
+// Copy the level-major node table into shared memory (once per persistent CTA) and return a view of it.
+template <bool SMEM_TABLE>
+__device__ __forceinline__ NodeTableView stage_table(const NodeTableView& gt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NodeTableView t = gt;
     if (SMEM_TABLE) {
@@ -121,6 +119,28 @@ disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long lo
         t.nodes = s_nodes;
         t.level_off = s_off;
     }
+    return t;
+}
+
+__device__ __forceinline__ bool next_item(unsigned long long* queue, long long n, long long& idx) {
+    unsigned long long v = 0;
+    if ((threadIdx.x & 31) == 0) v = atomicAdd(queue, 1ull);
+    v = __shfl_sync(0xffffffffu, v, 0);
+    idx = (long long)v;
+    return v < (unsigned long long)n;
+}
+
+// K1.  One specialisation per work class (NK, VISC); a launch handles the points of ITS class and
+// skips the others (a batch normally holds a single class, see launch_disp_eval).
+template <bool SMEM_TABLE, int NK, bool VISC>
+__global__ void __launch_bounds__(kEvalThreads, 1)
+disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long long n, int broadcast,
+                 const int* __restrict__ dist, const double* __restrict__ kx,
+                 const double* __restrict__ kz, const double* __restrict__ alpha,
+                 const int* __restrict__ pidx, const double2* __restrict__ w, double2* __restrict__ D,
+                 double2* __restrict__ M, unsigned long long* __restrict__ queue,
+                 unsigned long long* __restrict__ node_evals) {
+    const NodeTableView t = stage_table<SMEM_TABLE>(gt);
     const int lane = threadIdx.x & 31;
     unsigned long long nodes = 0;
     while (true) {
@@ -164,6 +184,102 @@ static eval_kernel_t eval_kernel_for(int cls) {
     default: return disp_eval_kernel<SMEM, 3, true>;
     }
 }
+
+// K3 polish_kernel: one warp per root search; the whole two-stage secant polish of all its start
+// values runs on the device, every D evaluated inline (psi_batch.cuh, polish_run).
+template <bool SMEM_TABLE, int NK, bool VISC>
+__global__ void __launch_bounds__(kEvalThreads, 1)
+polish_kernel(NodeTableView gt, const DistParams* __restrict__ dists, int n_items,
+              const int* __restrict__ pidx, const int* __restrict__ dist, const double* __restrict__ kx,
+              const double* __restrict__ kz, const double* __restrict__ alpha,
+              const double* __restrict__ dom, const int* __restrict__ off, double2* w0,
+              const int* __restrict__ max_iter, double2* out, int* n_calls, int* max_conv, int* status,
+              unsigned long long* queue, unsigned long long* counters) {
+    const NodeTableView t = stage_table<SMEM_TABLE>(gt);
+    const int lane = threadIdx.x & 31;
+    unsigned long long nodes = 0, evals = 0;
+    long long idx;
+    while (next_item(queue, n_items, idx)) {
+        const int pi = pidx[idx];
+        const DistParams& d = dists[dist[pi]];
+        const double al = alpha[pi];
+        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
+        WarpEval<WarpCuda, NK, VISC> f;
+        f.t = &t; f.d = &d; f.kx = kx[pi]; f.kz = kz[pi]; f.alpha = al; f.nodes = 0; f.evals = 0;
+        const RectDom rd{dom[4 * idx], dom[4 * idx + 1], dom[4 * idx + 2], dom[4 * idx + 3]};
+        const int o = off[idx], n = off[idx + 1] - o;
+        int conv = 0, st = 0;
+        const int calls = polish_run(f, rd, reinterpret_cast<cx*>(w0 + o), n, max_iter[idx],
+                                     reinterpret_cast<cx*>(out + o), &conv, &st);
+        if (lane == 0) { n_calls[idx] = calls; max_conv[idx] = conv; status[idx] = st; }
+        nodes += f.nodes; evals += (unsigned long long)f.evals;
+    }
+    if (counters != nullptr && lane == 0) {
+        if (nodes) atomicAdd(counters, nodes);
+        if (evals) atomicAdd(counters + 1, evals);
+    }
+}
+
+// K2 contour_kernel: one warp per closed contour; adaptive refinement passes and the winding sum on
+// the device (psi_batch.cuh, contour_run).  scratch: 4*cap complex per warp of the grid.
+template <bool SMEM_TABLE, int NK, bool VISC>
+__global__ void __launch_bounds__(kEvalThreads, 1)
+contour_kernel(NodeTableView gt, const DistParams* __restrict__ dists, int n_items,
+               const int* __restrict__ dist, const double* __restrict__ kx, const double* __restrict__ kz,
+               const double* __restrict__ alpha, const int* __restrict__ z_off,
+               const double2* __restrict__ z_list, const double* __restrict__ tol,
+               const double* __restrict__ max_step, const int* __restrict__ max_iter, double2* scratch,
+               int cap, int* counts, int* status, int* n_points, unsigned long long* queue,
+               unsigned long long* counters) {
+    const NodeTableView t = stage_table<SMEM_TABLE>(gt);
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    cx* base = reinterpret_cast<cx*>(scratch) + (size_t)warp_global * 4 * cap;
+    unsigned long long nodes = 0, evals = 0;
+    long long idx;
+    while (next_item(queue, n_items, idx)) {
+        const DistParams& d = dists[dist[idx]];
+        const double al = alpha[idx];
+        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
+        WarpEval<WarpCuda, NK, VISC> f;
+        f.t = &t; f.d = &d; f.kx = kx[idx]; f.kz = kz[idx]; f.alpha = al; f.nodes = 0; f.evals = 0;
+        const int o = z_off[idx], n0 = z_off[idx + 1] - o;
+        int cnt = -666, np = n0, st = kContourCapacity;
+        if (n0 <= cap) {
+            for (int i = 0; i < n0; ++i) base[i] = cx(z_list[o + i].x, z_list[o + i].y);
+            st = contour_run(f, base, base + cap, base + 2 * cap, base + 3 * cap, n0, cap, tol[idx],
+                             max_step[idx], max_iter[idx], &cnt, &np);
+        }
+        if (lane == 0) { counts[idx] = cnt; status[idx] = st; n_points[idx] = np; }
+        nodes += f.nodes; evals += (unsigned long long)f.evals;
+    }
+    if (counters != nullptr && lane == 0) {
+        if (nodes) atomicAdd(counters, nodes);
+        if (evals) atomicAdd(counters + 1, evals);
+    }
+}
+
+typedef void (*polish_kernel_t)(NodeTableView, const DistParams*, int, const int*, const int*, const double*,
+                                const double*, const double*, const double*, const int*, double2*, const int*,
+                                double2*, int*, int*, int*, unsigned long long*, unsigned long long*);
+typedef void (*contour_kernel_t)(NodeTableView, const DistParams*, int, const int*, const double*,
+                                 const double*, const double*, const int*, const double2*, const double*,
+                                 const double*, const int*, double2*, int, int*, int*, int*,
+                                 unsigned long long*, unsigned long long*);
+
+#define PSI_CLASS_SWITCH(NAME, SMEM, cls)                       \
+    switch (cls) {                                              \
+    case 0: return NAME<SMEM, 0, false>;                        \
+    case 1: return NAME<SMEM, 0, true>;                         \
+    case 2: return NAME<SMEM, 1, false>;                        \
+    case 3: return NAME<SMEM, 1, true>;                         \
+    case 4: return NAME<SMEM, 2, false>;                        \
+    case 5: return NAME<SMEM, 2, true>;                         \
+    case 6: return NAME<SMEM, 3, false>;                        \
+    default: return NAME<SMEM, 3, true>;                        \
+    }
+template <bool SMEM> static polish_kernel_t polish_kernel_for(int cls) { PSI_CLASS_SWITCH(polish_kernel, SMEM, cls) }
+template <bool SMEM> static contour_kernel_t contour_kernel_for(int cls) { PSI_CLASS_SWITCH(contour_kernel, SMEM, cls) }
 
 // DFMA-pipe peak: 8 independent FMA chains per thread, all in registers.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
@@ -224,8 +340,14 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
     c->table_in_smem = c->table_smem + 1024 <= (size_t)c->smem_optin;
     if (c->table_in_smem)
         for (int cls = 0; cls < kNumClasses; ++cls)
+        {
             CK(cudaFuncSetAttribute(eval_kernel_for<true>(cls),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+            CK(cudaFuncSetAttribute(polish_kernel_for<true>(cls),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+            CK(cudaFuncSetAttribute(contour_kernel_for<true>(cls),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+        }
     CK(cudaMalloc(&c->d_dists, sizeof(DistParams) * kMaxDists));
     CK(cudaMalloc(&c->d_counter, sizeof(unsigned long long) * 8));
     CK(cudaMemset(c->d_counter, 0, sizeof(unsigned long long) * 8));
@@ -238,7 +360,7 @@ void psi_ctx_destroy(psi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_nodes); cudaFree(c->d_level_off); cudaFree(c->d_dists); cudaFree(c->d_counter);
-    cudaFree(c->d_stage);
+    cudaFree(c->d_stage); cudaFree(c->d_contour_scratch);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -414,7 +536,145 @@ int psi_internal_eval_indexed(psi_ctx* c, long long n, const int* pidx, int n_pa
     return PSI_OK;
 }
 
+// stage a list of host arrays contiguously on the device; returns device pointers in the same order
+struct StageItem { const void* src; size_t bytes; };
+static int stage_upload(psi_ctx* c, const StageItem* items, int n, size_t extra, char** dptr, char** extra_ptr) {
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += al(items[i].bytes);
+    total += al(extra);
+    int rc = ensure_stage(c, total);
+    if (rc != PSI_OK) return rc;
+    char* p = (char*)c->d_stage;
+    for (int i = 0; i < n; ++i) {
+        dptr[i] = p;
+        if (items[i].src && items[i].bytes)
+            CK(cudaMemcpyAsync(p, items[i].src, items[i].bytes, cudaMemcpyHostToDevice, c->stream));
+        p += al(items[i].bytes);
+    }
+    if (extra_ptr) *extra_ptr = p;
+    return PSI_OK;
+}
+
+static unsigned class_mask_of(psi_ctx* c, int n_params, const int* dist, const double* alpha, bool* ok) {
+    unsigned m = 0;
+    *ok = true;
+    for (int i = 0; i < n_params; ++i) {
+        if (dist[i] < 0 || dist[i] >= (int)c->h_dists.size()) { *ok = false; return 0; }
+        m |= 1u << point_class(c->h_dists[dist[i]], alpha[i]);
+    }
+    return m;
+}
+
+int psi_internal_polish(psi_ctx* c, int n_items, const int* pidx, int n_params, const int* dist,
+                        const double* kx, const double* kz, const double* alpha, const double* dom,
+                        const int* off, double* w0, const int* max_iter, double* out, int* n_calls,
+                        int* max_conv, int* status, long long* evals) {
+    if (evals) *evals = 0;
+    if (n_items == 0) return PSI_OK;
+    CK(cudaSetDevice(c->device));
+    bool ok;
+    const unsigned mask = class_mask_of(c, n_params, dist, alpha, &ok);
+    if (!ok) return fail(PSI_ERR_ARG, "distribution id out of range");
+    const size_t nw = (size_t)off[n_items], ni = (size_t)n_items, np = (size_t)n_params;
+    StageItem it[] = {{pidx, 4 * ni}, {dist, 4 * np}, {kx, 8 * np}, {kz, 8 * np}, {alpha, 8 * np},
+                      {dom, 32 * ni}, {off, 4 * (ni + 1)}, {w0, 16 * nw}, {max_iter, 4 * ni},
+                      {nullptr, 16 * nw}, {nullptr, 4 * ni}, {nullptr, 4 * ni}, {nullptr, 4 * ni}};
+    char* d[13];
+    int rc = stage_upload(c, it, 13, 0, d, nullptr);
+    if (rc != PSI_OK) return rc;
+    cudaStream_t st = c->stream;
+    const int warps = kEvalThreads / 32;
+    const int grid = std::min(c->sm_count, (n_items + warps - 1) / warps);
+    CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
+    NodeTableView t = table_view(c);
+    for (int cls = 0; cls < kNumClasses; ++cls) {
+        if (!(mask & (1u << cls))) continue;
+        CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+        polish_kernel_t k = c->table_in_smem ? polish_kernel_for<true>(cls) : polish_kernel_for<false>(cls);
+        k<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+            t, c->d_dists, n_items, (const int*)d[0], (const int*)d[1], (const double*)d[2],
+            (const double*)d[3], (const double*)d[4], (const double*)d[5], (const int*)d[6], (double2*)d[7],
+            (const int*)d[8], (double2*)d[9], (int*)d[10], (int*)d[11], (int*)d[12], c->d_counter,
+            c->d_counter + 4);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    unsigned long long cnt[2] = {0, 0};
+    CK(cudaMemcpyAsync(out, d[9], 16 * nw, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_calls, d[10], 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(max_conv, d[11], 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, d[12], 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cnt, c->d_counter + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (evals) *evals = (long long)cnt[1];
+    return PSI_OK;
+}
+
 extern "C" {
+
+int psi_polish_batch_host(psi_ctx* c, int n_items, const int* dist, const double* kx, const double* kz,
+                          const double* alpha, const double* domain, const int* w0_off, const double* w0,
+                          const int* max_iter, double* roots, int* n_calls, int* max_conv, int* status) {
+    if (!c || n_items < 0 || !dist || !kx || !kz || !alpha || !domain || !w0_off || !w0 || !max_iter ||
+        !roots || !n_calls || !max_conv || !status)
+        return fail(PSI_ERR_ARG, "psi_polish_batch_host: bad argument");
+    std::vector<int> pidx(n_items);
+    for (int i = 0; i < n_items; ++i) pidx[i] = i;
+    std::vector<double> w0copy(w0, w0 + 2 * (size_t)w0_off[n_items]);
+    return psi_internal_polish(c, n_items, pidx.data(), n_items, dist, kx, kz, alpha, domain, w0_off,
+                               w0copy.data(), max_iter, roots, n_calls, max_conv, status, nullptr);
+}
+
+int psi_contour_batch_host(psi_ctx* c, int n_items, const int* dist, const double* kx, const double* kz,
+                           const double* alpha, const int* z_off, const double* z_list, const double* tol,
+                           const double* max_step, const int* max_iter, int* counts, int* status,
+                           int* n_points, long long* stats) {
+    if (!c || n_items < 0 || !dist || !kx || !kz || !alpha || !z_off || !z_list || !tol || !max_step ||
+        !max_iter || !counts || !status || !n_points)
+        return fail(PSI_ERR_ARG, "psi_contour_batch_host: bad argument");
+    if (stats) { stats[0] = 0; stats[1] = 0; }
+    if (n_items == 0) return PSI_OK;
+    CK(cudaSetDevice(c->device));
+    bool ok;
+    const unsigned mask = class_mask_of(c, n_items, dist, alpha, &ok);
+    if (!ok) return fail(PSI_ERR_ARG, "distribution id out of range");
+    const int cap = kContourCap;
+    const int warps = kEvalThreads / 32;
+    const int grid = std::min(c->sm_count, (n_items + warps - 1) / warps);
+    if (!c->d_contour_scratch)
+        CK(cudaMalloc(&c->d_contour_scratch, (size_t)c->sm_count * warps * 4 * cap * sizeof(double2)));
+    const size_t ni = (size_t)n_items, nz = (size_t)z_off[n_items];
+    StageItem it[] = {{dist, 4 * ni}, {kx, 8 * ni}, {kz, 8 * ni}, {alpha, 8 * ni}, {z_off, 4 * (ni + 1)},
+                      {z_list, 16 * nz}, {tol, 8 * ni}, {max_step, 8 * ni}, {max_iter, 4 * ni},
+                      {nullptr, 4 * ni}, {nullptr, 4 * ni}, {nullptr, 4 * ni}};
+    char* d[12];
+    int rc = stage_upload(c, it, 12, 0, d, nullptr);
+    if (rc != PSI_OK) return rc;
+    cudaStream_t st = c->stream;
+    CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
+    NodeTableView t = table_view(c);
+    for (int cls = 0; cls < kNumClasses; ++cls) {
+        if (!(mask & (1u << cls))) continue;
+        CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+        contour_kernel_t k = c->table_in_smem ? contour_kernel_for<true>(cls) : contour_kernel_for<false>(cls);
+        k<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+            t, c->d_dists, n_items, (const int*)d[0], (const double*)d[1], (const double*)d[2],
+            (const double*)d[3], (const int*)d[4], (const double2*)d[5], (const double*)d[6],
+            (const double*)d[7], (const int*)d[8], (double2*)c->d_contour_scratch, cap, (int*)d[9],
+            (int*)d[10], (int*)d[11], c->d_counter, c->d_counter + 4);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    unsigned long long cnt[2] = {0, 0};
+    CK(cudaMemcpyAsync(counts, d[9], 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, d[10], 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_points, d[11], 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cnt, c->d_counter + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (stats) { stats[0] = 1; stats[1] = (long long)cnt[1]; }
+    return PSI_OK;
+}
 
 int psi_measure_fp64_peak(psi_ctx* c, int reps, double* tflops) {
     if (!c || !tflops || reps < 1) return fail(PSI_ERR_ARG, "psi_measure_fp64_peak: bad argument");

@@ -13,6 +13,7 @@
 // and remain the general path (verbose runs, count_roots=True inside PSIMode, user callables).
 #include <dlfcn.h>
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -51,6 +52,12 @@ struct ScopedTimer {
         cnt += 1;
     }
 };
+
+int g_threads = 0;          // host threads of the engine (0 = OpenMP default)
+int engine_threads() {
+    int n = g_threads > 0 ? g_threads : omp_get_max_threads();
+    return n < 1 ? 1 : n;
+}
 
 struct Lapack {
     void* h_np = nullptr;
@@ -471,15 +478,14 @@ struct ModeItem {
     std::vector<cd> guesses;
     MT19937 rng;
     // state
-    enum Phase { INIT, SAMPLES, GUESS, ANALYZE, SECANT_A, SECANT_B, ZOOM, DONE, FAILED } phase = INIT;
+    enum Phase { INIT, SAMPLES, GUESS, ANALYZE, POLISH, ZOOM, DONE, FAILED } phase = INIT;
     std::vector<cd> zs, fs, req, zeros_start, out_roots, zoom;
     AAA ra;
-    Secant sec;
-    int level = 0, iguess = 0, izero = 0, izoom = 0, max_iter = 0, n_calls = 0, max_conv_iter = 0;
+    int level = 0, iguess = 0, izoom = 0, max_iter = 0, n_calls = 0, max_conv_iter = 0;
     double zoom_dx = 0;
-    cd w0_cur;
-    std::vector<cd> w0;               // start values of the current polish (mutated on restart)
-    std::vector<cd> polished;
+    std::vector<cd> w0;               // start values handed to the polish kernel (K3)
+    std::vector<cd> polished;         // its answer: roots, or the sentinel -1j
+    int polish_calls = 0, polish_conv = 0, polish_status = 0;
     std::string error;
 
     void request_box(double sx, double sy, cd centre) {
@@ -495,11 +501,6 @@ struct ModeItem {
     void absorb_samples(const cd* vals) {
         for (size_t i = 0; i < req.size(); ++i) { zs.push_back(req[i]); fs.push_back(vals[i]); }
         n_calls += (int)req.size();
-    }
-    double polish_xtol() const {
-        double t = 1.48e-8;
-        for (cd w : w0) t = std::min(t, fabs(w.imag() * 1e-5));
-        return t;
     }
     // zeros inside the search rectangle
     void zeros_in_domain(std::vector<cd>& z) {
@@ -552,18 +553,6 @@ struct ModeItem {
         if (level < max_zoom) max_iter = n_sample;
         if (w0.empty() && have_least) { w0.push_back(least); max_iter = 5; }
         polished.assign(w0.size(), cd(0, 0));
-        izero = 0;
-    }
-
-    // start the secant for zero `izero`, or finish the polish; returns true when a request is pending
-    bool next_zero() {
-        if (izero >= (int)w0.size()) return false;
-        cd r2[2];
-        w0_cur = w0[izero];
-        sec.start(w0_cur, second_point(w0_cur, 1.0e-6), 5, polish_xtol(), r2);
-        req.assign(r2, r2 + 2);
-        phase = SECANT_A;
-        return true;
     }
 
     // after the polish of a level: return, or open zoom domains (psi_mode.py:312-331)
@@ -618,36 +607,16 @@ struct ModeItem {
                     break;
                 case ANALYZE:
                     analyze();
-                    if (next_zero()) return;
+                    if (!w0.empty()) { phase = POLISH; req.clear(); return; }   // K3 takes over
                     if (after_polish()) return;
                     return;
-                case SECANT_A:
-                case SECANT_B: {
-                    cd r1[2];
-                    const int n = sec.feed(vals, r1);
-                    if (n > 0) { req.assign(r1, r1 + n); return; }
-                    n_calls += sec.calls;
-                    if (phase == SECANT_A && !sec.converged &&
-                        abs_c(sec.root - w0_cur) / abs_c(w0_cur) < 1 && max_iter > 5) {
-                        w0[izero] = sec.root;                     // continue from where it stopped
-                        w0_cur = sec.root;
-                        cd r2[2];
-                        sec.start(w0_cur, second_point(w0_cur, 1.0e-6), max_iter, polish_xtol(), r2);
-                        req.assign(r2, r2 + 2);
-                        phase = SECANT_B;
-                        return;
-                    }
-                    if (sec.converged && dom.is_in(sec.root)) {
-                        max_conv_iter = std::max(max_conv_iter, sec.iterations);
-                        polished[izero] = sec.root;
-                    } else {
-                        polished[izero] = cd(0.0, -1.0);          // sentinel, outside every domain
-                    }
-                    ++izero;
-                    if (next_zero()) return;
+                case POLISH:
+                    // `polished`, polish_calls, polish_conv were filled in by the polish kernel
+                    if (polish_status != 0) throw EngineError{"tol too small (<= 0) in secant"};
+                    n_calls += polish_calls;
+                    max_conv_iter = std::max(max_conv_iter, polish_conv);
                     if (after_polish()) return;
                     return;
-                }
                 case ZOOM:
                     absorb_samples(vals);
                     ++izoom;
@@ -672,102 +641,50 @@ struct ModeItem {
 };
 
 // ------------------------------------------------------------------------------------------------
-// ClosedPath.count_roots as a resumable machine
+// lock-step driver: per round ONE K1 launch for the union of all sample requests and ONE K3 launch
+// for the union of all polish requests
 // ------------------------------------------------------------------------------------------------
-struct ContourItem {
-    int pidx = 0, max_iter = 100, iter = 0, count = 0;
-    double tol = 0.1, max_step = 0.1;
-    std::vector<cd> pts, fv, req;
-    std::vector<int> where;
-    enum Phase { INIT, CORNERS, REFINE, DONE, FAILED } phase = INIT;
-    std::string error;
-
-    // decide which edges to bisect; false when nothing is to be added
-    bool select() {
-        const int n = (int)pts.size();
-        std::vector<double> len(n), ang(n);
-        for (int i = 0; i < n; ++i) {
-            len[i] = abs_c(pts[i] - pts[(i + n - 1) % n]);
-            ang[i] = atan2(fv[i].imag(), fv[i].real());
-        }
-        where.clear();
-        req.clear();
-        for (int i = 0; i < n; ++i) {
-            const int im = (i + n - 1) % n, ip = (i + 1) % n;
-            const double jump = ang[i] - ang[im];
-            const bool uneven = (len[i] > 2 * len[im]) || (len[i] > 2 * len[ip]);
-            if (((fabs(jump) > tol) || uneven || (len[i] > max_step)) && len[i] > 1.0e-8) {
-                where.push_back(i);
-                req.push_back(0.5 * (pts[i] + pts[im]));
-            }
-        }
-        return !where.empty();
-    }
-    void finish() {
-        const int n = (int)pts.size();
-        double sum = 0;
-        for (int i = 0; i < n; ++i) {
-            const cd a = fv[i] + cd(0, 1.0e-30), b = fv[(i + 1) % n] + cd(0, 1.0e-30);
-            const cd q = np_div(b, a);
-            sum += atan2(q.imag(), q.real());
-        }
-        const double winding = 0.5 * sum / M_PI, nearest = rint(winding);
-        if (fabs(winding - nearest) < 1.0e-6) { count = (int)nearest; phase = DONE; }
-        else { error = "No convergence to integer number of roots"; phase = FAILED; }
-    }
-    void advance(const cd* vals) {
-        if (phase == INIT) { req = pts; phase = CORNERS; return; }
-        if (phase == CORNERS) {
-            fv.assign(vals, vals + pts.size());
-        } else if (phase == REFINE) {
-            for (size_t k = 0; k < where.size(); ++k)
-                if (!finite_c(vals[k])) { error = "Infinite value in f_add"; phase = FAILED; return; }
-            std::vector<cd> np_, nf_;
-            size_t k = 0;
-            for (int i = 0; i < (int)pts.size(); ++i) {
-                if (k < where.size() && where[k] == i) { np_.push_back(req[k]); nf_.push_back(vals[k]); ++k; }
-                np_.push_back(pts[i]); nf_.push_back(fv[i]);
-            }
-            pts.swap(np_); fv.swap(nf_);
-            ++iter;
-        }
-        if (iter >= max_iter) { error = "Maximum number of iterations exceeded"; phase = FAILED; return; }
-        if (select()) { phase = REFINE; return; }
-        finish();
-    }
-};
-
-// ------------------------------------------------------------------------------------------------
-// lock-step driver: one K1 launch per pass over the union of all requests
-// ------------------------------------------------------------------------------------------------
-template <class Item>
-int run_lockstep(psi_ctx* ctx, std::vector<Item>& items, int n_params, const int* dist, const double* kx,
-                 const double* kz, const double* alpha, long long* passes_out, long long* evals_out,
-                 long long* usec_logic = nullptr, long long* usec_eval = nullptr) {
+int run_lockstep(psi_ctx* ctx, std::vector<ModeItem>& items, int n_params, const int* dist, const double* kx,
+                 const double* kz, const double* alpha, long long* stats) {
     typedef std::chrono::steady_clock clk;
     auto us = [](clk::time_point a, clk::time_point b) {
         return (long long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
     };
-    long long t_logic = 0, t_eval = 0;
+    long long t_logic = 0, t_eval = 0, rounds = 0, evals = 0, launches = 0, polish_evals = 0;
     auto t0 = clk::now();
+    const int nt = engine_threads();
     std::vector<int> live;
     for (int i = 0; i < (int)items.size(); ++i) live.push_back(i);
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nt)
     for (int k = 0; k < (int)live.size(); ++k) items[live[k]].advance(nullptr);
-    long long passes = 0, evals = 0;
-    std::vector<cd> w, D;
-    std::vector<int> pidx;
+    std::vector<cd> w, D, pw, pout;
+    std::vector<int> pidx, ppidx, poff, pmax, pcalls, pconv, pstat;
+    std::vector<double> pdom;
     std::vector<size_t> off;
     for (;;) {
         std::vector<int> pend;
         for (int i : live)
-            if (items[i].phase != Item::DONE && items[i].phase != Item::FAILED) pend.push_back(i);
+            if (items[i].phase != ModeItem::DONE && items[i].phase != ModeItem::FAILED) pend.push_back(i);
         if (pend.empty()) break;
+        // sample requests -> K1
         w.clear(); pidx.clear(); off.assign(pend.size() + 1, 0);
+        // polish requests -> K3
+        pw.clear(); ppidx.clear(); poff.assign(1, 0); pmax.clear(); pdom.clear();
+        std::vector<int> pitem;
         for (size_t k = 0; k < pend.size(); ++k) {
-            const Item& it = items[pend[k]];
+            ModeItem& it = items[pend[k]];
             off[k] = w.size();
-            for (cd z : it.req) { w.push_back(z); pidx.push_back(it.pidx); }
+            if (it.phase == ModeItem::POLISH) {
+                pitem.push_back(pend[k]);
+                ppidx.push_back(it.pidx);
+                for (cd z : it.w0) pw.push_back(z);
+                poff.push_back((int)pw.size());
+                pmax.push_back(it.max_iter);
+                pdom.push_back(it.dom.xmin); pdom.push_back(it.dom.xmax);
+                pdom.push_back(it.dom.ymin); pdom.push_back(it.dom.ymax);
+            } else {
+                for (cd z : it.req) { w.push_back(z); pidx.push_back(it.pidx); }
+            }
         }
         off[pend.size()] = w.size();
         D.resize(w.size());
@@ -777,20 +694,37 @@ int run_lockstep(psi_ctx* ctx, std::vector<Item>& items, int n_params, const int
             int rc = psi_internal_eval_indexed(ctx, (long long)w.size(), pidx.data(), n_params, dist, kx, kz,
                                                alpha, (const double*)w.data(), (double*)D.data());
             if (rc != PSI_OK) return rc;
+            ++launches;
+            evals += (long long)w.size();
+        }
+        if (!pitem.empty()) {
+            const int np = (int)pitem.size();
+            pout.resize(pw.size()); pcalls.assign(np, 0); pconv.assign(np, 0); pstat.assign(np, 0);
+            long long pe = 0;
+            int rc = psi_internal_polish(ctx, np, ppidx.data(), n_params, dist, kx, kz, alpha, pdom.data(),
+                                         poff.data(), (double*)pw.data(), pmax.data(), (double*)pout.data(),
+                                         pcalls.data(), pconv.data(), pstat.data(), &pe);
+            if (rc != PSI_OK) return rc;
+            ++launches;
+            polish_evals += pe;
+            for (int k = 0; k < np; ++k) {
+                ModeItem& it = items[pitem[k]];
+                it.polished.assign(pout.begin() + poff[k], pout.begin() + poff[k + 1]);
+                it.polish_calls = pcalls[k]; it.polish_conv = pconv[k]; it.polish_status = pstat[k];
+            }
         }
         t0 = clk::now();
         t_eval += us(t1, t0);
-        ++passes;
-        evals += (long long)w.size();
-#pragma omp parallel for schedule(dynamic, 4)
+        ++rounds;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nt)
         for (int k = 0; k < (int)pend.size(); ++k) items[pend[k]].advance(D.data() + off[k]);
         live.swap(pend);
     }
     t_logic += us(t0, clk::now());
-    if (passes_out) *passes_out = passes;
-    if (evals_out) *evals_out = evals;
-    if (usec_logic) *usec_logic = t_logic;
-    if (usec_eval) *usec_eval = t_eval;
+    if (stats) {
+        stats[0] = rounds; stats[1] = evals + polish_evals; stats[3] = t_logic; stats[4] = t_eval;
+        stats[5] = launches; stats[6] = polish_evals;
+    }
     return PSI_OK;
 }
 
@@ -817,6 +751,9 @@ int psi_engine_bind_lapack(const char* numpy_openblas64, const char* scipy_openb
     return PSI_OK;
 }
 
+/* host threads used by the engine's per-item logic (AAA etc.); n <= 0 restores the OpenMP default */
+void psi_engine_set_threads(int n) { g_threads = n; }
+
 /* profiling aid: {svd calls, svd ns, eig calls, eig ns} accumulated since load */
 void psi_engine_counters(long long out[4]) {
     out[0] = g_cnt_svd; out[1] = g_us_svd; out[2] = g_cnt_eig; out[3] = g_us_eig;
@@ -841,8 +778,8 @@ int psi_mode_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double
         for (int g = guess_off[i]; g < guess_off[i + 1]; ++g) m.guesses.push_back(cd(guesses[2 * g], guesses[2 * g + 1]));
         if (m.n_sample < 2) return psi_internal_fail(PSI_ERR_ARG, "n_sample must be at least 2");
     }
-    long long passes = 0, evals = 0, tl = 0, te = 0;
-    int rc = run_lockstep(ctx, items, n_items, dist, kx, kz, alpha, &passes, &evals, &tl, &te);
+    long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int rc = run_lockstep(ctx, items, n_items, dist, kx, kz, alpha, st);
     if (rc != PSI_OK) return rc;
     int failed = 0;
     for (int i = 0; i < n_items; ++i) {
@@ -858,35 +795,8 @@ int psi_mode_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double
         }
         if (n_calls) n_calls[i] = m.n_calls;
     }
-    if (stats) { stats[0] = passes; stats[1] = evals; stats[2] = failed; stats[3] = tl; stats[4] = te; }
-    return PSI_OK;
-}
-
-int psi_contour_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
-                           const double* alpha, const int* z_off, const double* z_list, const double* tol,
-                           const double* max_step, const int* max_iter, int* counts, int* status,
-                           int* n_points, long long* stats) {
-    if (!ctx || n_items < 0 || !dist || !kx || !kz || !alpha || !z_off || !z_list || !tol || !max_step ||
-        !max_iter || !counts || !status)
-        return psi_internal_fail(PSI_ERR_ARG, "psi_contour_batch_host: bad argument");
-    std::vector<ContourItem> items(n_items);
-    for (int i = 0; i < n_items; ++i) {
-        ContourItem& c = items[i];
-        c.pidx = i; c.tol = tol[i]; c.max_step = max_step[i]; c.max_iter = max_iter[i];
-        for (int k = z_off[i]; k < z_off[i + 1]; ++k) c.pts.push_back(cd(z_list[2 * k], z_list[2 * k + 1]));
-        if (c.pts.size() < 2) return psi_internal_fail(PSI_ERR_ARG, "a contour needs at least 2 points");
-    }
-    long long passes = 0, evals = 0;
-    int rc = run_lockstep(ctx, items, n_items, dist, kx, kz, alpha, &passes, &evals);
-    if (rc != PSI_OK) return rc;
-    for (int i = 0; i < n_items; ++i) {
-        const ContourItem& c = items[i];
-        status[i] = c.phase == ContourItem::DONE ? 0
-                    : (c.error == "Infinite value in f_add" ? 2 : 1);     // 1 = RuntimeError, 2 = ValueError
-        counts[i] = c.phase == ContourItem::DONE ? c.count : -666;          // complex_roots_mpi.py:171-174
-        if (n_points) n_points[i] = (int)c.pts.size();
-    }
-    if (stats) { stats[0] = passes; stats[1] = evals; }
+    st[2] = failed;
+    if (stats) for (int k = 0; k < 7; ++k) stats[k] = st[k];
     return PSI_OK;
 }
 

@@ -12,3 +12,12 @@ int psi_internal_fail(int code, const std::string& msg);
 int psi_internal_eval_indexed(psi_ctx* ctx, long long n, const int* pidx, int n_params, const int* dist,
                               const double* kx, const double* kz, const double* alpha, const double* w,
                               double* D);
+
+// K3 for n_items polish jobs (HOST arrays): item k polishes the start values w0[off[k]..off[k+1]) of the
+// dispersion relation of parameter row pidx[k] inside the rectangle dom[4k..4k+4) with at most
+// max_iter[k] secant iterations; out gets one complex per start value (root or the sentinel -1j),
+// n_calls / max_conv / status one int per item; *evals the number of D evaluations performed.
+int psi_internal_polish(psi_ctx* ctx, int n_items, const int* pidx, int n_params, const int* dist,
+                        const double* kx, const double* kz, const double* alpha, const double* dom,
+                        const int* off, double* w0, const int* max_iter, double* out, int* n_calls,
+                        int* max_conv, int* status, long long* evals);

@@ -14,8 +14,10 @@
 
 #if defined(__CUDACC__)
 #define PSI_HD __host__ __device__ __forceinline__
+#define PSI_NOINLINE __host__ __device__ __noinline__
 #else
 #define PSI_HD inline
+#define PSI_NOINLINE
 #endif
 
 namespace psi {

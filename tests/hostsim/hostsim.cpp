@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include "../../psitools_public_b200/csrc/psi_batch.cuh"
+#include "../../psitools_public_b200/csrc/psi_internal.hpp"
 #include "../../psitools_public_b200/csrc/psi_table.hpp"
 
 using namespace psi;
@@ -56,11 +58,86 @@ int psi_internal_eval_indexed(psi_ctx* c, long long n, const int* pidx, int n_pa
     return PSI_OK;
 }
 
+// CPU stand-in for the class dispatch of kernels K2/K3: run F with the WarpEval of the point's class
+template <class F>
+static void with_eval(psi_ctx* c, int dist, double kx, double kz, double alpha, F&& body) {
+    const DistParams& d = c->dists[dist];
+    auto go = [&](auto ev) {
+        ev.t = &c->view; ev.d = &d; ev.kx = kx; ev.kz = kz; ev.alpha = alpha; ev.nodes = 0; ev.evals = 0;
+        body(ev);
+    };
+    switch (point_class(d, alpha)) {
+    case 0: go(WarpEval<WarpOne, 0, false>()); break;
+    case 1: go(WarpEval<WarpOne, 0, true>()); break;
+    case 2: go(WarpEval<WarpOne, 1, false>()); break;
+    case 3: go(WarpEval<WarpOne, 1, true>()); break;
+    case 4: go(WarpEval<WarpOne, 2, false>()); break;
+    case 5: go(WarpEval<WarpOne, 2, true>()); break;
+    case 6: go(WarpEval<WarpOne, 3, false>()); break;
+    default: go(WarpEval<WarpOne, 3, true>()); break;
+    }
+}
+
+int psi_internal_polish(psi_ctx* c, int n_items, const int* pidx, int n_params, const int* dist,
+                        const double* kx, const double* kz, const double* alpha, const double* dom,
+                        const int* off, double* w0, const int* max_iter, double* out, int* n_calls,
+                        int* max_conv, int* status, long long* evals) {
+    (void)n_params;
+    long long total = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+    for (int i = 0; i < n_items; ++i) {
+        const int pi = pidx[i];
+        with_eval(c, dist[pi], kx[pi], kz[pi], alpha[pi], [&](auto& ev) {
+            RectDom rd{dom[4 * i], dom[4 * i + 1], dom[4 * i + 2], dom[4 * i + 3]};
+            int conv = 0, st = 0;
+            n_calls[i] = polish_run(ev, rd, reinterpret_cast<cx*>(w0) + off[i], off[i + 1] - off[i], max_iter[i],
+                                    reinterpret_cast<cx*>(out) + off[i], &conv, &st);
+            max_conv[i] = conv; status[i] = st;
+            total += ev.evals;
+        });
+    }
+    if (evals) *evals = total;
+    return PSI_OK;
+}
+
 #include "../../psitools_public_b200/csrc/psi_engine.cu"
 
 extern "C" {
 
 const char* hs_last_error(void) { return g_err.c_str(); }
+
+int psi_polish_batch_host(psi_ctx* c, int n_items, const int* dist, const double* kx, const double* kz,
+                          const double* alpha, const double* domain, const int* w0_off, const double* w0,
+                          const int* max_iter, double* roots, int* n_calls, int* max_conv, int* status) {
+    std::vector<int> pidx(n_items);
+    for (int i = 0; i < n_items; ++i) pidx[i] = i;
+    std::vector<double> w0copy(w0, w0 + 2 * (size_t)w0_off[n_items]);
+    return psi_internal_polish(c, n_items, pidx.data(), n_items, dist, kx, kz, alpha, domain, w0_off,
+                               w0copy.data(), max_iter, roots, n_calls, max_conv, status, nullptr);
+}
+
+int psi_contour_batch_host(psi_ctx* c, int n_items, const int* dist, const double* kx, const double* kz,
+                           const double* alpha, const int* z_off, const double* z_list, const double* tol,
+                           const double* max_step, const int* max_iter, int* counts, int* status,
+                           int* n_points, long long* stats) {
+    const int cap = 4096;
+    long long total = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+    for (int i = 0; i < n_items; ++i) {
+        with_eval(c, dist[i], kx[i], kz[i], alpha[i], [&](auto& ev) {
+            std::vector<cx> buf(4 * (size_t)cap);
+            const int o = z_off[i], n0 = z_off[i + 1] - o;
+            for (int k = 0; k < n0; ++k) buf[k] = cx(z_list[2 * (o + k)], z_list[2 * (o + k) + 1]);
+            int cnt = -666, np = n0;
+            status[i] = contour_run(ev, buf.data(), buf.data() + cap, buf.data() + 2 * cap, buf.data() + 3 * cap,
+                                    n0, cap, tol[i], max_step[i], max_iter[i], &cnt, &np);
+            counts[i] = cnt; n_points[i] = np;
+            total += ev.evals;
+        });
+    }
+    if (stats) { stats[0] = 1; stats[1] = total; }
+    return PSI_OK;
+}
 
 psi_ctx* hs_ctx_create(const double* xj, const double* wj, int n, int max_m, double eps) {
     psi_ctx* c = new psi_ctx();

@@ -143,3 +143,48 @@ def test_mode_with_count_and_guess(backend):
     assert len(roots) >= 1
     assert min(abs(r - (-1.004879704650626 + 0.0008946325671658642j)) for r in roots) < 1e-9
     assert pm.n_function_call >= 40
+
+
+def test_polish_kernel_k3(backend):
+    """Kernel K3 (two-stage secant polish on the device) against the Python statement of the same
+    logic (psi_mode.polish_machine) driven through the lock-step engine: same roots, same sentinel
+    pattern, same number of dispersion evaluations."""
+    from psitools_public_b200 import PSIMode, TanhSinh
+    from psitools_public_b200._engine import Job, run_lockstep
+    from psitools_public_b200.psi_mode import ModeTrace, polish_machine
+    pm = PSIMode(3.0, [1e-8, 1.0], [-2, 2], [1e-8, 1], tanhsinh_integrator=TanhSinh())
+    ctx, did = pm.psi_dispersion.ctx, pm.psi_dispersion.dist_id
+    root = -1.004879704650626 + 0.0008946325671658642j
+    starts = [[root*(1 + 1e-4), 0.5 + 0.3j, -1.2 + 0.05j], [root + 1e-5], [1.5 + 0.9j]]
+    ks = [(0.1, 10.0), (0.1, 10.0), (0.1, 10.0)]
+    max_iter = [20, 100, 5]
+    got, ncalls, mconv, status = ctx.polish_batch([did]*3, [k[0] for k in ks], [k[1] for k in ks], [0.0]*3,
+                                                  [[-2, 2, 1e-8, 1]]*3, starts, max_iter)
+    assert list(status) == [0, 0, 0]
+    for i in range(3):
+        tr = ModeTrace()
+        pm._sync_cfg()
+        job = Job(polish_machine(pm.cfg, starts[i], max_iter[i], tr), did, ks[i][0], ks[i][1], 0.0)
+        run_lockstep(ctx, [job])
+        kept = [z for z in got[i] if pm.domain.is_in(z)]
+        assert same_root_sets(kept, list(job.result)), (i, got[i], job.result)
+        assert ncalls[i] == tr.n_function_call, (i, ncalls[i], tr.n_function_call)
+    assert abs(got[0][0] - root) < 1e-9 and abs(got[1][0] - root) < 1e-9
+    assert mconv[1] >= 1
+    # a start value on the real axis makes the reference's tolerance zero -> ValueError there
+    _, _, _, st = ctx.polish_batch([did], [0.1], [10.0], [0.0], [[-2, 2, 1e-8, 1]], [[0.3 + 0j]], [20])
+    assert st[0] == 1
+
+
+def test_contour_kernel_k2_status(backend):
+    """Kernel K2 error paths: max_iter exhausted -> RuntimeError in the reference -> count -666."""
+    from psitools_public_b200 import PSIDispersion, TanhSinh
+    pd = PSIDispersion(3.0, [1e-8, 1.0], tanhsinh_integrator=TanhSinh())
+    z = [-2.0 + 2e-7j, 2.0 + 2e-7j, 2.0 + 2.0j, -2.0 + 2.0j]
+    counts, status, npts, st = pd.ctx.contour_batch([pd.dist_id]*2, [0.1, 0.1], [10.0, 10.0], [0.0, 0.0],
+                                                    [z, z], [0.1, 0.1], [0.1, 0.1], [3, 100])
+    assert counts[0] == -666 and status[0] == 2
+    assert counts[1] == 1 and status[1] == 0
+    gold = load("contour.json")["cases"][3]
+    assert abs(npts[1] - gold["n_points"]) <= 0.05*gold["n_points"]
+    assert st["evals"] >= npts[1]
