@@ -353,6 +353,9 @@ def run_b200(args):
                  "pixels": len(items), "pixels_with_roots": int(sum(len(v) > 0 for v in res.values())),
                  "rank0_passes": st.get("passes"), "rank0_D_evals": st.get("evals"),
                  "rank0_engine_seconds": st.get("seconds"), "rank0_launches": ctx.launch_count - l0,
+                 "rank0_host_logic_seconds": st.get("host_logic_seconds"),
+                 "rank0_device_seconds": st.get("device_seconds"),
+                 "rank0_D_evals_in_K3": st.get("polish_evals"), "host_threads": ctx.default_engine_threads(),
                  "engine": st.get("engine")}
 
     t = torch.tensor([ms_total, ms_kernel, e2e_s, modes["seconds"] if modes else 0.0],

@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Secondary workloads (not part of the bench.py contract): root-count map (kernel K2) and adaptive
+grid refinement (BASELINE config 4 family) on one GPU.  Prints one JSON line per workload."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def count_map(n_axis):
+    """example_psicountgrid.py family: roots of D inside [-2,2]x[2e-7,2] on an n_axis^2 log K grid."""
+    from psitools_public_b200 import TanhSinhNoDeepCopy, complex_roots_mpi
+    ts = TanhSinhNoDeepCopy()
+    z_list = [-2.0 + 2e-7j, 2.0 + 2e-7j, 2.0 + 2.0j, -2.0 + 2.0j]
+    ax = np.logspace(-1, 3, n_axis)
+    kxg, kzg = np.meshgrid(ax, ax)
+    init = {'stokes_range': [1e-8, 1.0], 'dust_to_gas_ratio': 3.0, 'size_distribution_power': 3.5,
+            'tanhsinh_integrator': ts}
+    items = [{'PSIDispersion.__init__': init,
+              'dispersion': {'wave_number_x': float(a), 'wave_number_z': float(b), 'viscous_alpha': 0.0},
+              'z_list': z_list, 'count_roots': {'tol': 0.1}} for a, b in zip(kxg.ravel(), kzg.ravel())]
+    ms = complex_roots_mpi.MpiScheduler(time.time(), 1e9, verbose=False)
+    ms.run_all(items[:8])
+    t0 = time.perf_counter()
+    res = ms.run_all(items)
+    dt = time.perf_counter() - t0
+    counts = np.array([res[i] for i in range(len(items))])
+    st = ms.last_stats
+    print(json.dumps({"workload": "root-count map %dx%d (K2 contour_kernel)" % (n_axis, n_axis),
+                      "seconds": dt, "contours_per_s": len(items)/dt, "D_evals": st.get("evals"),
+                      "contour_points": st.get("points"), "failed(-666)": int(np.sum(counts == -666)),
+                      "histogram": {str(k): int(v) for k, v in zip(*np.unique(counts, return_counts=True))}}),
+          flush=True)
+
+
+def refine(nbase, fills, reruns):
+    """test_psi_grid_refine.py's PowerBump distribution on the default krange (-1, 3)."""
+    from psitools_public_b200 import PowerBump, PSIGridRefiner, SizeDensity, TanhSinhNoDeepCopy
+    pb = PowerBump(amin=1e-8, aP=0.1, aL=2.0/3.0*0.1, aR=0.156, bumpfac=2.0)
+    sd = SizeDensity(pb.sigma0, [1e-8, 0.156])
+    sd.poles = [pb.get_discontinuity()]
+    baseargs = {'__init__': {'stokes_range': [1e-8, 0.156], 'dust_to_gas_ratio': 10.0, 'size_density': sd,
+                             'real_range': [-2.0, 2.0], 'imag_range': [1e-7, 1.0], 'n_sample': 20,
+                             'max_zoom_domains': 1, 'tol': 1.0e-13, 'clean_tol': 1e-4,
+                             'tanhsinh_integrator': TanhSinhNoDeepCopy()},
+                'calculate': {'wave_number_x': None, 'wave_number_z': None, 'guess_roots': []},
+                'random_seed': 2}
+    gr = PSIGridRefiner('bench', baseargs=baseargs, nbase=(nbase, nbase), reruns=reruns, krange=(-1, 3))
+    t0 = time.perf_counter()
+    gr.run_basegrid()
+    times = [time.perf_counter() - t0]
+    for _ in range(fills):
+        gr.fill_in_grid()
+        times.append(time.perf_counter() - t0)
+    g = gr.grids[-1]
+    runs = sum(n for _, n, _ in gr.sweep_log) + gr.grids[0]['runs'].size
+    with_roots = int(sum(len(g['results'][r]) > 0 for r in g['runs'].ravel() if r >= 0))
+    print(json.dumps({"workload": "PSIGridRefiner PowerBump nbase=%d, %d fill-ins, reruns=%d -> %dx%d map"
+                                  % (nbase, fills, reruns, g['runs'].shape[0], g['runs'].shape[1]),
+                      "seconds_cumulative": times, "psimode_runs": int(runs),
+                      "runs_per_s": runs/times[-1], "sweeps": len(gr.sweep_log),
+                      "pixels_with_roots": with_roots}), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--count-grid", type=int, default=32)
+    ap.add_argument("--nbase", type=int, default=16)
+    ap.add_argument("--fills", type=int, default=2)
+    ap.add_argument("--reruns", type=int, default=3)
+    a = ap.parse_args()
+    if a.count_grid > 0:
+        count_map(a.count_grid)
+    if a.nbase > 0:
+        refine(a.nbase, a.fills, a.reruns)

@@ -186,13 +186,18 @@ struct NodeGen {
     // nodes at +x (p) and -x (n)
     PSI_HD void pair(double x, NodeVals& p, NodeVals& n) const {
         const double h = half * x;
+        if (NK == kNodePowerSqrt) {
+            // e^{u/2} weights: exponentiate h/2 once; E = R^2, 1/E = (1/R)^2
+            const double R = exp(0.5 * h), Ri = fast_rcp(R);
+            const double E = R * R, Ei = Ri * Ri;
+            p.tau = tm * E;  p.it = itm * Ei;  p.wt = cw * R;
+            n.tau = tm * Ei; n.it = itm * E;   n.wt = cw * Ri;
+            return;
+        }
         const double E = exp(h), Ei = fast_rcp(E);
         p.tau = tm * E;  p.it = itm * Ei;
         n.tau = tm * Ei; n.it = itm * E;
-        if (NK == kNodePowerSqrt) {
-            const double rs = fast_rsqrt(E);
-            p.wt = cw * (E * rs); n.wt = cw * rs;
-        } else if (NK == kNodePowerGen) {
+        if (NK == kNodePowerGen) {
             const double G = exp(qe * h);
             p.wt = cw * G; n.wt = cw * fast_rcp(G);
         } else {
@@ -218,6 +223,7 @@ struct PointConst {
     double A2;       // 2*denom
     double j0p;      // 1 + J0
     double j1, dn, vgx, vgy;
+    double kxA2, mkxdn, kxvgx, kxvgy;   // kx*2*denom, -kx*denom, kx*vgx, kx*vgy
 };
 
 PSI_HD PointConst make_point(const DistParams& d, cx w, double kx, double kz, double alpha) {
@@ -229,6 +235,7 @@ PSI_HD PointConst make_point(const DistParams& d, cx w, double kx, double kz, do
     p.ic0 = mul_i(p.c0);
     p.c1 = w.im * w.im + 1.0;
     p.A2 = 2 * d.denom; p.j0p = 1 + d.j0; p.j1 = d.j1; p.dn = d.denom; p.vgx = d.vgx; p.vgy = d.vgy;
+    p.kxA2 = kx * p.A2; p.mkxdn = -kx * d.denom; p.kxvgx = kx * d.vgx; p.kxvgy = kx * d.vgy;
     return p;
 }
 
@@ -253,19 +260,35 @@ PSI_HD void m_apply_scales(const PointConst& p, cx* m) {
 template <bool VISC>
 PSI_HD void m_node(const PointConst& p, const NodeVals& nv, double wq, cx* acc) {
     const double tau = nv.tau, it = nv.it;
-    const double r1 = fast_rcp(fma(tau, tau, 1.0));
-    const double ux = p.A2 * (p.j1 - tau * p.j0p) * r1;            // :80
-    const double uy = -p.dn * (p.j0p + tau * p.j1) * r1;           // :81
-    const double s1 = (ux - p.vgx) * p.kx, s3 = (uy - p.vgy) * p.kx;
-    const double dr = fma(p.kx, ux, -p.w.re);                      // Re delta = Re d
-    const double di = -p.w.im - it;                                // Im d
-    const cx den = fast_recip(cx(1.0 - (dr * dr - di * di), -2.0 * dr * di));
-    const cx rd = fast_recip(cx(dr, di));
+    const double t1 = fma(tau, tau, 1.0);                          // 1 + tau^2
+    // kx*ux, kx*uy from :80-81 with the common factor kx/(1+tau^2) applied once
+    const double nx = fma(-tau, p.j0p, p.j1);                      // j1 - tau*(1+j0)
+    const double ny = fma(tau, p.j1, p.j0p);                       // (1+j0) + tau*j1
+    const double dr_num = p.kxA2 * nx;                             // kx*ux*(1+tau^2)
+    // d = kx*ux - w - i/tau                                         (:214);  dr = Re d, di = Im d
+    const double di = -p.w.im - it;
+    // the four real denominators are inverted together (one MUFU seed + Newton, products back out):
+    //   n1 = 1+tau^2,  n2 = |1-d^2|^2,  n3 = |d|^2,  n4 = |w - kx*ux + i(k^2 Dtau + 1e-10)|^2
+    const double r1 = fast_rcp(t1);
+    const double kxux = dr_num * r1;
+    const double s1 = kxux - p.kxvgx;                              // (ux - vgx)*kx
+    const double s3 = fma(p.mkxdn * ny, r1, -p.kxvgy);             // (uy - vgy)*kx
+    const double dr = kxux - p.w.re;
+    const double dr2 = dr * dr;
+    const cx one_md2(fma(di, di, 1.0 - dr2), -2.0 * dr * di);      // 1 - d^2
     double dif = 0.0;
     if (VISC) dif = (1.0 + tau + 4.0 * tau * tau) * p.nu * (r1 * r1);   // :390
-    const cx dv = fast_recip(cx(-dr, p.w.im + (p.k2 * dif + 1.0e-10)));
+    const double yi = p.w.im + (p.k2 * dif + 1.0e-10);             // Im(w - kx*ux + i(...)); Re = -dr
+    const double n2 = norm2(one_md2), n3 = fma(di, di, dr2), n4 = fma(yi, yi, dr2);
+    const double p23 = n2 * n3;
+    const double inv = fast_rcp(p23 * n4);
+    const double i4 = inv * p23, i23 = inv * n4;
+    const double i2 = i23 * n3, i3 = i23 * n2;
+    const cx den(one_md2.re * i2, -one_md2.im * i2);               // 1/(1-d^2)   (:215)
+    const cx rd(dr * i3, -di * i3);                                // 1/d
+    const cx dv(-dr * i4, -yi * i4);                               // (:288-289)
     // N = delta^2 - (i/tau) delta - 1, delta = (dr, -w.im)
-    const cx N(dr * dr - p.c1 - it * p.w.im, -dr * (2.0 * p.w.im + it));
+    const cx N(dr2 - p.c1 - it * p.w.im, -dr * (2.0 * p.w.im + it));
     const cx Nden = N * den;
     const cx P0(-dr * s1, 2.0 * s3 - di * s1);
     const cx R0(-dr * s3, -di * s3 - 0.5 * s1);
@@ -274,30 +297,32 @@ PSI_HD void m_node(const PointConst& p, const NodeVals& nv, double wq, cx* acc) 
     const cx X(fma(it, Ep.re, Nden.re), fma(it, Ep.im, Nden.im));         // A11D11... - 1
     const cx T1 = dv * cx(X.re + 1.0, X.im);
     const cx Y = dv * den;
-    const cx dvEp = dv * Ep, dvrd = dv * rd;
-    const cx S(dvEp.re + dvrd.im, dvEp.im - dvrd.re);                     // dv*Ep - i dv*rd
+    const cx S = dv * cx(Ep.re + rd.im, Ep.im - rd.re);                    // dv*(Ep - i rd)
     cx o0(fma(s1, T1.re, X.re), fma(s1, T1.im, X.im));
-    const cx o1(it * fma(s1, Y.re, den.re), it * fma(s1, Y.im, den.im));
-    cx o2(it * fma(s1, S.re, Ep.re), it * fma(s1, S.im, Ep.im));
+    const cx o1(fma(s1, Y.re, den.re), fma(s1, Y.im, den.im));            // * it (folded into g1)
+    cx o2(fma(s1, S.re, Ep.re), fma(s1, S.im, Ep.im));                    // * it
     cx o3(fma(it, fma(-0.5, den.re, Er.re), s3 * T1.re), fma(it, fma(-0.5, den.im, Er.im), s3 * T1.im));
     const double its3 = 2.0 * it * s3;
     const cx o4(fma(its3, Y.re, Nden.re), fma(its3, Y.im, Nden.im));
-    cx o5(it * fma(s3, S.re, Er.re), it * fma(s3, S.im, Er.im));
+    cx o5(fma(s3, S.re, Er.re), fma(s3, S.im, Er.im));                    // * it
     const cx o6(-(dr * rd.re + p.w.im * rd.im), -(dr * rd.im - p.w.im * rd.re));   // -delta*rd
+    const double g = wq * nv.wt * it;
+    const double g1 = g * it;
     if (VISC) {
         // W + I: q = i*Dtau*k2*dv*c0                                       (:338-345)
         const cx q = (dif * p.k2) * (dv * p.ic0);
         o0 = o0 + s1 * q; o3 = o3 + s3 * q;
-        // columns 3 carry kz = kappa*kx; with kappa deferred the W13/W23 terms are s1 q, s3 q
-        o2 = o2 + s1 * q; o5 = o5 + s3 * q;
+        // columns 3 carry kz = kappa*kx; with kappa deferred the W13/W23 terms are s1 q, s3 q and are
+        // NOT multiplied by 1/tau: accumulate them with g instead of g1
+        acc[2].re = fma(-g, s1 * q.im, acc[2].re); acc[2].im = fma(g, s1 * q.re, acc[2].im);
+        acc[5].re = fma(-g, s3 * q.im, acc[5].re); acc[5].im = fma(g, s3 * q.re, acc[5].im);
     }
-    const double g = wq * nv.wt * it;
     acc[0].re = fma(-g, o0.im, acc[0].re); acc[0].im = fma(g, o0.re, acc[0].im);
-    acc[1].re = fma(-g, o1.im, acc[1].re); acc[1].im = fma(g, o1.re, acc[1].im);
-    acc[2].re = fma(-g, o2.im, acc[2].re); acc[2].im = fma(g, o2.re, acc[2].im);
+    acc[1].re = fma(-g1, o1.im, acc[1].re); acc[1].im = fma(g1, o1.re, acc[1].im);
+    acc[2].re = fma(-g1, o2.im, acc[2].re); acc[2].im = fma(g1, o2.re, acc[2].im);
     acc[3].re = fma(-g, o3.im, acc[3].re); acc[3].im = fma(g, o3.re, acc[3].im);
     acc[4].re = fma(-g, o4.im, acc[4].re); acc[4].im = fma(g, o4.re, acc[4].im);
-    acc[5].re = fma(-g, o5.im, acc[5].re); acc[5].im = fma(g, o5.re, acc[5].im);
+    acc[5].re = fma(-g1, o5.im, acc[5].re); acc[5].im = fma(g1, o5.re, acc[5].im);
     acc[6].re = fma(-g, o6.im, acc[6].re); acc[6].im = fma(g, o6.re, acc[6].im);
 }
 

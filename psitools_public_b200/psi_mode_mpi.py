@@ -122,7 +122,9 @@ class MpiScheduler:
                 self.last_stats = dict(items=len(mine), passes=st.get("passes", 0),
                                        function_calls=st.get("function_calls", 0),
                                        evals=st.get("evals", 0), seconds=time.time() - t0,
-                                       engine="native")
+                                       host_logic_seconds=st.get("logic_s"),
+                                       device_seconds=st.get("eval_s"), launches=st.get("launches"),
+                                       polish_evals=st.get("polish_evals"), engine="native")
                 merged = _dist.all_gather_records({i: self._encode(r) for i, r in res.items()})
                 return {i: self._decode(merged[i]) for i in sorted(merged)}
         jobs, ctx = [], None

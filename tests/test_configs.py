@@ -1,0 +1,75 @@
+"""Small-scale parity for the remaining BASELINE configurations.
+
+config 5: parameter sweep -- many (mu, tau_max) dust distributions x a (Kx, Kz) grid of PSIMode solves
+          in ONE batch (mixed distribution ids per item), incl. the high-order table TanhSinh(15, 13)
+          whose 408 KB node table no longer fits shared memory (K1 reads it through L1/L2 instead).
+config 4: covered by test_grid_refine.py.  config 2/3: test_disp_parity.py / test_host_logic.py."""
+import time
+
+import numpy as np
+import pytest
+
+from test_grid_refine import distinct
+from test_host_logic import same_root_sets
+
+
+def sweep_items(ts, mus, taumaxs, n_axis):
+    ax = np.logspace(-1, 3, n_axis)
+    items = []
+    for mu in mus:
+        for tmax in taumaxs:
+            for kx in ax:
+                for kz in ax:
+                    items.append({'__init__': {'stokes_range': [1e-8, tmax], 'dust_to_gas_ratio': mu,
+                                               'real_range': [-2.0, 2.0], 'imag_range': [1e-8, 1.0],
+                                               'n_sample': 20, 'max_zoom_domains': 1,
+                                               'tanhsinh_integrator': ts},
+                                  'calculate': {'wave_number_x': kx, 'wave_number_z': kz},
+                                  'random_seed': 2})
+    return items
+
+
+def oracle_roots(item, tab):
+    from oracle import psi_oracle as po
+    init = {k: v for k, v in item['__init__'].items() if k != 'tanhsinh_integrator'}
+    return po.run_mode_item({'__init__': init, 'calculate': item['calculate'],
+                             'random_seed': item['random_seed']}, tab)
+
+
+def test_config5_parameter_sweep(backend):
+    from oracle import psi_oracle as po
+    from psitools_public_b200 import TanhSinhNoDeepCopy, psi_mode_mpi
+    ts = TanhSinhNoDeepCopy()
+    items = sweep_items(ts, [0.1, 10.0], [1e-3, 1.0], 3)          # 4 distributions x 3x3 K
+    ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False)
+    res = ms.run(items)
+    assert ms.last_stats["engine"] == "native" and len(res) == 36
+    tab = po.NodeTable()
+    n_with_roots = 0
+    for i in range(0, 36, 2):                                     # every other item against the oracle
+        ref = oracle_roots(items[i], tab)
+        # root sets are compared de-duplicated: how often the searches of one pixel land on the same
+        # root is an internal-trajectory quantity, the set of roots is not
+        assert same_root_sets(distinct(res[i]), distinct(ref)), (i, items[i]['calculate'], res[i], ref)
+        n_with_roots += len(ref) > 0
+    assert n_with_roots >= 2
+
+
+def test_high_order_table_level13(backend):
+    """TanhSinh(15, 13): 25,485 nodes; D against the oracle run with the same table."""
+    from oracle import psi_oracle as po
+    from psitools_public_b200 import PSIDispersion, TanhSinh
+    ts = TanhSinh(15, 13)
+    assert len(ts.xj) == 25485
+    pd = PSIDispersion(3.0, [1e-8, 1.0], tanhsinh_integrator=ts)
+    w = np.array([0.3 + 0.2j, -1.0048 + 1e-4j, 1.5 - 0.7j, -0.2 + 1e-6j])
+    got, M = pd.calculate(w, 10.0, 100.0, return_M=True)
+    od = po.Dispersion(po.DustDist.power_law(3.0, [1e-8, 1.0]), po.NodeTable(15, 13))
+    ref, Mref = od.calculate(w, 10.0, 100.0, return_M=True)
+    assert abs(pd.vgx - od.vgx) < 1e-14*abs(od.vgx)
+    for i in range(len(w)):
+        assert np.max(np.abs(M[i] - Mref[i])) <= 2e-9*np.max(np.abs(Mref[i]))
+        assert abs(got[i] - ref[i]) <= 2e-9*abs(ref[i])
+    # levels 12 and 13 agree (the extra level only confirms convergence)
+    pd12 = PSIDispersion(3.0, [1e-8, 1.0], tanhsinh_integrator=TanhSinh(15, 12))
+    np.testing.assert_allclose(pd12.calculate(w[:3], 10.0, 100.0), got[:3], rtol=1e-11)
