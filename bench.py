@@ -357,6 +357,16 @@ def run_b200(args):
                  "rank0_device_seconds": st.get("device_seconds"),
                  "rank0_D_evals_in_K3": st.get("polish_evals"), "host_threads": ctx.default_engine_threads(),
                  "engine": st.get("engine")}
+        if args.modes_compare:
+            # same map through the host-AAA engine (LAPACK on the host cores + K1/K3), for comparison
+            ms2 = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False, engine="native")
+            ms2.run_all(arglist(min(32, args.modes_grid)))
+            barrier()
+            t0 = time.perf_counter()
+            res2 = ms2.run_all(items)
+            barrier()
+            modes["native_engine_seconds"] = time.perf_counter() - t0
+            modes["native_engine_pixels_with_roots"] = int(sum(len(v) > 0 for v in res2.values()))
 
     t = torch.tensor([ms_total, ms_kernel, e2e_s, modes["seconds"] if modes else 0.0],
                      dtype=torch.float64, device=dev)
@@ -411,6 +421,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--modes-compare", action="store_true",
+                    help="also time the PSIMode map with the host-AAA (native) engine")
     ap.add_argument("--modes-grid", type=int, default=256,
                     help="axis length of the secondary PSIMode map (0 = skip)")
     args = ap.parse_args()

@@ -123,6 +123,17 @@ int psi_mode_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double
                         const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,
                         double* roots, int* n_roots, int* n_calls, int* status, long long* stats);
 
+/* Kernel K4 -- the same batch (same arguments, same outputs) with every search running ENTIRELY on the
+ * device: one warp per item does the sampling, the D evaluations, the AAA rational approximation
+ * (one-sided Jacobi SVD + Ehrlich-Aberth instead of LAPACK), the zoom logic and the secant polish
+ * (csrc/psi_mode.cuh); one launch per work class, no host round trip.  status: 0 ok, 1 non-finite
+ * samples (ValueError in the reference), 2 sample capacity, 3 start value on the real axis
+ * (ValueError), 4 more roots than max_roots.  stats = {launches, D evaluations, node evaluations}. */
+int psi_mode_batch_device(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
+                          const double* alpha, const double* domain, const int* iparams, const double* dparams,
+                          const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,
+                          double* roots, int* n_roots, int* n_calls, int* status, long long* stats);
+
 /* Kernel K2 -- n_items ClosedPath(f, z_list).count_roots(max_iter, tol, max_step)
  * (complex_roots.py:517-625) in ONE launch: one warp per contour runs every refinement pass and the
  * winding sum on the device.

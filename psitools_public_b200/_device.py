@@ -63,6 +63,7 @@ _SIGNATURES = {
     "psi_engine_counters": (None, [_vp]),
     "psi_engine_set_threads": (None, [C.c_int]),
     "psi_mode_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*10 + [C.c_int] + [_vp]*5),
+    "psi_mode_batch_device": (C.c_int, [_vp, C.c_int] + [_vp]*10 + [C.c_int] + [_vp]*5),
     "psi_contour_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*13),
     "psi_polish_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*12),
 }
@@ -151,10 +152,13 @@ class EngineAPI:
         return check(rc, what)
 
     def mode_batch(self, dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
-                   seeds, guesses, max_roots=8):
-        """Run len(dist) PSIMode.calculate searches in lock-step.  Per-item arrays; ``guesses`` is a
-        list of complex sequences.  Returns (list of root arrays, n_function_call array, stats)."""
-        self._bind_lapack()
+                   seeds, guesses, max_roots=8, device_aaa=False):
+        """Run len(dist) PSIMode.calculate searches.  Per-item arrays; ``guesses`` is a list of
+        complex sequences.  ``device_aaa=False``: native lock-step engine (AAA with LAPACK on the host
+        cores, D and the secant polish on the GPU); ``True``: kernel K4, everything on the device.
+        Returns (list of root arrays, n_function_call array, stats)."""
+        if not device_aaa:
+            self._bind_lapack()
         n = len(dist)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -168,7 +172,7 @@ class EngineAPI:
         goff[1:] = np.cumsum([len(g) for g in guesses])
         flat = [complex(z) for g in guesses for z in g]
         gz = np.ascontiguousarray(np.array(flat, dtype=np.complex128)) if flat else np.zeros(1, np.complex128)
-        fn = self.lib.psi_mode_batch_host
+        fn = self.lib.psi_mode_batch_device if device_aaa else self.lib.psi_mode_batch_host
         fn.restype = C.c_int
         while True:
             roots = np.zeros((n, max_roots), dtype=np.complex128)
@@ -179,7 +183,14 @@ class EngineAPI:
             self._check(fn(self.handle, C.c_int(n), _ptr(dist), _ptr(kx), _ptr(kz), _ptr(alpha),
                            _ptr(domain), _ptr(ip), _ptr(dp), _ptr(seeds), _ptr(goff), _ptr(gz),
                            C.c_int(max_roots), _ptr(roots), _ptr(nr), _ptr(nc), _ptr(st), _ptr(stats)),
-                        "psi_mode_batch_host")
+                        "psi_mode_batch")
+            if device_aaa:
+                stats[5], stats[6], stats[0] = stats[0], 0, 1
+                st = np.where(st == 4, 0, st)
+                if np.any(st != 0):
+                    bad = int(np.flatnonzero(st != 0)[0])
+                    raise PsiError("device root search failed for item %d (Kx=%g, Kz=%g): status %d"
+                                   % (bad, kx[bad], kz[bad], st[bad]))
             if n and nr.max() > max_roots:           # rare: more roots than slots, redo with room
                 max_roots = int(nr.max())
                 continue

@@ -15,8 +15,8 @@ FAILED_COUNT = -666
 
 
 class MpiScheduler:
-    def __init__(self, wall_start, wall_limit_total, verbose=True, native_engine=True):
-        self.native_engine = native_engine
+    def __init__(self, wall_start, wall_limit_total, verbose=True, engine="device"):
+        self.engine = engine          # "device": kernel K2; "python": contour_machine generators + K1
         self.last_stats = {}
         self.verbose = verbose
         self.rank = _dist.rank()
@@ -79,12 +79,12 @@ class MpiScheduler:
             if s_ in (1, 2):
                 print('complex_roots_mpi caught RuntimeError in count_roots')
                 print('Likely means the max iterations was exceeded.')
-        self.last_stats = dict(st, items=len(mine), points=int(np.sum(npts)), engine="native")
+        self.last_stats = dict(st, items=len(mine), points=int(np.sum(npts)), engine="device")
         return {i: np.array([float(c)]) for i, c in zip(mine, counts)}
 
     def run_all(self, arglist):
         mine = _dist.my_items(len(arglist))
-        if self.native_engine:
+        if self.engine != "python":
             local = self._run_native(arglist, mine)
             if local is not None:
                 merged = _dist.all_gather_records(local)

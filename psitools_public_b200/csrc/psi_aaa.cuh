@@ -1,0 +1,540 @@
+// psi_aaa.cuh -- warp-cooperative AAA rational approximation on the device (kernel K4's building
+// blocks): Loewner-matrix fit by a one-sided complex Jacobi SVD, greedy support-point selection,
+// Froissart-doublet cleanup, zeros and poles of the barycentric form by Ehrlich-Aberth iteration.
+//
+// Replaces RationalApproximation (complex_roots.py:38-368), which leans on LAPACK (numpy.linalg.svd,
+// scipy.linalg.eig).  The mathematics is the same -- weights = right singular vector of the smallest
+// singular value of the Loewner matrix; poles/zeros = roots of sum_j w_j/(z-z_j) and
+// sum_j w_j f_j/(z-z_j) -- the numerical kernels are GPU-friendly ones:
+//   * one-sided Jacobi keeps high relative accuracy for the tiny singular values AAA lives on and
+//     needs only column operations (lanes split the rows);
+//   * Aberth's simultaneous iteration works directly on the barycentric sums (O(m) per root and
+//     step, one root per lane) instead of a generalised eigenvalue problem.
+// One warp owns one approximation; all arrays live in a per-warp scratch area in global memory (L2).
+// Written against the warp policy W like psi_quad.cuh, so the CPU harness runs the same code.
+#pragma once
+#include "psi_batch.cuh"
+
+namespace psi {
+
+#if defined(PSI_AAA_STATS)
+// test-harness counters: fits, Jacobi sweeps, rotations, Aberth calls, Aberth iterations
+static long long g_aaa_stats[8];
+#define PSI_STAT(i, n) (g_aaa_stats[i] += (n))
+#else
+#define PSI_STAT(i, n)
+#endif
+
+constexpr int kMemoSlots = 12;
+
+// scratch layout of one warp (all sizes in elements, cap = maximum number of samples)
+struct AAAScratch {
+    cx* Z;        // [cap]   sample points
+    cx* F;        // [cap]   function samples
+    int* mask;    // [cap]   1 = support point
+    cx* A;        // [cap * ncol]  Loewner matrix, column-major (destroyed by the SVD)
+    cx* V;        // [ncol * ncol] right singular vectors
+    cx* w;        // [ncol]  weights
+    double* R;    // [cap]   residuals at the non-support points (in sample order of those points)
+    int* on;      // [ncol]  sample index of the k-th support point
+    int* off;     // [cap]   sample index of the k-th non-support point
+    cx* roots;    // [ncol]  Aberth iterates (zeros or poles)
+    cx* tmp;      // [ncol]  second root buffer
+    // greedy-phase result, replayed by PSIMode's clean_tol-halving loop
+    int* g_mask;  // [cap]
+    cx* g_w;      // [ncol]
+    double* g_R;  // [cap]
+    // work lists of the mode machine (psi_mode.cuh)
+    cx* w0;       // [ncol]  start values of the polish
+    cx* pol;      // [ncol]  polished values
+    // memo of Loewner fits keyed by the support mask (kMemoSlots entries, round robin): PSIMode's
+    // clean_tol-halving loop revisits the same masks again and again
+    cx* memo_w;        // [kMemoSlots * ncol]
+    double* memo_R;    // [kMemoSlots * cap]
+    double* memo_res;  // [kMemoSlots]
+    int* memo_mask;    // [kMemoSlots * cap]
+    int* memo_m;       // [kMemoSlots]   number of support points of the entry, -1 = empty
+    int cap, ncol;
+};
+
+PSI_HD size_t aaa_scratch_bytes(int cap) {
+    const size_t ncol = (size_t)cap / 2 + 2;
+    return sizeof(cx) * (2 * (size_t)cap + (size_t)cap * ncol + ncol * ncol + (6 + kMemoSlots) * ncol) +
+           sizeof(double) * ((2 + kMemoSlots) * (size_t)cap + kMemoSlots) +
+           sizeof(int) * ((3 + kMemoSlots) * (size_t)cap + ncol + kMemoSlots) + 256;
+}
+
+PSI_HD AAAScratch aaa_carve(void* base, int cap) {
+    AAAScratch s;
+    const size_t ncol = (size_t)cap / 2 + 2;
+    s.cap = cap; s.ncol = (int)ncol;
+    cx* c = reinterpret_cast<cx*>(base);
+    s.Z = c; c += cap;
+    s.F = c; c += cap;
+    s.A = c; c += (size_t)cap * ncol;
+    s.V = c; c += ncol * ncol;
+    s.w = c; c += ncol;
+    s.roots = c; c += ncol;
+    s.tmp = c; c += ncol;
+    s.g_w = c; c += ncol;
+    s.w0 = c; c += ncol;
+    s.pol = c; c += ncol;
+    s.memo_w = c; c += (size_t)kMemoSlots * ncol;
+    double* d = reinterpret_cast<double*>(c);
+    s.R = d; d += cap;
+    s.g_R = d; d += cap;
+    s.memo_R = d; d += (size_t)kMemoSlots * cap;
+    s.memo_res = d; d += kMemoSlots;
+    int* i = reinterpret_cast<int*>(d);
+    s.mask = i; i += cap;
+    s.off = i; i += cap;
+    s.g_mask = i; i += cap;
+    s.memo_mask = i; i += (size_t)kMemoSlots * cap;
+    s.memo_m = i; i += kMemoSlots;
+    s.on = i;
+    return s;
+}
+
+struct AAAState {
+    int M;          // number of samples
+    int m;          // number of support points
+    int r;          // number of non-support points
+    double fmax;    // max |F|
+    double tol, clean_tol;
+    RectDom dom;
+    int memo_next;  // next memo slot to overwrite
+};
+
+template <class W>
+PSI_HD void aaa_memo_clear(const AAAScratch& s, AAAState& st) {
+    for (int k = W::lane(); k < kMemoSlots; k += W::width) s.memo_m[k] = -1;
+    st.memo_next = 0;
+    W::sync();
+}
+
+// rebuild the index lists from the mask (every lane computes the same lists)
+template <class W>
+PSI_HD void aaa_index(const AAAScratch& s, AAAState& st) {
+    W::sync();
+    if (W::lane() == 0) {
+        int m = 0, r = 0;
+        for (int i = 0; i < st.M; ++i) {
+            if (s.mask[i]) s.on[m++] = i; else s.off[r++] = i;
+        }
+    }
+    W::sync();
+    int m = 0;
+    for (int i = 0; i < st.M; ++i) m += s.mask[i] ? 1 : 0;
+    st.m = m; st.r = st.M - m;
+}
+
+// One-sided Jacobi SVD of the r x m matrix A (column-major, leading dimension r): on return the
+// columns of A are orthogonal, V holds the accumulated rotations; returns the index of the column
+// with the smallest norm (the right singular vector of the smallest singular value is V[:, j]).
+template <class W>
+PSI_NOINLINE int jacobi_smallest(cx* A, cx* V, int r, int m) {
+    const int lane = W::lane();
+    for (int j = 0; j < m; ++j)
+        for (int i = lane; i < m; i += W::width) V[i + (size_t)j * m] = cx(i == j ? 1.0 : 0.0, 0.0);
+    W::sync();
+    PSI_STAT(0, 1);
+    double fro2 = 0.0;
+    for (int j = 0; j < m; ++j) {
+        const cx* aj = A + (size_t)j * r;
+        for (int i = lane; i < r; i += W::width) fro2 += aj[i].re * aj[i].re + aj[i].im * aj[i].im;
+    }
+    fro2 = W::sum(fro2);
+    const double negligible = 1.0e-30 * fro2;      // squared norm of a column that is pure rounding noise
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        bool rotated = false;
+        PSI_STAT(1, 1);
+        for (int p = 0; p < m - 1; ++p) {
+            for (int q = p + 1; q < m; ++q) {
+                cx* ap = A + (size_t)p * r;
+                cx* aq = A + (size_t)q * r;
+                double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+                for (int i = lane; i < r; i += W::width) {
+                    const cx x = ap[i], y = aq[i];
+                    al += x.re * x.re + x.im * x.im;
+                    be += y.re * y.re + y.im * y.im;
+                    gr += x.re * y.re + x.im * y.im;          // conj(x)*y
+                    gi += x.re * y.im - x.im * y.re;
+                }
+                al = W::sum(al); be = W::sum(be); gr = W::sum(gr); gi = W::sum(gi);
+                const double g = sqrt(gr * gr + gi * gi);
+                if (g <= 1.0e-14 * sqrt(al * be) || g == 0.0) continue;
+                if (al <= negligible && be <= negligible) continue;
+                rotated = true;
+                PSI_STAT(2, 1);
+                // Hermitian 2x2 [[al, gamma],[conj(gamma), be]]: rotation that annihilates gamma
+                const double zeta = (be - al) / (2.0 * g);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                const cx ph(gr / g, gi / g);                   // gamma/|gamma|
+                // a_p' = c*a_p - sn*conj(ph)*a_q ;  a_q' = sn*ph*a_p + c*a_q
+                const cx sp(sn * ph.re, -sn * ph.im), sq(sn * ph.re, sn * ph.im);
+                for (int i = lane; i < r; i += W::width) {
+                    const cx x = ap[i], y = aq[i];
+                    ap[i] = c * x - sp * y;
+                    aq[i] = sq * x + c * y;
+                }
+                cx* vp = V + (size_t)p * m;
+                cx* vq = V + (size_t)q * m;
+                for (int i = lane; i < m; i += W::width) {
+                    const cx x = vp[i], y = vq[i];
+                    vp[i] = c * x - sp * y;
+                    vq[i] = sq * x + c * y;
+                }
+                W::sync();
+            }
+        }
+        if (!rotated) break;
+    }
+    int best = 0;
+    double bn = -1.0;
+    for (int j = 0; j < m; ++j) {
+        double n2 = 0.0;
+        const cx* aj = A + (size_t)j * r;
+        for (int i = lane; i < r; i += W::width) n2 += aj[i].re * aj[i].re + aj[i].im * aj[i].im;
+        n2 = W::sum(n2);
+        if (bn < 0.0 || n2 < bn) { bn = n2; best = j; }
+    }
+    return best;
+}
+
+// Loewner fit for the current mask: weights and residuals (complex_roots.py:56-90).  Returns the
+// largest residual divided by max|F|.
+template <class W>
+PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st) {
+    aaa_index<W>(s, st);
+    const int lane = W::lane(), r = st.r, m = st.m;
+    // memo lookup
+    for (int k = 0; k < kMemoSlots; ++k) {
+        if (s.memo_m[k] != m) continue;
+        bool same = true;
+        const int* mk = s.memo_mask + (size_t)k * s.cap;
+        for (int i = lane; i < st.M; i += W::width) if (mk[i] != s.mask[i]) same = false;
+        if (W::any(!same)) continue;
+        for (int j = lane; j < m; j += W::width) s.w[j] = s.memo_w[(size_t)k * s.ncol + j];
+        for (int i = lane; i < r; i += W::width) s.R[i] = s.memo_R[(size_t)k * s.cap + i];
+        W::sync();
+        return s.memo_res[k];
+    }
+    for (int j = 0; j < m; ++j) {
+        const cx zj = s.Z[s.on[j]], fj = s.F[s.on[j]];
+        for (int i = lane; i < r; i += W::width) {
+            const cx c = np_div(cx(1.0, 0.0), s.Z[s.off[i]] - zj);
+            s.A[i + (size_t)j * r] = (s.F[s.off[i]] - fj) * c;        // F_i C_ij - C_ij f_j
+        }
+    }
+    W::sync();
+    if (r == 0) {
+        for (int j = lane; j < m; j += W::width) s.w[j] = cx(j == m - 1 ? 1.0 : 0.0, 0.0);
+    } else {
+        const int jmin = jacobi_smallest<W>(s.A, s.V, r, m);
+        for (int j = lane; j < m; j += W::width) s.w[j] = s.V[j + (size_t)jmin * m];
+    }
+    W::sync();
+    double rmax = 0.0;
+    for (int i = lane; i < r; i += W::width) {
+        const cx Zi = s.Z[s.off[i]];
+        cx num(0.0, 0.0), den(0.0, 0.0);
+        for (int j = 0; j < m; ++j) {
+            const cx t = np_div(s.w[j], Zi - s.Z[s.on[j]]);
+            num = num + t * s.F[s.on[j]];
+            den = den + t;
+        }
+        const double res = abs_c(s.F[s.off[i]] - np_div(num, den));
+        s.R[i] = res;
+        rmax = fmax(rmax, res);
+    }
+    W::sync();
+    const double resid = W::max(rmax) / st.fmax;
+    {   // memo insert
+        const int k = st.memo_next;
+        st.memo_next = (k + 1) % kMemoSlots;
+        for (int i = lane; i < st.M; i += W::width) s.memo_mask[(size_t)k * s.cap + i] = s.mask[i];
+        for (int j = lane; j < m; j += W::width) s.memo_w[(size_t)k * s.ncol + j] = s.w[j];
+        for (int i = lane; i < r; i += W::width) s.memo_R[(size_t)k * s.cap + i] = s.R[i];
+        if (lane == 0) { s.memo_m[k] = m; s.memo_res[k] = resid; }
+        W::sync();
+    }
+    return resid;
+}
+
+// barycentric evaluation r(z) = sum w_j f_j/(z-z_j) / sum w_j/(z-z_j)   (complex_roots.py:331-368)
+PSI_HD cx aaa_eval(const AAAScratch& s, const AAAState& st, cx z) {
+    cx num(0.0, 0.0), den(0.0, 0.0);
+    for (int j = 0; j < st.m; ++j) {
+        cx t = s.w[j];
+        if (t.re != 0.0 || t.im != 0.0) t = np_div(t, z - s.Z[s.on[j]]);
+        num = num + t * s.F[s.on[j]];
+        den = den + t;
+    }
+    return np_div(num, den);
+}
+
+// Roots of S(z) = sum_j a_j/(z - z_j) (a_j = w_j for the poles, w_j f_j for the zeros) by the
+// Ehrlich-Aberth iteration on p(z) = S(z) prod(z - z_j): p/p' = 1/(S'/S + sum 1/(z - z_j)).
+// m - 1 roots are written to out[]; roots that run away (|z| > 1e12 * scale: the leading coefficient
+// sum a_j is numerically zero) are returned as +inf.  Returns the number of iterations used.
+template <class W>
+PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with_f, cx* out) {
+    const int lane = W::lane(), m = st.m, nr = m - 1;
+    if (nr <= 0) return 0;
+    // scale and centre of the support points
+    double cre = 0.0, cim = 0.0;
+    for (int j = 0; j < m; ++j) { cre += s.Z[s.on[j]].re; cim += s.Z[s.on[j]].im; }
+    cre /= m; cim /= m;
+    double scale = 0.0;
+    for (int j = 0; j < m; ++j) scale = fmax(scale, abs_c(s.Z[s.on[j]] - cx(cre, cim)));
+    if (!(scale > 0.0)) scale = 1.0;
+    // start values: between consecutive support points, nudged off the connecting line
+    for (int k = lane; k < nr; k += W::width) {
+        const cx a = s.Z[s.on[k]], b = s.Z[s.on[k + 1]];
+        const cx d = b - a;
+        out[k] = cx(0.5 * (a.re + b.re) - 0.31 * d.im + 0.013 * scale, 0.5 * (a.im + b.im) + 0.31 * d.re + 0.017 * scale);
+    }
+    W::sync();
+    // Convergence per root: Aberth contracts cubically until the step reaches the rounding noise of
+    // the barycentric sums (1e-16..1e-13 relative, depending on how the terms cancel) and then just
+    // jitters; a root is frozen once its step is tiny and no longer shrinking fast.  prev[] = previous
+    // step length (stored in tmp[k].im after the swap; roots themselves are double-buffered).
+    int it = 0;
+    PSI_STAT(3, 1);
+    double prev_step[8];
+    bool frozen[8];
+    for (int q = 0; q < 8; ++q) { prev_step[q] = INFINITY; frozen[q] = false; }
+    for (; it < 60; ++it) {
+        PSI_STAT(4, 1);
+        bool moving = false;
+        int slot = 0;
+        for (int k = lane; k < nr; k += W::width, ++slot) {
+            const cx z = out[k];
+            const int q = slot < 8 ? slot : 7;
+            if (!finite_c(z) || frozen[q]) { s.tmp[k] = z; continue; }
+            cx S(0.0, 0.0), S1(0.0, 0.0), T(0.0, 0.0);
+            bool hit = false;
+            for (int j = 0; j < m; ++j) {
+                const cx dz = z - s.Z[s.on[j]];
+                if (dz.re == 0.0 && dz.im == 0.0) { hit = true; break; }
+                const cx inv = recip(dz);
+                cx a = s.w[j];
+                if (with_f) a = a * s.F[s.on[j]];
+                const cx t = a * inv;
+                S = S + t;
+                S1 = S1 - t * inv;
+                T = T + inv;
+            }
+            if (hit) {                                   // sitting on a support point: step aside
+                s.tmp[k] = cx(z.re + 1.0e-3 * scale, z.im + 1.3e-3 * scale);
+                moving = true;
+                continue;
+            }
+            if (S.re == 0.0 && S.im == 0.0) { s.tmp[k] = z; frozen[q] = true; continue; }     // exact root
+            const cx newton = recip(S1 * recip(S) + T);      // p/p'
+            cx rep(0.0, 0.0);
+            for (int l = 0; l < nr; ++l) {
+                if (l == k) continue;
+                const cx zl = out[l];
+                if (!finite_c(zl)) continue;
+                const cx dz = z - zl;
+                if (dz.re == 0.0 && dz.im == 0.0) continue;
+                rep = rep + recip(dz);
+            }
+            const cx step = np_div(newton, cx(1.0, 0.0) - newton * rep);
+            cx zn = z - step;
+            const double sl = abs_c(step);
+            if (!finite_c(zn) || abs_c(zn - cx(cre, cim)) > 1.0e12 * scale) {
+                zn = cx(INFINITY, 0.0);
+            } else if (sl <= 1.0e-15 * abs_c(zn) ||
+                       (sl <= 1.0e-9 * (abs_c(zn) + scale) && sl > 0.1 * prev_step[q])) {
+                if (slot < 8) frozen[q] = true;
+                if (sl > prev_step[q]) zn = z;              // keep the better iterate
+            } else {
+                moving = true;
+            }
+            prev_step[q] = sl;
+            s.tmp[k] = zn;
+        }
+        W::sync();
+        for (int k = lane; k < nr; k += W::width) out[k] = s.tmp[k];
+        W::sync();
+        if (!W::any(moving)) break;
+    }
+    return it;
+}
+
+// lexicographic order of numpy's sort for complex numbers (real part, then imaginary; NaN/inf last)
+PSI_HD bool np_less(cx a, cx b) {
+    if (a.re < b.re) return a.im == a.im || b.im != b.im;
+    if (a.re > b.re) return b.im != b.im && a.im == a.im;
+    if (a.re == b.re || (a.re != a.re && b.re != b.re)) return a.im < b.im || (b.im != b.im && a.im == a.im);
+    return b.re != b.re;
+}
+
+// sort n values ascending (rank sort: every lane places its own elements); result in `out`
+template <class W>
+PSI_HD void sort_complex(const cx* in, cx* out, int n) {
+    const int lane = W::lane();
+    W::sync();
+    for (int k = lane; k < n; k += W::width) {
+        int rank = 0;
+        for (int l = 0; l < n; ++l)
+            if (np_less(in[l], in[k]) || (!np_less(in[k], in[l]) && l < k)) ++rank;
+        out[rank] = in[k];
+    }
+    W::sync();
+}
+
+// Zeros of the approximant: Aberth roots, each polished by scipy's secant rule on r(z) itself
+// (50 iterations, tol 1.48e-8; a start is kept when the iteration degenerates or leaves the finite
+// numbers), sorted, entries closer than 1e-12 (numpy's lexicographic ">" on the difference) merged
+// (complex_roots.py:178-240).  Result in s.roots[0..n); returns n.
+template <class W>
+PSI_NOINLINE int aaa_zeros(const AAAScratch& s, const AAAState& st) {
+    const int lane = W::lane(), nr = st.m - 1;
+    if (nr <= 0) return 0;
+    aberth_roots<W>(s, st, true, s.roots);
+    for (int k = lane; k < nr; k += W::width) {
+        const cx z0 = s.roots[k];
+        if (!finite_c(z0)) continue;
+        // secant on the approximant (per lane: every lane polishes its own zero)
+        cx p0 = z0, p1 = second_point(z0, 1.0e-4);
+        cx q0 = aaa_eval(s, st, p0), q1 = aaa_eval(s, st, p1);
+        bool ok = finite_c(q0) && finite_c(q1), flagged = false;
+        cx root = z0;
+        if (ok) {
+            if (abs_c(q1) < abs_c(q0)) { cx t = p0; p0 = p1; p1 = t; t = q0; q0 = q1; q1 = t; }
+            cx p = p1;
+            bool done = false;
+            for (int it = 0; it < 50 && !done; ++it) {
+                if (eq_c(q1, q0)) { flagged = !eq_c(p1, p0); root = cx(0.5 * (p1.re + p0.re), 0.5 * (p1.im + p0.im)); done = true; break; }
+                if (abs_c(q1) > abs_c(q0)) {
+                    const cx rr = np_div(q0, q1);
+                    p = np_div(np_mul(-rr, p1) + p0, cx(1.0 - rr.re, -rr.im));
+                } else {
+                    const cx rr = np_div(q1, q0);
+                    p = np_div(np_mul(-rr, p0) + p1, cx(1.0 - rr.re, -rr.im));
+                }
+                if (!finite_c(p)) { ok = false; break; }
+                if (abs_c(p - p1) <= 1.48e-8) { root = p; done = true; break; }
+                p0 = p1; q0 = q1; p1 = p;
+                q1 = aaa_eval(s, st, p1);
+                if (!finite_c(q1)) { ok = false; break; }
+                root = p;
+            }
+        }
+        if (ok && !flagged) s.roots[k] = root;
+    }
+    W::sync();
+    sort_complex<W>(s.roots, s.tmp, nr);
+    // unique_within_tol (every lane computes the same compaction)
+    int n = 0;
+    if (lane == 0) {
+        for (int k = 0; k < nr; ++k) {
+            if (k == 0) { s.roots[n++] = s.tmp[0]; continue; }
+            const cx d = s.tmp[k] - s.tmp[k - 1];
+            if (np_less(cx(1.0e-12, 0.0), d)) s.roots[n++] = s.tmp[k];
+        }
+    }
+    W::sync();
+    n = 0;
+    for (int k = 0; k < nr; ++k) {
+        if (k == 0) { ++n; continue; }
+        const cx d = s.tmp[k] - s.tmp[k - 1];
+        if (np_less(cx(1.0e-12, 0.0), d)) ++n;
+    }
+    return n;
+}
+
+// One cleanup pass (complex_roots.py:286-329): every pole inside the domain whose residue, measured by
+// a 4-point contour integral of side 1e-5, is below clean_tol*max|F| costs the nearest support point.
+// Returns the number of support points removed (the fit is redone either way, as in the reference).
+template <class W>
+PSI_NOINLINE int aaa_cleanup(const AAAScratch& s, AAAState& st) {
+    const int lane = W::lane(), np_ = st.m - 1;
+    aberth_roots<W>(s, st, false, s.roots);
+    // decisions per pole (lane-parallel), collected in tmp[k].re = position to drop or -1
+    const double side = 1.0e-5;
+    const double c45 = 0.7071067811865476;
+    const cx ring[4] = {cx(side * c45, -side * c45), cx(side * c45, side * c45), cx(-side * c45, side * c45),
+                        cx(-side * c45, -side * c45)};
+    for (int k = lane; k < np_; k += W::width) {
+        const cx pole = s.roots[k];
+        double drop = -1.0;
+        if (finite_c(pole) && st.dom.is_in(pole)) {
+            cx zc[4], fc[4];
+            for (int q = 0; q < 4; ++q) { zc[q] = pole + ring[q]; fc[q] = aaa_eval(s, st, zc[q]); }
+            cx integral(0.0, 0.0);
+            for (int q = 0; q < 4; ++q) {
+                const cx dz = zc[(q + 1) & 3] - zc[q], fs = fc[(q + 1) & 3] + fc[q];
+                integral = integral + (0.5 * dz) * fs;
+            }
+            if (abs_c(integral) / st.fmax < st.clean_tol) {
+                int nearest = 0; double bd = INFINITY;
+                for (int j = 0; j < st.m; ++j) {
+                    const double d = abs_c(pole - s.Z[s.on[j]]);
+                    if (d < bd) { bd = d; nearest = j; }
+                }
+                drop = (double)s.on[nearest];
+            }
+        }
+        s.tmp[k] = cx(drop, 0.0);
+    }
+    W::sync();
+    int removed = 0;
+    for (int k = 0; k < np_; ++k) if (s.tmp[k].re >= 0.0) ++removed;
+    if (lane == 0)
+        for (int k = 0; k < np_; ++k) if (s.tmp[k].re >= 0.0) s.mask[(int)s.tmp[k].re] = 0;
+    W::sync();
+    aaa_fit<W>(s, st);
+    return removed;
+}
+
+// RationalApproximation.calculate (complex_roots.py:126-176).  `reuse_greedy`: replay the greedy phase
+// stored by the previous call on the same samples (the clean_tol-halving loop of psi_mode.py:174-217
+// calls calculate() on identical samples; the greedy phase does not depend on clean_tol).
+// Returns false when the samples are not finite (the reference raises ValueError).
+template <class W>
+PSI_NOINLINE bool aaa_calculate(const AAAScratch& s, AAAState& st, bool reuse_greedy) {
+    const int lane = W::lane(), M = st.M;
+    if (!reuse_greedy) {
+        aaa_memo_clear<W>(s, st);
+        double fm = 0.0; bool fin = true;
+        for (int i = lane; i < M; i += W::width) {
+            fm = fmax(fm, abs_c(s.F[i]));
+            if (!finite_c(s.F[i]) || !finite_c(s.Z[i])) fin = false;
+        }
+        st.fmax = W::max(fm);
+        if (W::any(!fin)) return false;
+        for (int i = lane; i < M; i += W::width) s.mask[i] = (i < 2) ? 1 : 0;
+        W::sync();
+        aaa_fit<W>(s, st);
+        for (int k = 1; k < M / 2; ++k) {
+            // promote the worst-fitted sample (first maximum, like numpy.argmax)
+            int best = -1; double bv = -1.0;
+            for (int i = lane; i < st.r; i += W::width)
+                if (s.R[i] > bv) { bv = s.R[i]; best = i; }
+            W::argmax(bv, best);
+            if (lane == 0) s.mask[s.off[best]] = 1;
+            W::sync();
+            if (aaa_fit<W>(s, st) < st.tol) break;
+        }
+        for (int i = lane; i < M; i += W::width) s.g_mask[i] = s.mask[i];
+        for (int j = lane; j < st.m; j += W::width) s.g_w[j] = s.w[j];
+        for (int i = lane; i < st.r; i += W::width) s.g_R[i] = s.R[i];
+        W::sync();
+    } else {
+        for (int i = lane; i < M; i += W::width) s.mask[i] = s.g_mask[i];
+        W::sync();
+        aaa_index<W>(s, st);
+        for (int j = lane; j < st.m; j += W::width) s.w[j] = s.g_w[j];
+        for (int i = lane; i < st.r; i += W::width) s.R[i] = s.g_R[i];
+        W::sync();
+    }
+    while (aaa_cleanup<W>(s, st) != 0) {}
+    return true;
+}
+
+}  // namespace psi

@@ -15,7 +15,7 @@
 
 #include "../../include/psi_b200.h"
 #include "psi_internal.hpp"
-#include "psi_batch.cuh"
+#include "psi_mode.cuh"
 #include "psi_table.hpp"
 
 using namespace psi;
@@ -43,6 +43,22 @@ struct WarpCuda {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         return v;
+    }
+    static __device__ __forceinline__ double max(double v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
+    static __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+    // largest v over the lanes, ties to the smallest index (idx < 0: lane has no candidate)
+    static __device__ __forceinline__ void argmax(double& v, int& idx) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (oi >= 0 && (idx < 0 || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
+        }
     }
 };
 
@@ -78,6 +94,9 @@ struct psi_ctx {
     size_t stage_bytes = 0;
     // per-warp ping-pong point buffers of the contour kernel (K2)
     void* d_contour_scratch = nullptr;
+    // per-warp AAA scratch of the mode kernel (K4), grown on demand
+    void* d_mode_scratch = nullptr;
+    size_t mode_scratch_bytes = 0;
     long long launches = 0;
 };
 
@@ -104,11 +123,10 @@ __global__ void background_kernel(NodeTableView t, DistParams* dists, int id) {
 }
 
 // Copy the level-major node table into shared memory (once per persistent CTA) and return a view of it.
-template <bool SMEM_TABLE>
-__device__ __forceinline__ NodeTableView stage_table(const NodeTableView& gt) {
+__device__ __forceinline__ NodeTableView stage_table(const NodeTableView& gt, bool in_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NodeTableView t = gt;
-    if (SMEM_TABLE) {
+    if (in_smem) {
         node_t* s_nodes = reinterpret_cast<node_t*>(smem_raw);
         int* s_off = reinterpret_cast<int*>(smem_raw + sizeof(node_t) * (size_t)gt.n_nodes);
         const double2* src = reinterpret_cast<const double2*>(gt.nodes);
@@ -132,15 +150,16 @@ __device__ __forceinline__ bool next_item(unsigned long long* queue, long long n
 
 // K1.  One specialisation per work class (NK, VISC); a launch handles the points of ITS class and
 // skips the others (a batch normally holds a single class, see launch_disp_eval).
-template <bool SMEM_TABLE, int NK, bool VISC>
+template <int NK, bool VISC>
 __global__ void __launch_bounds__(kEvalThreads, 1)
-disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long long n, int broadcast,
+disp_eval_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, long long n,
+                 int broadcast,
                  const int* __restrict__ dist, const double* __restrict__ kx,
                  const double* __restrict__ kz, const double* __restrict__ alpha,
                  const int* __restrict__ pidx, const double2* __restrict__ w, double2* __restrict__ D,
                  double2* __restrict__ M, unsigned long long* __restrict__ queue,
                  unsigned long long* __restrict__ node_evals) {
-    const NodeTableView t = stage_table<SMEM_TABLE>(gt);
+    const NodeTableView t = stage_table(gt, table_in_smem != 0);
     const int lane = threadIdx.x & 31;
     unsigned long long nodes = 0;
     while (true) {
@@ -167,35 +186,33 @@ disp_eval_kernel(NodeTableView gt, const DistParams* __restrict__ dists, long lo
     if (node_evals != nullptr && lane == 0 && nodes) atomicAdd(node_evals, nodes);
 }
 
-typedef void (*eval_kernel_t)(NodeTableView, const DistParams*, long long, int, const int*, const double*,
+typedef void (*eval_kernel_t)(NodeTableView, int, const DistParams*, long long, int, const int*, const double*,
                               const double*, const double*, const int*, const double2*, double2*, double2*,
                               unsigned long long*, unsigned long long*);
 
-template <bool SMEM>
 static eval_kernel_t eval_kernel_for(int cls) {
     switch (cls) {
-    case 0: return disp_eval_kernel<SMEM, 0, false>;
-    case 1: return disp_eval_kernel<SMEM, 0, true>;
-    case 2: return disp_eval_kernel<SMEM, 1, false>;
-    case 3: return disp_eval_kernel<SMEM, 1, true>;
-    case 4: return disp_eval_kernel<SMEM, 2, false>;
-    case 5: return disp_eval_kernel<SMEM, 2, true>;
-    case 6: return disp_eval_kernel<SMEM, 3, false>;
-    default: return disp_eval_kernel<SMEM, 3, true>;
+    case 0: return disp_eval_kernel<0, false>;
+    case 1: return disp_eval_kernel<0, true>;
+    case 2: return disp_eval_kernel<1, false>;
+    case 3: return disp_eval_kernel<1, true>;
+    case 4: return disp_eval_kernel<2, false>;
+    case 5: return disp_eval_kernel<2, true>;
+    case 6: return disp_eval_kernel<3, false>;
+    default: return disp_eval_kernel<3, true>;
     }
 }
 
 // K3 polish_kernel: one warp per root search; the whole two-stage secant polish of all its start
 // values runs on the device, every D evaluated inline (psi_batch.cuh, polish_run).
-template <bool SMEM_TABLE, int NK, bool VISC>
 __global__ void __launch_bounds__(kEvalThreads, 1)
-polish_kernel(NodeTableView gt, const DistParams* __restrict__ dists, int n_items,
+polish_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, int n_items,
               const int* __restrict__ pidx, const int* __restrict__ dist, const double* __restrict__ kx,
               const double* __restrict__ kz, const double* __restrict__ alpha,
               const double* __restrict__ dom, const int* __restrict__ off, double2* w0,
               const int* __restrict__ max_iter, double2* out, int* n_calls, int* max_conv, int* status,
               unsigned long long* queue, unsigned long long* counters) {
-    const NodeTableView t = stage_table<SMEM_TABLE>(gt);
+    const NodeTableView t = stage_table(gt, table_in_smem != 0);
     const int lane = threadIdx.x & 31;
     unsigned long long nodes = 0, evals = 0;
     long long idx;
@@ -203,8 +220,7 @@ polish_kernel(NodeTableView gt, const DistParams* __restrict__ dists, int n_item
         const int pi = pidx[idx];
         const DistParams& d = dists[dist[pi]];
         const double al = alpha[pi];
-        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
-        WarpEval<WarpCuda, NK, VISC> f;
+        WarpEval<WarpCuda> f;
         f.t = &t; f.d = &d; f.kx = kx[pi]; f.kz = kz[pi]; f.alpha = al; f.nodes = 0; f.evals = 0;
         const RectDom rd{dom[4 * idx], dom[4 * idx + 1], dom[4 * idx + 2], dom[4 * idx + 3]};
         const int o = off[idx], n = off[idx + 1] - o;
@@ -222,16 +238,15 @@ polish_kernel(NodeTableView gt, const DistParams* __restrict__ dists, int n_item
 
 // K2 contour_kernel: one warp per closed contour; adaptive refinement passes and the winding sum on
 // the device (psi_batch.cuh, contour_run).  scratch: 4*cap complex per warp of the grid.
-template <bool SMEM_TABLE, int NK, bool VISC>
 __global__ void __launch_bounds__(kEvalThreads, 1)
-contour_kernel(NodeTableView gt, const DistParams* __restrict__ dists, int n_items,
+contour_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, int n_items,
                const int* __restrict__ dist, const double* __restrict__ kx, const double* __restrict__ kz,
                const double* __restrict__ alpha, const int* __restrict__ z_off,
                const double2* __restrict__ z_list, const double* __restrict__ tol,
                const double* __restrict__ max_step, const int* __restrict__ max_iter, double2* scratch,
                int cap, int* counts, int* status, int* n_points, unsigned long long* queue,
                unsigned long long* counters) {
-    const NodeTableView t = stage_table<SMEM_TABLE>(gt);
+    const NodeTableView t = stage_table(gt, table_in_smem != 0);
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     cx* base = reinterpret_cast<cx*>(scratch) + (size_t)warp_global * 4 * cap;
@@ -240,8 +255,7 @@ contour_kernel(NodeTableView gt, const DistParams* __restrict__ dists, int n_ite
     while (next_item(queue, n_items, idx)) {
         const DistParams& d = dists[dist[idx]];
         const double al = alpha[idx];
-        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
-        WarpEval<WarpCuda, NK, VISC> f;
+        WarpEval<WarpCuda> f;
         f.t = &t; f.d = &d; f.kx = kx[idx]; f.kz = kz[idx]; f.alpha = al; f.nodes = 0; f.evals = 0;
         const int o = z_off[idx], n0 = z_off[idx + 1] - o;
         int cnt = -666, np = n0, st = kContourCapacity;
@@ -259,27 +273,46 @@ contour_kernel(NodeTableView gt, const DistParams* __restrict__ dists, int n_ite
     }
 }
 
-typedef void (*polish_kernel_t)(NodeTableView, const DistParams*, int, const int*, const int*, const double*,
-                                const double*, const double*, const double*, const int*, double2*, const int*,
-                                double2*, int*, int*, int*, unsigned long long*, unsigned long long*);
-typedef void (*contour_kernel_t)(NodeTableView, const DistParams*, int, const int*, const double*,
-                                 const double*, const double*, const int*, const double2*, const double*,
-                                 const double*, const int*, double2*, int, int*, int*, int*,
-                                 unsigned long long*, unsigned long long*);
-
-#define PSI_CLASS_SWITCH(NAME, SMEM, cls)                       \
-    switch (cls) {                                              \
-    case 0: return NAME<SMEM, 0, false>;                        \
-    case 1: return NAME<SMEM, 0, true>;                         \
-    case 2: return NAME<SMEM, 1, false>;                        \
-    case 3: return NAME<SMEM, 1, true>;                         \
-    case 4: return NAME<SMEM, 2, false>;                        \
-    case 5: return NAME<SMEM, 2, true>;                         \
-    case 6: return NAME<SMEM, 3, false>;                        \
-    default: return NAME<SMEM, 3, true>;                        \
+// K4 mode_kernel: one warp per PSIMode.calculate -- sampling, D evaluations, AAA, zeros, zoom domains and
+// the secant polish all on the device (psi_mode.cuh); scratch: aaa_scratch_bytes(cap) per warp.
+__global__ void __launch_bounds__(kEvalThreads, 1)
+mode_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, int n_items,
+            const int* __restrict__ dist, const double* __restrict__ kx, const double* __restrict__ kz,
+            const double* __restrict__ alpha, const double* __restrict__ domain,
+            const int* __restrict__ iparams, const double* __restrict__ dparams,
+            const double* __restrict__ uni, const int* __restrict__ uni_off,
+            const int* __restrict__ guess_off, const double2* __restrict__ guesses, unsigned char* scratch,
+            size_t scratch_per_warp, int cap, int max_roots, double2* roots, int* n_roots, int* n_calls,
+            int* status, unsigned long long* queue, unsigned long long* counters) {
+    const NodeTableView t = stage_table(gt, table_in_smem != 0);
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const AAAScratch sc = aaa_carve(scratch + (size_t)warp_global * scratch_per_warp, cap);
+    unsigned long long nodes = 0, evals = 0;
+    long long idx;
+    while (next_item(queue, n_items, idx)) {
+        const DistParams& d = dists[dist[idx]];
+        const double al = alpha[idx];
+        WarpEval<WarpCuda> f;
+        f.t = &t; f.d = &d; f.kx = kx[idx]; f.kz = kz[idx]; f.alpha = al; f.nodes = 0; f.evals = 0;
+        ModeCfg cfg;
+        cfg.dom = RectDom{domain[4 * idx], domain[4 * idx + 1], domain[4 * idx + 2], domain[4 * idx + 3]};
+        cfg.n_sample = iparams[3 * idx]; cfg.max_zoom = iparams[3 * idx + 1]; cfg.max_secant = iparams[3 * idx + 2];
+        cfg.tol = dparams[2 * idx]; cfg.clean_tol = dparams[2 * idx + 1];
+        const int g0 = guess_off[idx], ng = guess_off[idx + 1] - g0;
+        int nr = 0, nc = 0;
+        const int st = mode_run<WarpCuda>(f, cfg, reinterpret_cast<const cx*>(guesses + g0), ng,
+                                          uni + uni_off[idx], sc,
+                                          reinterpret_cast<cx*>(roots + (size_t)idx * max_roots), max_roots,
+                                          &nr, &nc);
+        if (lane == 0) { n_roots[idx] = nr; n_calls[idx] = nc; status[idx] = st; }
+        nodes += f.nodes; evals += (unsigned long long)f.evals;
     }
-template <bool SMEM> static polish_kernel_t polish_kernel_for(int cls) { PSI_CLASS_SWITCH(polish_kernel, SMEM, cls) }
-template <bool SMEM> static contour_kernel_t contour_kernel_for(int cls) { PSI_CLASS_SWITCH(contour_kernel, SMEM, cls) }
+    if (counters != nullptr && lane == 0) {
+        if (nodes) atomicAdd(counters, nodes);
+        if (evals) atomicAdd(counters + 1, evals);
+    }
+}
 
 // DFMA-pipe peak: 8 independent FMA chains per thread, all in registers.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
@@ -338,16 +371,14 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
     CK(cudaMemcpy(c->d_level_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
     c->table_smem = sizeof(node_t) * (size_t)n_nodes + sizeof(int) * off.size();
     c->table_in_smem = c->table_smem + 1024 <= (size_t)c->smem_optin;
-    if (c->table_in_smem)
+    if (c->table_in_smem) {
         for (int cls = 0; cls < kNumClasses; ++cls)
-        {
-            CK(cudaFuncSetAttribute(eval_kernel_for<true>(cls),
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
-            CK(cudaFuncSetAttribute(polish_kernel_for<true>(cls),
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
-            CK(cudaFuncSetAttribute(contour_kernel_for<true>(cls),
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
-        }
+            CK(cudaFuncSetAttribute(eval_kernel_for(cls), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)c->table_smem));
+        CK(cudaFuncSetAttribute(polish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+        CK(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+        CK(cudaFuncSetAttribute(mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+    }
     CK(cudaMalloc(&c->d_dists, sizeof(DistParams) * kMaxDists));
     CK(cudaMalloc(&c->d_counter, sizeof(unsigned long long) * 8));
     CK(cudaMemset(c->d_counter, 0, sizeof(unsigned long long) * 8));
@@ -360,7 +391,7 @@ void psi_ctx_destroy(psi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_nodes); cudaFree(c->d_level_off); cudaFree(c->d_dists); cudaFree(c->d_counter);
-    cudaFree(c->d_stage); cudaFree(c->d_contour_scratch);
+    cudaFree(c->d_stage); cudaFree(c->d_contour_scratch); cudaFree(c->d_mode_scratch);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -424,9 +455,9 @@ static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* d
     for (int cls = 0; cls < kNumClasses; ++cls) {
         if (!(class_mask & (1u << cls))) continue;
         CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
-        eval_kernel_t k = c->table_in_smem ? eval_kernel_for<true>(cls) : eval_kernel_for<false>(cls);
+        eval_kernel_t k = eval_kernel_for(cls);
         k<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
-            t, c->d_dists, n, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w, (double2*)D,
+            t, c->table_in_smem ? 1 : 0, c->d_dists, n, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w, (double2*)D,
             (double2*)M, c->d_counter, node_evals_dev);
         c->launches++;
         CK(cudaGetLastError());
@@ -588,18 +619,15 @@ int psi_internal_polish(psi_ctx* c, int n_items, const int* pidx, int n_params, 
     const int grid = std::min(c->sm_count, (n_items + warps - 1) / warps);
     CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
     NodeTableView t = table_view(c);
-    for (int cls = 0; cls < kNumClasses; ++cls) {
-        if (!(mask & (1u << cls))) continue;
-        CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
-        polish_kernel_t k = c->table_in_smem ? polish_kernel_for<true>(cls) : polish_kernel_for<false>(cls);
-        k<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
-            t, c->d_dists, n_items, (const int*)d[0], (const int*)d[1], (const double*)d[2],
-            (const double*)d[3], (const double*)d[4], (const double*)d[5], (const int*)d[6], (double2*)d[7],
-            (const int*)d[8], (double2*)d[9], (int*)d[10], (int*)d[11], (int*)d[12], c->d_counter,
-            c->d_counter + 4);
-        c->launches++;
-        CK(cudaGetLastError());
-    }
+    (void)mask;
+    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+    polish_kernel<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+        t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, (const int*)d[0], (const int*)d[1],
+        (const double*)d[2], (const double*)d[3], (const double*)d[4], (const double*)d[5], (const int*)d[6],
+        (double2*)d[7], (const int*)d[8], (double2*)d[9], (int*)d[10], (int*)d[11], (int*)d[12], c->d_counter,
+        c->d_counter + 4);
+    c->launches++;
+    CK(cudaGetLastError());
     unsigned long long cnt[2] = {0, 0};
     CK(cudaMemcpyAsync(out, d[9], 16 * nw, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(n_calls, d[10], 4 * ni, cudaMemcpyDeviceToHost, st));
@@ -608,6 +636,59 @@ int psi_internal_polish(psi_ctx* c, int n_items, const int* pidx, int n_params, 
     CK(cudaMemcpyAsync(cnt, c->d_counter + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (evals) *evals = (long long)cnt[1];
+    return PSI_OK;
+}
+
+int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const double* kx, const double* kz,
+                             const double* alpha, const double* domain, const int* iparams,
+                             const double* dparams, const double* uni, long long n_uni, const int* uni_off,
+                             const int* guess_off, const double* guesses, int cap, int max_roots,
+                             double* roots, int* n_roots, int* n_calls, int* status, long long* stats) {
+    if (n_items == 0) return PSI_OK;
+    CK(cudaSetDevice(c->device));
+    bool ok;
+    const unsigned mask = class_mask_of(c, n_items, dist, alpha, &ok);
+    if (!ok) return fail(PSI_ERR_ARG, "distribution id out of range");
+    const int warps = kEvalThreads / 32;
+    const int grid = std::min(c->sm_count, (n_items + warps - 1) / warps);
+    const size_t per_warp = (aaa_scratch_bytes(cap) + 255) & ~(size_t)255;
+    const size_t need = per_warp * (size_t)c->sm_count * warps;
+    if (need > c->mode_scratch_bytes) {
+        if (c->d_mode_scratch) CK(cudaFree(c->d_mode_scratch));
+        c->d_mode_scratch = nullptr; c->mode_scratch_bytes = 0;
+        CK(cudaMalloc(&c->d_mode_scratch, need));
+        c->mode_scratch_bytes = need;
+    }
+    const size_t ni = (size_t)n_items, ng = (size_t)guess_off[n_items];
+    StageItem it[] = {{dist, 4 * ni}, {kx, 8 * ni}, {kz, 8 * ni}, {alpha, 8 * ni}, {domain, 32 * ni},
+                      {iparams, 12 * ni}, {dparams, 16 * ni}, {uni, 8 * (size_t)n_uni}, {uni_off, 4 * ni},
+                      {guess_off, 4 * (ni + 1)}, {guesses, 16 * std::max<size_t>(ng, 1)},
+                      {nullptr, 16 * ni * max_roots}, {nullptr, 4 * ni}, {nullptr, 4 * ni}, {nullptr, 4 * ni}};
+    char* d[15];
+    int rc = stage_upload(c, it, 15, 0, d, nullptr);
+    if (rc != PSI_OK) return rc;
+    cudaStream_t st = c->stream;
+    CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
+    NodeTableView t = table_view(c);
+    (void)mask;
+    const int launches = 1;
+    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+    mode_kernel<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+        t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, (const int*)d[0], (const double*)d[1],
+        (const double*)d[2], (const double*)d[3], (const double*)d[4], (const int*)d[5], (const double*)d[6],
+        (const double*)d[7], (const int*)d[8], (const int*)d[9], (const double2*)d[10],
+        (unsigned char*)c->d_mode_scratch, per_warp, cap, max_roots, (double2*)d[11], (int*)d[12], (int*)d[13],
+        (int*)d[14], c->d_counter, c->d_counter + 4);
+    c->launches++;
+    CK(cudaGetLastError());
+    unsigned long long cnt[2] = {0, 0};
+    CK(cudaMemcpyAsync(roots, d[11], 16 * ni * max_roots, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_roots, d[12], 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_calls, d[13], 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, d[14], 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cnt, c->d_counter + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (stats) { stats[0] = launches; stats[1] = (long long)cnt[1]; stats[2] = (long long)cnt[0]; }
     return PSI_OK;
 }
 
@@ -654,18 +735,15 @@ int psi_contour_batch_host(psi_ctx* c, int n_items, const int* dist, const doubl
     cudaStream_t st = c->stream;
     CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
     NodeTableView t = table_view(c);
-    for (int cls = 0; cls < kNumClasses; ++cls) {
-        if (!(mask & (1u << cls))) continue;
-        CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
-        contour_kernel_t k = c->table_in_smem ? contour_kernel_for<true>(cls) : contour_kernel_for<false>(cls);
-        k<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
-            t, c->d_dists, n_items, (const int*)d[0], (const double*)d[1], (const double*)d[2],
-            (const double*)d[3], (const int*)d[4], (const double2*)d[5], (const double*)d[6],
-            (const double*)d[7], (const int*)d[8], (double2*)c->d_contour_scratch, cap, (int*)d[9],
-            (int*)d[10], (int*)d[11], c->d_counter, c->d_counter + 4);
-        c->launches++;
-        CK(cudaGetLastError());
-    }
+    (void)mask;
+    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+    contour_kernel<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+        t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, (const int*)d[0], (const double*)d[1],
+        (const double*)d[2], (const double*)d[3], (const int*)d[4], (const double2*)d[5], (const double*)d[6],
+        (const double*)d[7], (const int*)d[8], (double2*)c->d_contour_scratch, cap, (int*)d[9], (int*)d[10],
+        (int*)d[11], c->d_counter, c->d_counter + 4);
+    c->launches++;
+    CK(cudaGetLastError());
     unsigned long long cnt[2] = {0, 0};
     CK(cudaMemcpyAsync(counts, d[9], 4 * ni, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(status, d[10], 4 * ni, cudaMemcpyDeviceToHost, st));

@@ -54,7 +54,7 @@ struct SecantOut {
 
 // scipy.optimize.newton, secant branch (fprime=None, rtol=0), driven by an evaluator f(z) -> D.
 template <class EVAL>
-PSI_HD SecantOut secant_run(EVAL& f, cx x0, cx x1, int maxiter, double xtol) {
+PSI_NOINLINE SecantOut secant_run(EVAL& f, cx x0, cx x1, int maxiter, double xtol) {
     SecantOut o;
     cx p0 = x0, p1 = x1;
     cx q0 = f(p0), q1 = f(p1);
@@ -91,7 +91,7 @@ PSI_HD SecantOut secant_run(EVAL& f, cx x0, cx x1, int maxiter, double xtol) {
 // Returns the number of dispersion evaluations (PSIMode.n_function_call increment); status 1 = the
 // reference would raise ValueError (a start value on the real axis makes the tolerance zero).
 template <class EVAL>
-PSI_HD int polish_run(EVAL& f, const RectDom& dom, cx* w0, int n, int max_iter, cx* out, int* max_conv_iter,
+PSI_NOINLINE int polish_run(EVAL& f, const RectDom& dom, cx* w0, int n, int max_iter, cx* out, int* max_conv_iter,
                       int* status) {
     int calls = 0;
     *status = 0;
@@ -175,17 +175,19 @@ PSI_HD int contour_run(EVAL& f, cx* pts, cx* fv, cx* pts2, cx* fv2, int n0, int 
     return kContourMaxIter;
 }
 
-// evaluator handed to the state machines: one warp-cooperative D(omega) of class (NK, VISC)
-template <class W, int NK, bool VISC>
+// Evaluator handed to the state machines: one warp-cooperative D(omega).  The work class of the point
+// (size-density family x viscous) is dispatched at run time inside ONE non-inlined function, so the
+// kernels K2-K4 share a single compiled copy of the eight quadrature specialisations.
+template <class W>
 struct WarpEval {
     const NodeTableView* t;
     const DistParams* d;
     double kx, kz, alpha;
     unsigned long long nodes;
     long long evals;
-    PSI_NOINLINE cx operator()(cx w) {      // one copy of the evaluation per kernel, not one per call site
+    PSI_NOINLINE cx operator()(cx w) {
         ++evals;
-        return disp_eval_warp<W, NK, VISC>(*t, *d, w, kx, kz, alpha, nullptr, nodes);
+        return disp_eval_any<W>(*t, *d, w, kx, kz, alpha, nullptr, nodes);
     }
 };
 

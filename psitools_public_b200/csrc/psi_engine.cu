@@ -771,6 +771,45 @@ int psi_engine_bind_lapack(const char* numpy_openblas64, const char* scipy_openb
 /* host threads used by the engine's per-item logic (AAA etc.); n <= 0 restores the OpenMP default */
 void psi_engine_set_threads(int n) { g_threads = n; }
 
+/* K4 driver: the same batch as psi_mode_batch_host, but every search runs entirely on the device (one
+ * warp per item, one launch per work class).  The host only generates the random streams. */
+int psi_mode_batch_device(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
+                          const double* alpha, const double* domain, const int* iparams, const double* dparams,
+                          const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,
+                          double* roots, int* n_roots, int* n_calls, int* status, long long* stats) {
+    if (!ctx || n_items < 0 || !dist || !kx || !kz || !alpha || !domain || !iparams || !dparams || !seeds ||
+        !guess_off || !roots || !n_roots || !n_calls || !status || max_roots < 1)
+        return psi_internal_fail(PSI_ERR_ARG, "psi_mode_batch_device: bad argument");
+    // one U[0,1) stream per distinct seed, long enough for the hungriest item using it: every domain
+    // (initial, one per guess, four per zoom level) consumes 2*n_sample numbers
+    std::map<unsigned, long long> need;
+    int cap = 0;
+    for (int i = 0; i < n_items; ++i) {
+        const int ns = iparams[3 * i], mz = iparams[3 * i + 1], ng = guess_off[i + 1] - guess_off[i];
+        if (ns < 2 || mz < 0) return psi_internal_fail(PSI_ERR_ARG, "n_sample must be >= 2, max_zoom_domains >= 0");
+        const int domains = 1 + ng + 4 * mz;
+        cap = std::max(cap, ns * domains);
+        long long& n = need[seeds[i]];
+        n = std::max(n, 2ll * ns * domains);
+    }
+    std::vector<double> uni;
+    std::map<unsigned, long long> start;
+    for (auto& kv : need) {
+        start[kv.first] = (long long)uni.size();
+        MT19937 rng;
+        rng.seed(kv.first);
+        for (long long k = 0; k < kv.second; ++k) uni.push_back(rng.sample());
+    }
+    if (uni.size() > 0x7fffffffull) return psi_internal_fail(PSI_ERR_CAPACITY, "random streams too long");
+    std::vector<int> uoff(n_items);
+    for (int i = 0; i < n_items; ++i) uoff[i] = (int)start[seeds[i]];
+    const double dummy[2] = {0.0, 0.0};
+    return psi_internal_mode_device(ctx, n_items, dist, kx, kz, alpha, domain, iparams, dparams, uni.data(),
+                                    (long long)uni.size(), uoff.data(), guess_off,
+                                    guesses ? guesses : dummy, cap, max_roots, roots, n_roots, n_calls, status,
+                                    stats);
+}
+
 /* profiling aid: {svd calls, svd ns, eig calls, eig ns} accumulated since load */
 void psi_engine_counters(long long out[4]) {
     out[0] = g_cnt_svd; out[1] = g_us_svd; out[2] = g_cnt_eig; out[3] = g_us_eig;

@@ -21,3 +21,12 @@ int psi_internal_polish(psi_ctx* ctx, int n_items, const int* pidx, int n_params
                         const double* kx, const double* kz, const double* alpha, const double* dom,
                         const int* off, double* w0, const int* max_iter, double* out, int* n_calls,
                         int* max_conv, int* status, long long* evals);
+
+// K4 for n_items whole PSIMode.calculate searches (HOST arrays; see psi_mode_batch_device in
+// include/psi_b200.h).  uni: concatenated U[0,1) streams, uni_off[i]: start of item i's stream; cap:
+// largest number of samples any item can reach.  stats = {launches, D evaluations, node evaluations}.
+int psi_internal_mode_device(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
+                             const double* alpha, const double* domain, const int* iparams,
+                             const double* dparams, const double* uni, long long n_uni, const int* uni_off,
+                             const int* guess_off, const double* guesses, int cap, int max_roots,
+                             double* roots, int* n_roots, int* n_calls, int* status, long long* stats);

@@ -1,0 +1,167 @@
+// psi_mode.cuh -- kernel K4's body: one whole PSIMode.calculate (psi_mode.py:106-333) by one warp, with
+// no host round trip: random samples -> D (inline, warp-cooperative) -> AAA (psi_aaa.cuh) -> zeros ->
+// clean_tol halving -> zoom-domain selection -> secant polish (psi_batch.cuh) -> more samples ...
+//
+// The random sample points come from a pre-generated stream of U[0,1) numbers per work item (the numpy
+// legacy MT19937 stream of the item's seed, generated once per distinct seed on the host); the device
+// consumes it in the reference's order: for every domain first all real parts, then all imaginary parts
+// (complex_roots.py:404-409), lo + (hi-lo)*u with separate multiply and add.
+#pragma once
+#include "psi_aaa.cuh"
+
+namespace psi {
+
+struct ModeCfg {
+    RectDom dom;
+    int n_sample, max_zoom, max_secant;
+    double tol, clean_tol;
+};
+
+enum ModeStatus { kModeOk = 0, kModeBadSamples = 1, kModeCapacity = 2, kModeZeroTol = 3, kModeTruncated = 4 };
+
+// append n_sample random points of the box [x0,x1]x[y0,y1] and their D values
+template <class W, class EVAL>
+PSI_HD void mode_sample(EVAL& f, const AAAScratch& s, AAAState& st, const double* uni, int& upos, int n,
+                        double x0, double x1, double y0, double y1) {
+    const int base = st.M;
+    for (int i = W::lane(); i < n; i += W::width) {
+        const double re = add_rn(x0, mul_rn(x1 - x0, uni[upos + i]));
+        const double im = add_rn(y0, mul_rn(y1 - y0, uni[upos + n + i]));
+        s.Z[base + i] = cx(re, im);
+    }
+    W::sync();
+    for (int i = 0; i < n; ++i) {
+        const cx v = f(s.Z[base + i]);
+        if (W::lane() == 0) s.F[base + i] = v;
+    }
+    W::sync();
+    upos += 2 * n;
+    st.M = base + n;
+}
+
+// zoom box around `centre`, shifted to lie inside the search domain (psi_mode.py:354-397)
+template <class W, class EVAL>
+PSI_HD void mode_extra_domain(EVAL& f, const AAAScratch& s, AAAState& st, const ModeCfg& cfg, const double* uni,
+                              int& upos, double sx, double sy, cx centre) {
+    double re = centre.re, im = centre.im;
+    if (re < cfg.dom.xmin + 0.5 * sx) re = cfg.dom.xmin + 0.5 * sx;
+    if (re > cfg.dom.xmax - 0.5 * sx) re = cfg.dom.xmax - 0.5 * sx;
+    if (im < cfg.dom.ymin + 0.5 * sy) im = cfg.dom.ymin + 0.5 * sy;
+    if (im > cfg.dom.ymax - 0.5 * sy) im = cfg.dom.ymax - 0.5 * sy;
+    mode_sample<W>(f, s, st, uni, upos, cfg.n_sample, re - 0.5 * sx, re + 0.5 * sx, im - 0.5 * sy, im + 0.5 * sy);
+}
+
+// Returns a ModeStatus; out_roots[0..min(*n_roots, max_roots)) receive the roots inside the domain,
+// *n_calls the reference's n_function_call.
+template <class W, class EVAL>
+PSI_HD int mode_run(EVAL& f, const ModeCfg& cfg, const cx* guesses, int n_guess, const double* uni,
+                    const AAAScratch& s, cx* out_roots, int max_roots, int* n_roots, int* n_calls) {
+    AAAState st;
+    st.M = 0; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol; st.dom = cfg.dom;
+    int upos = 0, calls = 0;
+    *n_roots = 0; *n_calls = 0;
+    const int n_domains_max = 1 + n_guess + 4 * cfg.max_zoom;
+    if (cfg.n_sample * n_domains_max > s.cap) return kModeCapacity;
+
+    mode_sample<W>(f, s, st, uni, upos, cfg.n_sample, cfg.dom.xmin, cfg.dom.xmax, cfg.dom.ymin, cfg.dom.ymax);
+    calls += cfg.n_sample;
+    for (int g = 0; g < n_guess; ++g) {
+        const double side = fmin(1.0e-3, fabs(guesses[g].im) * 4.0);      // guess_domain_size (:34-37)
+        mode_extra_domain<W>(f, s, st, cfg, uni, upos, side, side, guesses[g]);
+        calls += cfg.n_sample;
+    }
+
+    int n_out = 0;
+    for (int level = 0; level <= cfg.max_zoom; ++level) {
+        st.clean_tol = cfg.clean_tol;
+        if (!aaa_calculate<W>(s, st, false)) { *n_calls = calls; return kModeBadSamples; }
+        int nz = aaa_zeros<W>(s, st);
+        // halve clean_tol until enough support points and one growing zero inside the domain (:174-217)
+        const int need = 4 * (1 + level + n_guess);
+        for (;;) {
+            bool growing = false;
+            for (int k = 0; k < nz; ++k) {
+                const cx z = s.roots[k];
+                if (cfg.dom.is_in(z) && z.im > 0.0) growing = true;
+            }
+            if (st.m >= need && growing) break;
+            st.clean_tol = 0.5 * st.clean_tol;
+            if (st.clean_tol < st.tol) break;
+            aaa_calculate<W>(s, st, true);
+            nz = aaa_zeros<W>(s, st);
+        }
+        // zoom candidates: below the top of the box, inside in Re; by decreasing Im, at least box_dx
+        // apart in Re, at most four (:236-261)
+        const double box_dx = pow(10.0, -1.0 - 0.5 * level);
+        cx zoom[4];
+        int n_zoom = 0;
+        {
+            // rank the candidates by Im (ascending) into tmp
+            int nc = 0;
+            for (int k = 0; k < nz; ++k) {
+                const cx z = s.roots[k];
+                if (z.im < cfg.dom.ymax && z.re < cfg.dom.xmax && z.re > cfg.dom.xmin) ++nc;
+            }
+            W::sync();
+            for (int k = W::lane(); k < nz; k += W::width) {
+                const cx z = s.roots[k];
+                if (!(z.im < cfg.dom.ymax && z.re < cfg.dom.xmax && z.re > cfg.dom.xmin)) continue;
+                int rank = 0;
+                for (int l = 0; l < nz; ++l) {
+                    const cx y = s.roots[l];
+                    if (!(y.im < cfg.dom.ymax && y.re < cfg.dom.xmax && y.re > cfg.dom.xmin)) continue;
+                    if (y.im < z.im || (y.im == z.im && l < k)) ++rank;
+                }
+                s.tmp[rank] = z;
+            }
+            W::sync();
+            for (int i = nc - 1; i >= 0 && n_zoom < 4; --i) {
+                const cx z = s.tmp[i];
+                bool ok = true;
+                // the distance rule is applied against the FULL list before truncation to four
+                // (:246-258); candidates beyond the fourth never matter for the first four
+                for (int q = 0; q < n_zoom; ++q) if (fabs(z.re - zoom[q].re) < box_dx) ok = false;
+                if (ok) zoom[n_zoom++] = z;
+            }
+        }
+        // start values of the polish: zeros inside the domain, else the least damped candidate
+        int n0 = 0;
+        W::sync();
+        if (W::lane() == 0) {
+            int c = 0;
+            for (int k = 0; k < nz; ++k) if (cfg.dom.is_in(s.roots[k])) s.w0[c++] = s.roots[k];
+        }
+        for (int k = 0; k < nz; ++k) if (cfg.dom.is_in(s.roots[k])) ++n0;
+        int max_iter = cfg.max_secant;
+        if (level < cfg.max_zoom) max_iter = cfg.n_sample;
+        if (n0 == 0 && n_zoom > 0) {
+            if (W::lane() == 0) s.w0[0] = zoom[0];
+            n0 = 1;
+            max_iter = 5;
+        }
+        W::sync();
+        int conv = 0, pst = 0;
+        calls += polish_run(f, cfg.dom, s.w0, n0, max_iter, s.pol, &conv, &pst);
+        W::sync();
+        if (pst != 0) { *n_calls = calls; return kModeZeroTol; }
+        n_out = 0;
+        bool grow = false;
+        for (int k = 0; k < n0; ++k) {
+            const cx z = s.pol[k];
+            if (!cfg.dom.is_in(z)) continue;
+            if (n_out < max_roots && W::lane() == 0) out_roots[n_out] = z;
+            ++n_out;
+            if (z.im > 0.0) grow = true;
+        }
+        if (grow || level == cfg.max_zoom || n_zoom == 0) break;
+        for (int q = 0; q < n_zoom; ++q) {
+            mode_extra_domain<W>(f, s, st, cfg, uni, upos, box_dx, fmin(0.1, fabs(zoom[q].im)), zoom[q]);
+            calls += cfg.n_sample;
+        }
+    }
+    *n_roots = n_out;
+    *n_calls = calls;
+    return n_out > max_roots ? kModeTruncated : kModeOk;
+}
+
+}  // namespace psi

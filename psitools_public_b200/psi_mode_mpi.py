@@ -9,6 +9,7 @@ pass, _engine.py) and the results are exchanged with a single all-gather (_dist.
 re-seed their own random stream exactly like the reference's runcompute (:162-167), so results do
 not depend on the schedule.
 """
+import os
 import time
 
 import numpy as np
@@ -16,6 +17,9 @@ import numpy as np
 from . import _dist
 from ._engine import run_lockstep
 from .psi_mode import ModeTrace, PSIMode
+
+
+DEFAULT_ENGINE = "device"
 
 
 def _same_init(a, b):
@@ -43,7 +47,7 @@ class _ModeCache:
 class MpiScheduler:
     """Execute a set of PSIMode runs given as a list of arg-dicts."""
 
-    def __init__(self, wall_start, wall_limit_total, verbose=True, native_engine=True):
+    def __init__(self, wall_start, wall_limit_total, verbose=True, engine=None):
         self.verbose = verbose
         self.exitFlag = False
         self.rank = _dist.rank()
@@ -52,9 +56,13 @@ class MpiScheduler:
         self.wall_limit_total = wall_limit_total
         self._cache = _ModeCache()
         self.last_stats = {}
-        # True: the C++ lock-step engine of libpsi_b200 (csrc/psi_engine.cu) drives the searches;
-        # False: the Python generators of psi_mode.py do (same logic, same LAPACK, ~100x more host time)
-        self.native_engine = native_engine
+        # "device": kernel K4 -- every search runs entirely on the GPU (AAA by Jacobi SVD + Aberth);
+        # "native": the C++ lock-step engine (csrc/psi_engine.cu): AAA with LAPACK on the host cores,
+        #           D (K1) and the secant polish (K3) on the GPU;
+        # "python": the Python generators of psi_mode.py (same logic and LAPACK as "native", slow).
+        self.engine = engine or os.environ.get("PSI_B200_ENGINE", DEFAULT_ENGINE)
+        if self.engine not in ("device", "native", "python"):
+            raise ValueError("engine must be 'device', 'native' or 'python'")
 
     # -- per-item body ------------------------------------------------------------------------
     def _job(self, args):
@@ -104,7 +112,7 @@ class MpiScheduler:
             [pm.cfg.max_secant_iterations for pm in pms], [pm.cfg.tol for pm in pms],
             [pm.cfg.clean_tol for pm in pms],
             [int(arglist[i].get('random_seed', 0)) for i in mine],
-            [list(c.get('guess_roots', ())) for c in calc])
+            [list(c.get('guess_roots', ())) for c in calc], device_aaa=self.engine == "device")
         st["function_calls"] = int(np.sum(ncalls))
         return {i: r for i, r in zip(mine, roots)}, st
 
@@ -112,7 +120,7 @@ class MpiScheduler:
         """Results of every item, on every rank."""
         t0 = time.time()
         mine = _dist.my_items(len(arglist))
-        if self.native_engine:
+        if self.engine != "python":
             done = self._run_native(arglist, mine)
             if done is not None:
                 res, st = done
@@ -124,7 +132,7 @@ class MpiScheduler:
                                        evals=st.get("evals", 0), seconds=time.time() - t0,
                                        host_logic_seconds=st.get("logic_s"),
                                        device_seconds=st.get("eval_s"), launches=st.get("launches"),
-                                       polish_evals=st.get("polish_evals"), engine="native")
+                                       polish_evals=st.get("polish_evals"), engine=self.engine)
                 merged = _dist.all_gather_records({i: self._encode(r) for i, r in res.items()})
                 return {i: self._decode(merged[i]) for i in sorted(merged)}
         jobs, ctx = [], None

@@ -9,7 +9,9 @@
 #include <string>
 #include <vector>
 
-#include "../../psitools_public_b200/csrc/psi_batch.cuh"
+#define PSI_AAA_STATS 1
+
+#include "../../psitools_public_b200/csrc/psi_mode.cuh"
 #include "../../psitools_public_b200/csrc/psi_internal.hpp"
 #include "../../psitools_public_b200/csrc/psi_table.hpp"
 
@@ -19,6 +21,10 @@ struct WarpOne {
     static constexpr int width = 1;
     static int lane() { return 0; }
     static double sum(double v) { return v; }
+    static double max(double v) { return v; }
+    static void sync() {}
+    static bool any(bool p) { return p; }
+    static void argmax(double&, int&) {}
 };
 
 // test stand-in for the library's context
@@ -58,24 +64,12 @@ int psi_internal_eval_indexed(psi_ctx* c, long long n, const int* pidx, int n_pa
     return PSI_OK;
 }
 
-// CPU stand-in for the class dispatch of kernels K2/K3: run F with the WarpEval of the point's class
+// CPU stand-in for kernels K2-K4: run `body` with the evaluator of one item
 template <class F>
 static void with_eval(psi_ctx* c, int dist, double kx, double kz, double alpha, F&& body) {
-    const DistParams& d = c->dists[dist];
-    auto go = [&](auto ev) {
-        ev.t = &c->view; ev.d = &d; ev.kx = kx; ev.kz = kz; ev.alpha = alpha; ev.nodes = 0; ev.evals = 0;
-        body(ev);
-    };
-    switch (point_class(d, alpha)) {
-    case 0: go(WarpEval<WarpOne, 0, false>()); break;
-    case 1: go(WarpEval<WarpOne, 0, true>()); break;
-    case 2: go(WarpEval<WarpOne, 1, false>()); break;
-    case 3: go(WarpEval<WarpOne, 1, true>()); break;
-    case 4: go(WarpEval<WarpOne, 2, false>()); break;
-    case 5: go(WarpEval<WarpOne, 2, true>()); break;
-    case 6: go(WarpEval<WarpOne, 3, false>()); break;
-    default: go(WarpEval<WarpOne, 3, true>()); break;
-    }
+    WarpEval<WarpOne> ev;
+    ev.t = &c->view; ev.d = &c->dists[dist]; ev.kx = kx; ev.kz = kz; ev.alpha = alpha; ev.nodes = 0; ev.evals = 0;
+    body(ev);
 }
 
 int psi_internal_polish(psi_ctx* c, int n_items, const int* pidx, int n_params, const int* dist,
@@ -100,11 +94,40 @@ int psi_internal_polish(psi_ctx* c, int n_items, const int* pidx, int n_params, 
     return PSI_OK;
 }
 
+int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const double* kx, const double* kz,
+                             const double* alpha, const double* domain, const int* iparams,
+                             const double* dparams, const double* uni, long long n_uni, const int* uni_off,
+                             const int* guess_off, const double* guesses, int cap, int max_roots,
+                             double* roots, int* n_roots, int* n_calls, int* status, long long* stats) {
+    (void)n_uni;
+    long long total = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+    for (int i = 0; i < n_items; ++i) {
+        with_eval(c, dist[i], kx[i], kz[i], alpha[i], [&](auto& ev) {
+            std::vector<unsigned char> buf(aaa_scratch_bytes(cap));
+            const AAAScratch sc = aaa_carve(buf.data(), cap);
+            ModeCfg cfg;
+            cfg.dom = RectDom{domain[4 * i], domain[4 * i + 1], domain[4 * i + 2], domain[4 * i + 3]};
+            cfg.n_sample = iparams[3 * i]; cfg.max_zoom = iparams[3 * i + 1]; cfg.max_secant = iparams[3 * i + 2];
+            cfg.tol = dparams[2 * i]; cfg.clean_tol = dparams[2 * i + 1];
+            const int g0 = guess_off[i], ng = guess_off[i + 1] - g0;
+            int nr = 0, nc = 0;
+            status[i] = mode_run<WarpOne>(ev, cfg, reinterpret_cast<const cx*>(guesses) + g0, ng, uni + uni_off[i], sc,
+                                          reinterpret_cast<cx*>(roots) + (size_t)i * max_roots, max_roots, &nr, &nc);
+            n_roots[i] = nr; n_calls[i] = nc;
+            total += ev.evals;
+        });
+    }
+    if (stats) { stats[0] = 1; stats[1] = total; stats[2] = 0; }
+    return PSI_OK;
+}
+
 #include "../../psitools_public_b200/csrc/psi_engine.cu"
 
 extern "C" {
 
 const char* hs_last_error(void) { return g_err.c_str(); }
+void hs_aaa_stats(long long* out) { for (int i = 0; i < 8; ++i) { out[i] = g_aaa_stats[i]; g_aaa_stats[i] = 0; } }
 
 int psi_polish_batch_host(psi_ctx* c, int n_items, const int* dist, const double* kx, const double* kz,
                           const double* alpha, const double* domain, const int* w0_off, const double* w0,

@@ -43,7 +43,7 @@ def test_config5_parameter_sweep(backend):
     items = sweep_items(ts, [0.1, 10.0], [1e-3, 1.0], 3)          # 4 distributions x 3x3 K
     ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False)
     res = ms.run(items)
-    assert ms.last_stats["engine"] == "native" and len(res) == 36
+    assert ms.last_stats["engine"] == "device" and len(res) == 36
     tab = po.NodeTable()
     n_with_roots = 0
     for i in range(0, 36, 2):                                     # every other item against the oracle

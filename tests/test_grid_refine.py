@@ -28,7 +28,7 @@ def make_refiner(engine):
                              'tanhsinh_integrator': TanhSinhNoDeepCopy()},
                 'calculate': {'wave_number_x': None, 'wave_number_z': None, 'guess_roots': []},
                 'random_seed': 2}
-    ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False, native_engine=engine == "native")
+    ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False, engine=engine)
     log = []
     inner = ms.run_all
 
@@ -50,7 +50,7 @@ def distinct(roots):
     return list(prune_eps(roots, epsilon=1e-6*max(abs(r) for r in roots)))
 
 
-@pytest.mark.parametrize("engine", ["native", "python"])
+@pytest.mark.parametrize("engine", ["device", "native", "python"])
 def test_refiner_against_reference(backend, engine, tmp_path):
     from psitools_public_b200.psi_grid_refine import get_if
     gold = load("refine.json")

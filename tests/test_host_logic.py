@@ -53,7 +53,7 @@ def grid_arglist(n_axis, ts):
             for kx, kz in zip(kxg.flatten(), kzg.flatten())]
 
 
-@pytest.mark.parametrize("engine", ["native", "python"])
+@pytest.mark.parametrize("engine", ["device", "native", "python"])
 @pytest.mark.parametrize("n_axis", [3, 6])
 def test_mpischeduler_mode_grid(backend, n_axis, engine):
     """test_psi_mode_mpi.py:38-104 (3x3) and a 6x6 grid of the same family: root sets per pixel
@@ -61,7 +61,7 @@ def test_mpischeduler_mode_grid(backend, n_axis, engine):
     import time
     from psitools_public_b200 import TanhSinhNoDeepCopy, psi_mode_mpi
     g = load("modegrid.json")["grid%d" % n_axis]
-    ms = psi_mode_mpi.MpiScheduler(time.time(), 3600, verbose=False, native_engine=engine == "native")
+    ms = psi_mode_mpi.MpiScheduler(time.time(), 3600, verbose=False, engine=engine)
     res = ms.run(grid_arglist(n_axis, TanhSinhNoDeepCopy()))
     assert ms.last_stats["engine"] == engine
     assert sorted(res) == list(range(n_axis*n_axis))
@@ -103,13 +103,13 @@ def count_arglist(ts):
             for kx, kz in zip(kxg.flatten(), kzg.flatten())]
 
 
-@pytest.mark.parametrize("engine", ["native", "python"])
+@pytest.mark.parametrize("engine", ["device", "python"])
 def test_root_count_map(backend, engine):
     """test_complex_roots_mpi.py:32-102: counts [0,0,0,1,0,0,1,0,0] exactly."""
     import time
     from psitools_public_b200 import TanhSinhNoDeepCopy, complex_roots_mpi
     res = complex_roots_mpi.MpiScheduler(time.time(), 3600, verbose=False,
-                                         native_engine=engine == "native").run(
+                                         engine=engine).run(
         count_arglist(TanhSinhNoDeepCopy()))
     assert [res[i] for i in range(9)] == [0, 0, 0, 1, 0, 0, 1, 0, 0]
     gold = load("contour.json")["cases"]
