@@ -205,6 +205,7 @@ static eval_kernel_t eval_kernel_for(int cls) {
 
 // K3 polish_kernel: one warp per root search; the whole two-stage secant polish of all its start
 // values runs on the device, every D evaluated inline (psi_batch.cuh, polish_run).
+template <int NK, bool VISC>
 __global__ void __launch_bounds__(kEvalThreads, 1)
 polish_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, int n_items,
               const int* __restrict__ pidx, const int* __restrict__ dist, const double* __restrict__ kx,
@@ -220,7 +221,8 @@ polish_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict_
         const int pi = pidx[idx];
         const DistParams& d = dists[dist[pi]];
         const double al = alpha[pi];
-        WarpEval<WarpCuda> f;
+        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
+        WarpEvalClass<WarpCuda, NK, VISC> f;
         f.t = &t; f.d = &d; f.kx = kx[pi]; f.kz = kz[pi]; f.alpha = al; f.nodes = 0; f.evals = 0;
         const RectDom rd{dom[4 * idx], dom[4 * idx + 1], dom[4 * idx + 2], dom[4 * idx + 3]};
         const int o = off[idx], n = off[idx + 1] - o;
@@ -238,6 +240,7 @@ polish_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict_
 
 // K2 contour_kernel: one warp per closed contour; adaptive refinement passes and the winding sum on
 // the device (psi_batch.cuh, contour_run).  scratch: 4*cap complex per warp of the grid.
+template <int NK, bool VISC>
 __global__ void __launch_bounds__(kEvalThreads, 1)
 contour_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, int n_items,
                const int* __restrict__ dist, const double* __restrict__ kx, const double* __restrict__ kz,
@@ -255,7 +258,8 @@ contour_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict
     while (next_item(queue, n_items, idx)) {
         const DistParams& d = dists[dist[idx]];
         const double al = alpha[idx];
-        WarpEval<WarpCuda> f;
+        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
+        WarpEvalClass<WarpCuda, NK, VISC> f;
         f.t = &t; f.d = &d; f.kx = kx[idx]; f.kz = kz[idx]; f.alpha = al; f.nodes = 0; f.evals = 0;
         const int o = z_off[idx], n0 = z_off[idx + 1] - o;
         int cnt = -666, np = n0, st = kContourCapacity;
@@ -275,6 +279,7 @@ contour_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict
 
 // K4 mode_kernel: one warp per PSIMode.calculate -- sampling, D evaluations, AAA, zeros, zoom domains and
 // the secant polish all on the device (psi_mode.cuh); scratch: aaa_scratch_bytes(cap) per warp.
+template <int NK, bool VISC>
 __global__ void __launch_bounds__(kEvalThreads, 1)
 mode_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, int n_items,
             const int* __restrict__ dist, const double* __restrict__ kx, const double* __restrict__ kz,
@@ -293,7 +298,8 @@ mode_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ 
     while (next_item(queue, n_items, idx)) {
         const DistParams& d = dists[dist[idx]];
         const double al = alpha[idx];
-        WarpEval<WarpCuda> f;
+        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
+        WarpEvalClass<WarpCuda, NK, VISC> f;
         f.t = &t; f.d = &d; f.kx = kx[idx]; f.kz = kz[idx]; f.alpha = al; f.nodes = 0; f.evals = 0;
         ModeCfg cfg;
         cfg.dom = RectDom{domain[4 * idx], domain[4 * idx + 1], domain[4 * idx + 2], domain[4 * idx + 3]};
@@ -313,6 +319,16 @@ mode_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ 
         if (evals) atomicAdd(counters + 1, evals);
     }
 }
+
+#define PSI_CLASS_TABLE(NAME)                                                                      \
+    {NAME<0, false>, NAME<0, true>, NAME<1, false>, NAME<1, true>, NAME<2, false>, NAME<2, true>,    \
+     NAME<3, false>, NAME<3, true>}
+typedef decltype(&polish_kernel<0, false>) polish_kernel_t;
+typedef decltype(&contour_kernel<0, false>) contour_kernel_t;
+typedef decltype(&mode_kernel<0, false>) mode_kernel_t;
+static const polish_kernel_t kPolishKernels[kNumClasses] = PSI_CLASS_TABLE(polish_kernel);
+static const contour_kernel_t kContourKernels[kNumClasses] = PSI_CLASS_TABLE(contour_kernel);
+static const mode_kernel_t kModeKernels[kNumClasses] = PSI_CLASS_TABLE(mode_kernel);
 
 // DFMA-pipe peak: 8 independent FMA chains per thread, all in registers.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
@@ -375,9 +391,11 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
         for (int cls = 0; cls < kNumClasses; ++cls)
             CK(cudaFuncSetAttribute(eval_kernel_for(cls), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)c->table_smem));
-        CK(cudaFuncSetAttribute(polish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
-        CK(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
-        CK(cudaFuncSetAttribute(mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+        for (int cls = 0; cls < kNumClasses; ++cls) {
+            CK(cudaFuncSetAttribute(kPolishKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+            CK(cudaFuncSetAttribute(kContourKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+            CK(cudaFuncSetAttribute(kModeKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+        }
     }
     CK(cudaMalloc(&c->d_dists, sizeof(DistParams) * kMaxDists));
     CK(cudaMalloc(&c->d_counter, sizeof(unsigned long long) * 8));
@@ -619,15 +637,17 @@ int psi_internal_polish(psi_ctx* c, int n_items, const int* pidx, int n_params, 
     const int grid = std::min(c->sm_count, (n_items + warps - 1) / warps);
     CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
     NodeTableView t = table_view(c);
-    (void)mask;
+    for (int cls = 0; cls < kNumClasses; ++cls) {
+    if (!(mask & (1u << cls))) continue;
     CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
-    polish_kernel<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+    kPolishKernels[cls]<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
         t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, (const int*)d[0], (const int*)d[1],
         (const double*)d[2], (const double*)d[3], (const double*)d[4], (const double*)d[5], (const int*)d[6],
         (double2*)d[7], (const int*)d[8], (double2*)d[9], (int*)d[10], (int*)d[11], (int*)d[12], c->d_counter,
         c->d_counter + 4);
     c->launches++;
     CK(cudaGetLastError());
+    }
     unsigned long long cnt[2] = {0, 0};
     CK(cudaMemcpyAsync(out, d[9], 16 * nw, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(n_calls, d[10], 4 * ni, cudaMemcpyDeviceToHost, st));
@@ -670,10 +690,12 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     cudaStream_t st = c->stream;
     CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
     NodeTableView t = table_view(c);
-    (void)mask;
-    const int launches = 1;
+    int launches = 0;
+    for (int cls = 0; cls < kNumClasses; ++cls) {
+    if (!(mask & (1u << cls))) continue;
+    ++launches;
     CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
-    mode_kernel<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+    kModeKernels[cls]<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
         t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, (const int*)d[0], (const double*)d[1],
         (const double*)d[2], (const double*)d[3], (const double*)d[4], (const int*)d[5], (const double*)d[6],
         (const double*)d[7], (const int*)d[8], (const int*)d[9], (const double2*)d[10],
@@ -681,6 +703,7 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         (int*)d[14], c->d_counter, c->d_counter + 4);
     c->launches++;
     CK(cudaGetLastError());
+    }
     unsigned long long cnt[2] = {0, 0};
     CK(cudaMemcpyAsync(roots, d[11], 16 * ni * max_roots, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(n_roots, d[12], 4 * ni, cudaMemcpyDeviceToHost, st));
@@ -735,15 +758,17 @@ int psi_contour_batch_host(psi_ctx* c, int n_items, const int* dist, const doubl
     cudaStream_t st = c->stream;
     CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
     NodeTableView t = table_view(c);
-    (void)mask;
+    for (int cls = 0; cls < kNumClasses; ++cls) {
+    if (!(mask & (1u << cls))) continue;
     CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
-    contour_kernel<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+    kContourKernels[cls]<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
         t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, (const int*)d[0], (const double*)d[1],
         (const double*)d[2], (const double*)d[3], (const int*)d[4], (const double2*)d[5], (const double*)d[6],
         (const double*)d[7], (const int*)d[8], (double2*)c->d_contour_scratch, cap, (int*)d[9], (int*)d[10],
         (int*)d[11], c->d_counter, c->d_counter + 4);
     c->launches++;
     CK(cudaGetLastError());
+    }
     unsigned long long cnt[2] = {0, 0};
     CK(cudaMemcpyAsync(counts, d[9], 4 * ni, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(status, d[10], 4 * ni, cudaMemcpyDeviceToHost, st));

@@ -191,4 +191,20 @@ struct WarpEval {
     }
 };
 
+// Same, for ONE work class: the GPU kernels K2-K4 are compiled per class so that each carries a single
+// quadrature specialisation (the eight-way version is ~0.7 MB of machine code and thrashes the
+// instruction cache when every warp of an SM sits in a different phase of its state machine).
+template <class W, int NK, bool VISC>
+struct WarpEvalClass {
+    const NodeTableView* t;
+    const DistParams* d;
+    double kx, kz, alpha;
+    unsigned long long nodes;
+    long long evals;
+    PSI_NOINLINE cx operator()(cx w) {
+        ++evals;
+        return disp_eval_warp<W, NK, VISC>(*t, *d, w, kx, kz, alpha, nullptr, nodes);
+    }
+};
+
 }  // namespace psi
