@@ -158,7 +158,8 @@ disp_eval_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restri
                  const double* __restrict__ kz, const double* __restrict__ alpha,
                  const int* __restrict__ pidx, const double2* __restrict__ w, double2* __restrict__ D,
                  double2* __restrict__ M, unsigned long long* __restrict__ queue,
-                 unsigned long long* __restrict__ node_evals) {
+                 unsigned long long* __restrict__ node_evals, const long long* __restrict__ elem,
+                 int elem_cap) {
     const NodeTableView t = stage_table(gt, table_in_smem != 0);
     const int lane = threadIdx.x & 31;
     unsigned long long nodes = 0;
@@ -167,15 +168,18 @@ disp_eval_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restri
         if (lane == 0) idx = atomicAdd(queue, 1ull);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= (unsigned long long)n) break;
-        const long long pi = pidx != nullptr ? (long long)pidx[idx] : (broadcast ? 0 : (long long)idx);
+        // element mode (mode pipeline): point = entry e of the per-item sample buffers, item = e / cap
+        const long long e = elem != nullptr ? elem[idx] : (long long)idx;
+        const long long pi = elem != nullptr ? e / elem_cap
+                             : (pidx != nullptr ? (long long)pidx[idx] : (broadcast ? 0 : (long long)idx));
         const DistParams& d = dists[dist[pi]];
         const double al = alpha[pi];
         if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
-        const double2 wv = w[idx];
+        const double2 wv = w[e];
         cx m[7];
         const cx val = disp_eval_warp<WarpCuda, NK, VISC>(t, d, cx(wv.x, wv.y), kx[pi], kz[pi], al,
                                                           M != nullptr ? m : nullptr, nodes);
-        if (lane == 0) D[idx] = make_double2(val.re, val.im);
+        if (lane == 0) D[e] = make_double2(val.re, val.im);
         if (M != nullptr && lane < 7) {
             cx mv = m[0];
 #pragma unroll
@@ -188,7 +192,7 @@ disp_eval_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restri
 
 typedef void (*eval_kernel_t)(NodeTableView, int, const DistParams*, long long, int, const int*, const double*,
                               const double*, const double*, const int*, const double2*, double2*, double2*,
-                              unsigned long long*, unsigned long long*);
+                              unsigned long long*, unsigned long long*, const long long*, int);
 
 static eval_kernel_t eval_kernel_for(int cls) {
     switch (cls) {
@@ -203,6 +207,10 @@ static eval_kernel_t eval_kernel_for(int cls) {
     }
 }
 
+// phases of an item in the PSIMode pipeline (K4, below)
+enum ModePhase { kPhaseSample = 0, kPhaseAnalyze = 1, kPhasePolish = 2, kPhaseDecide = 3, kPhaseZoom = 4,
+                 kPhaseDone = 5 };
+
 // K3 polish_kernel: one warp per root search; the whole two-stage secant polish of all its start
 // values runs on the device, every D evaluated inline (psi_batch.cuh, polish_run).
 template <int NK, bool VISC>
@@ -212,20 +220,24 @@ polish_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict_
               const double* __restrict__ kz, const double* __restrict__ alpha,
               const double* __restrict__ dom, const int* __restrict__ off, double2* w0,
               const int* __restrict__ max_iter, double2* out, int* n_calls, int* max_conv, int* status,
-              unsigned long long* queue, unsigned long long* counters) {
+              unsigned long long* queue, unsigned long long* counters, int stride, const int* __restrict__ cnt,
+              const int* __restrict__ phase) {
     const NodeTableView t = stage_table(gt, table_in_smem != 0);
     const int lane = threadIdx.x & 31;
     unsigned long long nodes = 0, evals = 0;
     long long idx;
     while (next_item(queue, n_items, idx)) {
-        const int pi = pidx[idx];
+        if (phase != nullptr && phase[idx] != kPhasePolish) continue;       // mode pipeline: not this item's turn
+        const int pi = pidx != nullptr ? pidx[idx] : (int)idx;
         const DistParams& d = dists[dist[pi]];
         const double al = alpha[pi];
         if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
         WarpEvalClass<WarpCuda, NK, VISC> f;
         f.t = &t; f.d = &d; f.kx = kx[pi]; f.kz = kz[pi]; f.alpha = al; f.nodes = 0; f.evals = 0;
         const RectDom rd{dom[4 * idx], dom[4 * idx + 1], dom[4 * idx + 2], dom[4 * idx + 3]};
-        const int o = off[idx], n = off[idx + 1] - o;
+        // start values: packed with offsets (batch API) or strided per item (mode pipeline)
+        const long long o = off != nullptr ? (long long)off[idx] : idx * (long long)stride;
+        const int n = off != nullptr ? off[idx + 1] - off[idx] : cnt[idx];
         int conv = 0, st = 0;
         const int calls = polish_run(f, rd, reinterpret_cast<cx*>(w0 + o), n, max_iter[idx],
                                      reinterpret_cast<cx*>(out + o), &conv, &st);
@@ -277,46 +289,136 @@ contour_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict
     }
 }
 
-// K4 mode_kernel: one warp per PSIMode.calculate -- sampling, D evaluations, AAA, zeros, zoom domains and
-// the secant polish all on the device (psi_mode.cuh); scratch: aaa_scratch_bytes(cap) per warp.
-template <int NK, bool VISC>
-__global__ void __launch_bounds__(kEvalThreads, 1)
-mode_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, int n_items,
-            const int* __restrict__ dist, const double* __restrict__ kx, const double* __restrict__ kz,
-            const double* __restrict__ alpha, const double* __restrict__ domain,
-            const int* __restrict__ iparams, const double* __restrict__ dparams,
-            const double* __restrict__ uni, const int* __restrict__ uni_off,
-            const int* __restrict__ guess_off, const double2* __restrict__ guesses, unsigned char* scratch,
-            size_t scratch_per_warp, int cap, int max_roots, double2* roots, int* n_roots, int* n_calls,
-            int* status, unsigned long long* queue, unsigned long long* counters) {
-    const NodeTableView t = stage_table(gt, table_in_smem != 0);
+// ---- K4: the PSIMode.calculate pipeline.  Per-item state lives in device memory; every stage is a
+// homogeneous kernel over all items (sampling -> K1 -> AAA analysis -> K3 polish -> decision), repeated
+// once per zoom level.  Homogeneous stages keep the SMs' instruction caches and FP64 pipes busy; the
+// single-warp form of the same search (mode_run in psi_mode.cuh) is what the CPU harness exercises.
+
+struct ModeDev {            // device pointers of the per-item state (n items, cap samples, P start values)
+    cx *Z, *F, *w0, *pol, *zoom, *roots;
+    double* box_dx;
+    int *M, *level, *upos, *phase, *n0, *max_iter, *n_zoom, *calls, *status, *n_out, *pcalls, *pconv, *pstat;
+    long long* elem;                    // request list for K1 (element indices into Z/F)
+    unsigned long long* counters;       // [0] number of requests, [1] items still active
+    int cap, P, max_roots;
+};
+
+// thread per item: draw the next batch of sample points (initial domain + guess domains, or the zoom
+// boxes of the finished level) from the item's random stream and queue them for K1
+__global__ void mode_sample_kernel(ModeDev m, int n_items, const double* __restrict__ domain,
+                                   const int* __restrict__ iparams, const double* __restrict__ uni,
+                                   const int* __restrict__ uni_off, const int* __restrict__ guess_off,
+                                   const double2* __restrict__ guesses) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const int ph = m.phase[i];
+    if (ph != kPhaseSample && ph != kPhaseZoom) return;
+    const RectDom dom{domain[4 * i], domain[4 * i + 1], domain[4 * i + 2], domain[4 * i + 3]};
+    const int ns = iparams[3 * i];
+    const double* u = uni + uni_off[i];
+    cx* Z = m.Z + (size_t)i * m.cap;
+    int M = m.M[i], upos = m.upos[i];
+    const int first = M;
+    auto box = [&](double x0, double x1, double y0, double y1) {
+        for (int k = 0; k < ns; ++k)
+            Z[M + k] = cx(add_rn(x0, mul_rn(x1 - x0, u[upos + k])), add_rn(y0, mul_rn(y1 - y0, u[upos + ns + k])));
+        M += ns; upos += 2 * ns;
+    };
+    auto clamped = [&](double sx, double sy, cx c) {
+        double re = c.re, im = c.im;
+        if (re < dom.xmin + 0.5 * sx) re = dom.xmin + 0.5 * sx;
+        if (re > dom.xmax - 0.5 * sx) re = dom.xmax - 0.5 * sx;
+        if (im < dom.ymin + 0.5 * sy) im = dom.ymin + 0.5 * sy;
+        if (im > dom.ymax - 0.5 * sy) im = dom.ymax - 0.5 * sy;
+        box(re - 0.5 * sx, re + 0.5 * sx, im - 0.5 * sy, im + 0.5 * sy);
+    };
+    if (ph == kPhaseSample) {
+        box(dom.xmin, dom.xmax, dom.ymin, dom.ymax);
+        for (int g = guess_off[i]; g < guess_off[i + 1]; ++g) {
+            const double side = fmin(1.0e-3, fabs(guesses[g].y) * 4.0);
+            clamped(side, side, cx(guesses[g].x, guesses[g].y));
+        }
+    } else {
+        const double dx = m.box_dx[i];
+        for (int q = 0; q < m.n_zoom[i]; ++q) {
+            const cx c = m.zoom[4 * (size_t)i + q];
+            clamped(dx, fmin(0.1, fabs(c.im)), c);
+        }
+        m.level[i] += 1;
+    }
+    const int n_new = M - first;
+    m.calls[i] += n_new;
+    m.M[i] = M; m.upos[i] = upos;
+    m.phase[i] = kPhaseAnalyze;
+    const unsigned long long pos = atomicAdd(m.counters, (unsigned long long)n_new);
+    for (int k = 0; k < n_new; ++k) m.elem[pos + k] = (long long)i * m.cap + first + k;
+}
+
+// warp per item: AAA analysis of the current samples (mode_analyze) -> polish start values + zoom plan
+__global__ void __launch_bounds__(256)
+mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, const int* __restrict__ iparams,
+                    const double* __restrict__ dparams, const int* __restrict__ guess_off,
+                    unsigned char* scratch, size_t scratch_per_warp, unsigned long long* queue) {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const AAAScratch sc = aaa_carve(scratch + (size_t)warp_global * scratch_per_warp, cap);
-    unsigned long long nodes = 0, evals = 0;
+    AAAScratch sc = aaa_carve(scratch + (size_t)warp_global * scratch_per_warp, m.cap);
     long long idx;
     while (next_item(queue, n_items, idx)) {
-        const DistParams& d = dists[dist[idx]];
-        const double al = alpha[idx];
-        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
-        WarpEvalClass<WarpCuda, NK, VISC> f;
-        f.t = &t; f.d = &d; f.kx = kx[idx]; f.kz = kz[idx]; f.alpha = al; f.nodes = 0; f.evals = 0;
+        if (m.phase[idx] != kPhaseAnalyze) continue;
         ModeCfg cfg;
         cfg.dom = RectDom{domain[4 * idx], domain[4 * idx + 1], domain[4 * idx + 2], domain[4 * idx + 3]};
         cfg.n_sample = iparams[3 * idx]; cfg.max_zoom = iparams[3 * idx + 1]; cfg.max_secant = iparams[3 * idx + 2];
         cfg.tol = dparams[2 * idx]; cfg.clean_tol = dparams[2 * idx + 1];
-        const int g0 = guess_off[idx], ng = guess_off[idx + 1] - g0;
-        int nr = 0, nc = 0;
-        const int st = mode_run<WarpCuda>(f, cfg, reinterpret_cast<const cx*>(guesses + g0), ng,
-                                          uni + uni_off[idx], sc,
-                                          reinterpret_cast<cx*>(roots + (size_t)idx * max_roots), max_roots,
-                                          &nr, &nc);
-        if (lane == 0) { n_roots[idx] = nr; n_calls[idx] = nc; status[idx] = st; }
-        nodes += f.nodes; evals += (unsigned long long)f.evals;
+        sc.Z = m.Z + (size_t)idx * m.cap;                 // analyse the item's own sample buffers in place
+        sc.F = m.F + (size_t)idx * m.cap;
+        sc.w0 = m.w0 + (size_t)idx * m.P;
+        AAAState st;
+        st.M = m.M[idx]; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol;
+        st.dom = cfg.dom; st.memo_next = 0;
+        ModePlan plan;
+        const bool ok = mode_analyze<WarpCuda>(cfg, m.level[idx], guess_off[idx + 1] - guess_off[idx], sc, st, plan);
+        __syncwarp();
+        if (lane == 0) {
+            if (!ok) {
+                m.status[idx] = kModeBadSamples; m.phase[idx] = kPhaseDone; m.n_out[idx] = 0;
+            } else {
+                m.n0[idx] = plan.n0; m.max_iter[idx] = plan.max_iter; m.n_zoom[idx] = plan.n_zoom;
+                m.box_dx[idx] = plan.box_dx;
+                for (int q = 0; q < plan.n_zoom; ++q) m.zoom[4 * (size_t)idx + q] = plan.zoom[q];
+                m.pcalls[idx] = 0; m.pconv[idx] = 0; m.pstat[idx] = 0;
+                m.phase[idx] = plan.n0 > 0 ? kPhasePolish : kPhaseDecide;
+            }
+        }
     }
-    if (counters != nullptr && lane == 0) {
-        if (nodes) atomicAdd(counters, nodes);
-        if (evals) atomicAdd(counters + 1, evals);
+}
+
+// thread per item: collect the polished roots, then finish or schedule the zoom boxes (psi_mode.py:312-331)
+__global__ void mode_decide_kernel(ModeDev m, int n_items, const double* __restrict__ domain,
+                                   const int* __restrict__ iparams) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const int ph = m.phase[i];
+    if (ph != kPhasePolish && ph != kPhaseDecide) return;
+    const RectDom dom{domain[4 * i], domain[4 * i + 1], domain[4 * i + 2], domain[4 * i + 3]};
+    if (m.pstat[i] != 0) { m.status[i] = kModeZeroTol; m.phase[i] = kPhaseDone; m.n_out[i] = 0; return; }
+    m.calls[i] += m.pcalls[i];
+    int n_out = 0;
+    bool grow = false;
+    const int n0 = ph == kPhasePolish ? m.n0[i] : 0;
+    for (int k = 0; k < n0; ++k) {
+        const cx z = m.pol[(size_t)i * m.P + k];
+        if (!dom.is_in(z)) continue;
+        if (n_out < m.max_roots) m.roots[(size_t)i * m.max_roots + n_out] = z;
+        ++n_out;
+        if (z.im > 0.0) grow = true;
+    }
+    m.n_out[i] = n_out;
+    if (grow || m.level[i] == iparams[3 * i + 1] || m.n_zoom[i] == 0) {
+        m.phase[i] = kPhaseDone;
+        m.status[i] = n_out > m.max_roots ? kModeTruncated : kModeOk;
+    } else {
+        m.phase[i] = kPhaseZoom;
+        atomicAdd(m.counters + 1, 1ull);
     }
 }
 
@@ -325,10 +427,8 @@ mode_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ 
      NAME<3, false>, NAME<3, true>}
 typedef decltype(&polish_kernel<0, false>) polish_kernel_t;
 typedef decltype(&contour_kernel<0, false>) contour_kernel_t;
-typedef decltype(&mode_kernel<0, false>) mode_kernel_t;
 static const polish_kernel_t kPolishKernels[kNumClasses] = PSI_CLASS_TABLE(polish_kernel);
 static const contour_kernel_t kContourKernels[kNumClasses] = PSI_CLASS_TABLE(contour_kernel);
-static const mode_kernel_t kModeKernels[kNumClasses] = PSI_CLASS_TABLE(mode_kernel);
 
 // DFMA-pipe peak: 8 independent FMA chains per thread, all in registers.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
@@ -394,12 +494,11 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
         for (int cls = 0; cls < kNumClasses; ++cls) {
             CK(cudaFuncSetAttribute(kPolishKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
             CK(cudaFuncSetAttribute(kContourKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
-            CK(cudaFuncSetAttribute(kModeKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
         }
     }
     CK(cudaMalloc(&c->d_dists, sizeof(DistParams) * kMaxDists));
-    CK(cudaMalloc(&c->d_counter, sizeof(unsigned long long) * 8));
-    CK(cudaMemset(c->d_counter, 0, sizeof(unsigned long long) * 8));
+    CK(cudaMalloc(&c->d_counter, sizeof(unsigned long long) * 16));
+    CK(cudaMemset(c->d_counter, 0, sizeof(unsigned long long) * 16));
     *out = c;
     return PSI_OK;
 }
@@ -463,7 +562,8 @@ int psi_dist_get_background(psi_ctx* c, int dist, double out[5]) {
 static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* dist, const double* kx,
                             const double* kz, const double* alpha, const double* w, double* D,
                             double* M, unsigned long long* node_evals_dev, unsigned class_mask,
-                            cudaStream_t st, const int* pidx = nullptr) {
+                            cudaStream_t st, const int* pidx = nullptr, const long long* elem = nullptr,
+                            int elem_cap = 1) {
     if (n == 0) return PSI_OK;
     const int warps = kEvalThreads / 32;
     long long want = (n + warps - 1) / warps;
@@ -476,7 +576,7 @@ static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* d
         eval_kernel_t k = eval_kernel_for(cls);
         k<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
             t, c->table_in_smem ? 1 : 0, c->d_dists, n, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w, (double2*)D,
-            (double2*)M, c->d_counter, node_evals_dev);
+            (double2*)M, c->d_counter, node_evals_dev, elem, elem_cap);
         c->launches++;
         CK(cudaGetLastError());
     }
@@ -644,7 +744,7 @@ int psi_internal_polish(psi_ctx* c, int n_items, const int* pidx, int n_params, 
         t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, (const int*)d[0], (const int*)d[1],
         (const double*)d[2], (const double*)d[3], (const double*)d[4], (const double*)d[5], (const int*)d[6],
         (double2*)d[7], (const int*)d[8], (double2*)d[9], (int*)d[10], (int*)d[11], (int*)d[12], c->d_counter,
-        c->d_counter + 4);
+        c->d_counter + 4, 0, nullptr, nullptr);
     c->launches++;
     CK(cudaGetLastError());
     }
@@ -669,49 +769,107 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     bool ok;
     const unsigned mask = class_mask_of(c, n_items, dist, alpha, &ok);
     if (!ok) return fail(PSI_ERR_ARG, "distribution id out of range");
-    const int warps = kEvalThreads / 32;
-    const int grid = std::min(c->sm_count, (n_items + warps - 1) / warps);
+    int max_zoom = 0, max_req = 0;
+    for (int i = 0; i < n_items; ++i) {
+        const int ns = iparams[3 * i], ng = guess_off[i + 1] - guess_off[i];
+        if (ns * (1 + ng + 4 * iparams[3 * i + 1]) > cap) return fail(PSI_ERR_CAPACITY, "sample capacity too small");
+        max_zoom = std::max(max_zoom, iparams[3 * i + 1]);
+        max_req = std::max(max_req, ns * std::max(1 + ng, 4));
+    }
+    const size_t ni = (size_t)n_items, ng = (size_t)guess_off[n_items];
+    const int P = cap / 2 + 2;
+    // AAA scratch: one area per warp of the analysis kernel
+    const int awarps = 256 / 32;
+    const int agrid = std::min(c->sm_count * 4, (n_items + awarps - 1) / awarps);
     const size_t per_warp = (aaa_scratch_bytes(cap) + 255) & ~(size_t)255;
-    const size_t need = per_warp * (size_t)c->sm_count * warps;
+    const size_t need = per_warp * (size_t)c->sm_count * 4 * awarps;
     if (need > c->mode_scratch_bytes) {
         if (c->d_mode_scratch) CK(cudaFree(c->d_mode_scratch));
         c->d_mode_scratch = nullptr; c->mode_scratch_bytes = 0;
         CK(cudaMalloc(&c->d_mode_scratch, need));
         c->mode_scratch_bytes = need;
     }
-    const size_t ni = (size_t)n_items, ng = (size_t)guess_off[n_items];
-    StageItem it[] = {{dist, 4 * ni}, {kx, 8 * ni}, {kz, 8 * ni}, {alpha, 8 * ni}, {domain, 32 * ni},
-                      {iparams, 12 * ni}, {dparams, 16 * ni}, {uni, 8 * (size_t)n_uni}, {uni_off, 4 * ni},
-                      {guess_off, 4 * (ni + 1)}, {guesses, 16 * std::max<size_t>(ng, 1)},
-                      {nullptr, 16 * ni * max_roots}, {nullptr, 4 * ni}, {nullptr, 4 * ni}, {nullptr, 4 * ni}};
-    char* d[15];
-    int rc = stage_upload(c, it, 15, 0, d, nullptr);
+    // inputs + per-item state in one staging allocation
+    const size_t nreq = ni * (size_t)max_req;
+    StageItem it[] = {
+        {dist, 4 * ni}, {kx, 8 * ni}, {kz, 8 * ni}, {alpha, 8 * ni}, {domain, 32 * ni},            // 0-4
+        {iparams, 12 * ni}, {dparams, 16 * ni}, {uni, 8 * (size_t)n_uni}, {uni_off, 4 * ni},       // 5-8
+        {guess_off, 4 * (ni + 1)}, {guesses, 16 * std::max<size_t>(ng, 1)},                        // 9-10
+        {nullptr, 16 * ni * cap}, {nullptr, 16 * ni * cap},                                        // 11 Z, 12 F
+        {nullptr, 16 * ni * P}, {nullptr, 16 * ni * P}, {nullptr, 64 * ni},                        // 13 w0, 14 pol, 15 zoom
+        {nullptr, 16 * ni * max_roots}, {nullptr, 8 * ni},                                         // 16 roots, 17 box_dx
+        {nullptr, 4 * ni * 13}, {nullptr, 8 * nreq}};                                              // 18 ints, 19 elem
+    char* d[20];
+    int rc = stage_upload(c, it, 20, 0, d, nullptr);
     if (rc != PSI_OK) return rc;
     cudaStream_t st = c->stream;
+    ModeDev m;
+    m.Z = (cx*)d[11]; m.F = (cx*)d[12]; m.w0 = (cx*)d[13]; m.pol = (cx*)d[14]; m.zoom = (cx*)d[15];
+    m.roots = (cx*)d[16]; m.box_dx = (double*)d[17];
+    int* ints = (int*)d[18];
+    m.M = ints; m.level = ints + ni; m.upos = ints + 2 * ni; m.phase = ints + 3 * ni; m.n0 = ints + 4 * ni;
+    m.max_iter = ints + 5 * ni; m.n_zoom = ints + 6 * ni; m.calls = ints + 7 * ni; m.status = ints + 8 * ni;
+    m.n_out = ints + 9 * ni; m.pcalls = ints + 10 * ni; m.pconv = ints + 11 * ni; m.pstat = ints + 12 * ni;
+    m.elem = (long long*)d[19];
+    m.counters = c->d_counter + 6;
+    m.cap = cap; m.P = P; m.max_roots = max_roots;
+    CK(cudaMemsetAsync(ints, 0, 4 * ni * 13, st));                         // phase 0 = kPhaseSample everywhere
     CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
     NodeTableView t = table_view(c);
+    const int tgrid = (n_items + 255) / 256;
+    const int warps = kEvalThreads / 32;
+    const int pgrid = std::min(c->sm_count, (n_items + warps - 1) / warps);
     int launches = 0;
-    for (int cls = 0; cls < kNumClasses; ++cls) {
-    if (!(mask & (1u << cls))) continue;
-    ++launches;
-    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
-    kModeKernels[cls]<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
-        t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, (const int*)d[0], (const double*)d[1],
-        (const double*)d[2], (const double*)d[3], (const double*)d[4], (const int*)d[5], (const double*)d[6],
-        (const double*)d[7], (const int*)d[8], (const int*)d[9], (const double2*)d[10],
-        (unsigned char*)c->d_mode_scratch, per_warp, cap, max_roots, (double2*)d[11], (int*)d[12], (int*)d[13],
-        (int*)d[14], c->d_counter, c->d_counter + 4);
-    c->launches++;
-    CK(cudaGetLastError());
+    long long evals = 0;
+    for (int round = 0; round <= max_zoom; ++round) {
+        CK(cudaMemsetAsync(m.counters, 0, 2 * sizeof(unsigned long long), st));
+        mode_sample_kernel<<<tgrid, 256, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
+                                                  (const double*)d[7], (const int*)d[8], (const int*)d[9],
+                                                  (const double2*)d[10]);
+        CK(cudaGetLastError());
+        unsigned long long cnt[2] = {0, 0};
+        CK(cudaMemcpyAsync(cnt, m.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const long long n_req = (long long)cnt[0];
+        if (n_req == 0) break;
+        evals += n_req;
+        rc = launch_disp_eval(c, n_req, 0, (const int*)d[0], (const double*)d[1], (const double*)d[2],
+                              (const double*)d[3], (const double*)m.Z, (double*)m.F, nullptr, c->d_counter + 4,
+                              mask, st, nullptr, m.elem, cap);
+        if (rc != PSI_OK) return rc;
+        CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+        mode_analyze_kernel<<<agrid, 256, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
+                                                   (const double*)d[6], (const int*)d[9],
+                                                   (unsigned char*)c->d_mode_scratch, per_warp, c->d_counter);
+        CK(cudaGetLastError());
+        for (int cls = 0; cls < kNumClasses; ++cls) {
+            if (!(mask & (1u << cls))) continue;
+            CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+            kPolishKernels[cls]<<<pgrid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+                t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, nullptr, (const int*)d[0],
+                (const double*)d[1], (const double*)d[2], (const double*)d[3], (const double*)d[4], nullptr,
+                (double2*)m.w0, m.max_iter, (double2*)m.pol, m.pcalls, m.pconv, m.pstat, c->d_counter,
+                c->d_counter + 4, P, m.n0, m.phase);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        CK(cudaMemsetAsync(m.counters, 0, 2 * sizeof(unsigned long long), st));
+        mode_decide_kernel<<<tgrid, 256, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5]);
+        CK(cudaGetLastError());
+        launches += 4;
+        c->launches += 4;
+        CK(cudaMemcpyAsync(cnt, m.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (cnt[1] == 0) break;                                          // nobody wants to zoom
     }
-    unsigned long long cnt[2] = {0, 0};
-    CK(cudaMemcpyAsync(roots, d[11], 16 * ni * max_roots, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(n_roots, d[12], 4 * ni, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(n_calls, d[13], 4 * ni, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(status, d[14], 4 * ni, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(cnt, c->d_counter + 4, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    unsigned long long cnt2[2] = {0, 0};
+    CK(cudaMemcpyAsync(roots, m.roots, 16 * ni * max_roots, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_roots, m.n_out, 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_calls, m.calls, 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, m.status, 4 * ni, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cnt2, c->d_counter + 4, sizeof(cnt2), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (stats) { stats[0] = launches; stats[1] = (long long)cnt[1]; stats[2] = (long long)cnt[0]; }
+    if (stats) { stats[0] = launches; stats[1] = evals + (long long)cnt2[1]; stats[2] = (long long)cnt2[0]; }
     return PSI_OK;
 }
 

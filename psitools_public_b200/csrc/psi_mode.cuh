@@ -51,13 +51,97 @@ PSI_HD void mode_extra_domain(EVAL& f, const AAAScratch& s, AAAState& st, const 
     mode_sample<W>(f, s, st, uni, upos, cfg.n_sample, re - 0.5 * sx, re + 0.5 * sx, im - 0.5 * sy, im + 0.5 * sy);
 }
 
+// What the analysis of one zoom level hands to the polish and to the next sampling step
+struct ModePlan {
+    int n0;          // number of polish start values (written to s.w0)
+    int max_iter;    // secant iteration budget of this level
+    int n_zoom;      // zoom boxes to open if no growing root is found
+    cx zoom[4];
+    double box_dx;   // width of the zoom boxes in Re
+};
+
+// AAA + zero selection of one zoom level (psi_mode.py:147-310): rational approximation of the current
+// samples, clean_tol halving until enough support points and one growing zero, zoom candidates, start
+// values of the polish.  Returns false when the samples are not finite (ValueError in the reference).
+template <class W>
+PSI_HD bool mode_analyze(const ModeCfg& cfg, int level, int n_guess, const AAAScratch& s, AAAState& st,
+                         ModePlan& plan) {
+    st.clean_tol = cfg.clean_tol;
+    if (!aaa_calculate<W>(s, st, false)) return false;
+    int nz = aaa_zeros<W>(s, st);
+    // halve clean_tol until enough support points and one growing zero inside the domain (:174-217)
+    const int need = 4 * (1 + level + n_guess);
+    for (;;) {
+        bool growing = false;
+        for (int k = 0; k < nz; ++k) {
+            const cx z = s.roots[k];
+            if (cfg.dom.is_in(z) && z.im > 0.0) growing = true;
+        }
+        if (st.m >= need && growing) break;
+        st.clean_tol = 0.5 * st.clean_tol;
+        if (st.clean_tol < st.tol) break;
+        aaa_calculate<W>(s, st, true);
+        nz = aaa_zeros<W>(s, st);
+    }
+    // zoom candidates: below the top of the box, inside in Re; by decreasing Im, at least box_dx
+    // apart in Re, at most four (:236-261)
+    plan.box_dx = pow(10.0, -1.0 - 0.5 * level);
+    plan.n_zoom = 0;
+    {
+        int nc = 0;
+        for (int k = 0; k < nz; ++k) {
+            const cx z = s.roots[k];
+            if (z.im < cfg.dom.ymax && z.re < cfg.dom.xmax && z.re > cfg.dom.xmin) ++nc;
+        }
+        W::sync();
+        for (int k = W::lane(); k < nz; k += W::width) {       // rank by Im (ascending) into tmp
+            const cx z = s.roots[k];
+            if (!(z.im < cfg.dom.ymax && z.re < cfg.dom.xmax && z.re > cfg.dom.xmin)) continue;
+            int rank = 0;
+            for (int l = 0; l < nz; ++l) {
+                const cx y = s.roots[l];
+                if (!(y.im < cfg.dom.ymax && y.re < cfg.dom.xmax && y.re > cfg.dom.xmin)) continue;
+                if (y.im < z.im || (y.im == z.im && l < k)) ++rank;
+            }
+            s.tmp[rank] = z;
+        }
+        W::sync();
+        for (int i = nc - 1; i >= 0 && plan.n_zoom < 4; --i) {
+            const cx z = s.tmp[i];
+            bool ok = true;
+            for (int q = 0; q < plan.n_zoom; ++q) if (fabs(z.re - plan.zoom[q].re) < plan.box_dx) ok = false;
+            if (ok) plan.zoom[plan.n_zoom++] = z;
+        }
+    }
+    // start values of the polish: zeros inside the domain, else the least damped candidate
+    int n0 = 0;
+    W::sync();
+    if (W::lane() == 0) {
+        int c = 0;
+        for (int k = 0; k < nz; ++k) if (cfg.dom.is_in(s.roots[k])) s.w0[c++] = s.roots[k];
+    }
+    for (int k = 0; k < nz; ++k) if (cfg.dom.is_in(s.roots[k])) ++n0;
+    plan.max_iter = cfg.max_secant;
+    if (level < cfg.max_zoom) plan.max_iter = cfg.n_sample;
+    if (n0 == 0 && plan.n_zoom > 0) {
+        if (W::lane() == 0) s.w0[0] = plan.zoom[0];
+        n0 = 1;
+        plan.max_iter = 5;
+    }
+    W::sync();
+    plan.n0 = n0;
+    return true;
+}
+
 // Returns a ModeStatus; out_roots[0..min(*n_roots, max_roots)) receive the roots inside the domain,
-// *n_calls the reference's n_function_call.
+// *n_calls the reference's n_function_call.  (Single-warp form of the whole search; the GPU library runs
+// the same pieces as a pipeline of homogeneous kernels, see mode_pipeline in psi_b200.cu.)
 template <class W, class EVAL>
 PSI_HD int mode_run(EVAL& f, const ModeCfg& cfg, const cx* guesses, int n_guess, const double* uni,
                     const AAAScratch& s, cx* out_roots, int max_roots, int* n_roots, int* n_calls) {
     AAAState st;
     st.M = 0; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol; st.dom = cfg.dom;
+    st.memo_next = 0;
     int upos = 0, calls = 0;
     *n_roots = 0; *n_calls = 0;
     const int n_domains_max = 1 + n_guess + 4 * cfg.max_zoom;
@@ -73,89 +157,24 @@ PSI_HD int mode_run(EVAL& f, const ModeCfg& cfg, const cx* guesses, int n_guess,
 
     int n_out = 0;
     for (int level = 0; level <= cfg.max_zoom; ++level) {
-        st.clean_tol = cfg.clean_tol;
-        if (!aaa_calculate<W>(s, st, false)) { *n_calls = calls; return kModeBadSamples; }
-        int nz = aaa_zeros<W>(s, st);
-        // halve clean_tol until enough support points and one growing zero inside the domain (:174-217)
-        const int need = 4 * (1 + level + n_guess);
-        for (;;) {
-            bool growing = false;
-            for (int k = 0; k < nz; ++k) {
-                const cx z = s.roots[k];
-                if (cfg.dom.is_in(z) && z.im > 0.0) growing = true;
-            }
-            if (st.m >= need && growing) break;
-            st.clean_tol = 0.5 * st.clean_tol;
-            if (st.clean_tol < st.tol) break;
-            aaa_calculate<W>(s, st, true);
-            nz = aaa_zeros<W>(s, st);
-        }
-        // zoom candidates: below the top of the box, inside in Re; by decreasing Im, at least box_dx
-        // apart in Re, at most four (:236-261)
-        const double box_dx = pow(10.0, -1.0 - 0.5 * level);
-        cx zoom[4];
-        int n_zoom = 0;
-        {
-            // rank the candidates by Im (ascending) into tmp
-            int nc = 0;
-            for (int k = 0; k < nz; ++k) {
-                const cx z = s.roots[k];
-                if (z.im < cfg.dom.ymax && z.re < cfg.dom.xmax && z.re > cfg.dom.xmin) ++nc;
-            }
-            W::sync();
-            for (int k = W::lane(); k < nz; k += W::width) {
-                const cx z = s.roots[k];
-                if (!(z.im < cfg.dom.ymax && z.re < cfg.dom.xmax && z.re > cfg.dom.xmin)) continue;
-                int rank = 0;
-                for (int l = 0; l < nz; ++l) {
-                    const cx y = s.roots[l];
-                    if (!(y.im < cfg.dom.ymax && y.re < cfg.dom.xmax && y.re > cfg.dom.xmin)) continue;
-                    if (y.im < z.im || (y.im == z.im && l < k)) ++rank;
-                }
-                s.tmp[rank] = z;
-            }
-            W::sync();
-            for (int i = nc - 1; i >= 0 && n_zoom < 4; --i) {
-                const cx z = s.tmp[i];
-                bool ok = true;
-                // the distance rule is applied against the FULL list before truncation to four
-                // (:246-258); candidates beyond the fourth never matter for the first four
-                for (int q = 0; q < n_zoom; ++q) if (fabs(z.re - zoom[q].re) < box_dx) ok = false;
-                if (ok) zoom[n_zoom++] = z;
-            }
-        }
-        // start values of the polish: zeros inside the domain, else the least damped candidate
-        int n0 = 0;
-        W::sync();
-        if (W::lane() == 0) {
-            int c = 0;
-            for (int k = 0; k < nz; ++k) if (cfg.dom.is_in(s.roots[k])) s.w0[c++] = s.roots[k];
-        }
-        for (int k = 0; k < nz; ++k) if (cfg.dom.is_in(s.roots[k])) ++n0;
-        int max_iter = cfg.max_secant;
-        if (level < cfg.max_zoom) max_iter = cfg.n_sample;
-        if (n0 == 0 && n_zoom > 0) {
-            if (W::lane() == 0) s.w0[0] = zoom[0];
-            n0 = 1;
-            max_iter = 5;
-        }
-        W::sync();
+        ModePlan plan;
+        if (!mode_analyze<W>(cfg, level, n_guess, s, st, plan)) { *n_calls = calls; return kModeBadSamples; }
         int conv = 0, pst = 0;
-        calls += polish_run(f, cfg.dom, s.w0, n0, max_iter, s.pol, &conv, &pst);
+        calls += polish_run(f, cfg.dom, s.w0, plan.n0, plan.max_iter, s.pol, &conv, &pst);
         W::sync();
         if (pst != 0) { *n_calls = calls; return kModeZeroTol; }
         n_out = 0;
         bool grow = false;
-        for (int k = 0; k < n0; ++k) {
+        for (int k = 0; k < plan.n0; ++k) {
             const cx z = s.pol[k];
             if (!cfg.dom.is_in(z)) continue;
             if (n_out < max_roots && W::lane() == 0) out_roots[n_out] = z;
             ++n_out;
             if (z.im > 0.0) grow = true;
         }
-        if (grow || level == cfg.max_zoom || n_zoom == 0) break;
-        for (int q = 0; q < n_zoom; ++q) {
-            mode_extra_domain<W>(f, s, st, cfg, uni, upos, box_dx, fmin(0.1, fabs(zoom[q].im)), zoom[q]);
+        if (grow || level == cfg.max_zoom || plan.n_zoom == 0) break;
+        for (int q = 0; q < plan.n_zoom; ++q) {
+            mode_extra_domain<W>(f, s, st, cfg, uni, upos, plan.box_dx, fmin(0.1, fabs(plan.zoom[q].im)), plan.zoom[q]);
             calls += cfg.n_sample;
         }
     }

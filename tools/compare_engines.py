@@ -1,5 +1,7 @@
+"""Compare the device (K4 pipeline) and native (host LAPACK AAA) engines on an n x n PSIMode map:
+de-duplicated root sets per pixel and wall time.  usage: python tools/compare_engines.py [n]"""
 import sys, time, os, numpy as np
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import os; _R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, 'tests'))
 from psitools_public_b200 import PSIMode, TanhSinhNoDeepCopy
 from test_host_logic import same_root_sets
 from test_grid_refine import distinct
