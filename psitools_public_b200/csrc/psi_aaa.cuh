@@ -54,14 +54,19 @@ struct AAAScratch {
     double* memo_res;  // [kMemoSlots]
     int* memo_mask;    // [kMemoSlots * cap]
     int* memo_m;       // [kMemoSlots]   number of support points of the entry, -1 = empty
+    cx* memo_pole;     // [kMemoSlots * ncol]  per pole inside the domain: (residue ratio, sample to drop)
+    cx* memo_zero;     // [kMemoSlots * ncol]  zeros of the approximant
+    int* memo_np;      // [kMemoSlots]   number of stored pole decisions, -1 = not computed yet
+    int* memo_nz;      // [kMemoSlots]   number of stored zeros, -1 = not computed yet
+    double* nrm;       // [ncol]  squared column norms (Jacobi)
     int cap, ncol;
 };
 
 PSI_HD size_t aaa_scratch_bytes(int cap) {
     const size_t ncol = (size_t)cap / 2 + 2;
-    return sizeof(cx) * (2 * (size_t)cap + (size_t)cap * ncol + ncol * ncol + (6 + kMemoSlots) * ncol) +
-           sizeof(double) * ((2 + kMemoSlots) * (size_t)cap + kMemoSlots) +
-           sizeof(int) * ((3 + kMemoSlots) * (size_t)cap + ncol + kMemoSlots) + 256;
+    return sizeof(cx) * (2 * (size_t)cap + (size_t)cap * ncol + ncol * ncol + (6 + 3 * kMemoSlots) * ncol) +
+           sizeof(double) * ((2 + kMemoSlots) * (size_t)cap + kMemoSlots + ncol) +
+           sizeof(int) * ((3 + kMemoSlots) * (size_t)cap + ncol + 3 * kMemoSlots) + 256;
 }
 
 PSI_HD AAAScratch aaa_carve(void* base, int cap) {
@@ -80,17 +85,22 @@ PSI_HD AAAScratch aaa_carve(void* base, int cap) {
     s.w0 = c; c += ncol;
     s.pol = c; c += ncol;
     s.memo_w = c; c += (size_t)kMemoSlots * ncol;
+    s.memo_pole = c; c += (size_t)kMemoSlots * ncol;
+    s.memo_zero = c; c += (size_t)kMemoSlots * ncol;
     double* d = reinterpret_cast<double*>(c);
     s.R = d; d += cap;
     s.g_R = d; d += cap;
     s.memo_R = d; d += (size_t)kMemoSlots * cap;
     s.memo_res = d; d += kMemoSlots;
+    s.nrm = d; d += ncol;
     int* i = reinterpret_cast<int*>(d);
     s.mask = i; i += cap;
     s.off = i; i += cap;
     s.g_mask = i; i += cap;
     s.memo_mask = i; i += (size_t)kMemoSlots * cap;
     s.memo_m = i; i += kMemoSlots;
+    s.memo_np = i; i += kMemoSlots;
+    s.memo_nz = i; i += kMemoSlots;
     s.on = i;
     return s;
 }
@@ -103,6 +113,7 @@ struct AAAState {
     double tol, clean_tol;
     RectDom dom;
     int memo_next;  // next memo slot to overwrite
+    int slot;       // memo slot that holds the current mask (set by aaa_fit)
 };
 
 template <class W>
@@ -132,7 +143,7 @@ PSI_HD void aaa_index(const AAAScratch& s, AAAState& st) {
 // columns of A are orthogonal, V holds the accumulated rotations; returns the index of the column
 // with the smallest norm (the right singular vector of the smallest singular value is V[:, j]).
 template <class W>
-PSI_NOINLINE int jacobi_smallest(cx* A, cx* V, int r, int m) {
+PSI_NOINLINE int jacobi_smallest(cx* A, cx* V, double* nrm, int r, int m) {
     const int lane = W::lane();
     for (int j = 0; j < m; ++j)
         for (int i = lane; i < m; i += W::width) V[i + (size_t)j * m] = cx(i == j ? 1.0 : 0.0, 0.0);
@@ -148,22 +159,30 @@ PSI_NOINLINE int jacobi_smallest(cx* A, cx* V, int r, int m) {
     for (int sweep = 0; sweep < 40; ++sweep) {
         bool rotated = false;
         PSI_STAT(1, 1);
+        // squared column norms, refreshed every sweep and updated analytically after each rotation
+        for (int j = 0; j < m; ++j) {
+            double n2 = 0.0;
+            const cx* aj = A + (size_t)j * r;
+            for (int i = lane; i < r; i += W::width) n2 += aj[i].re * aj[i].re + aj[i].im * aj[i].im;
+            n2 = W::sum(n2);
+            if (lane == 0) nrm[j] = n2;
+        }
+        W::sync();
         for (int p = 0; p < m - 1; ++p) {
             for (int q = p + 1; q < m; ++q) {
                 cx* ap = A + (size_t)p * r;
                 cx* aq = A + (size_t)q * r;
-                double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+                const double al = nrm[p], be = nrm[q];
+                if (al <= negligible && be <= negligible) continue;
+                double gr = 0.0, gi = 0.0;
                 for (int i = lane; i < r; i += W::width) {
                     const cx x = ap[i], y = aq[i];
-                    al += x.re * x.re + x.im * x.im;
-                    be += y.re * y.re + y.im * y.im;
                     gr += x.re * y.re + x.im * y.im;          // conj(x)*y
                     gi += x.re * y.im - x.im * y.re;
                 }
-                al = W::sum(al); be = W::sum(be); gr = W::sum(gr); gi = W::sum(gi);
+                gr = W::sum(gr); gi = W::sum(gi);
                 const double g = sqrt(gr * gr + gi * gi);
                 if (g <= 1.0e-14 * sqrt(al * be) || g == 0.0) continue;
-                if (al <= negligible && be <= negligible) continue;
                 rotated = true;
                 PSI_STAT(2, 1);
                 // Hermitian 2x2 [[al, gamma],[conj(gamma), be]]: rotation that annihilates gamma
@@ -185,6 +204,7 @@ PSI_NOINLINE int jacobi_smallest(cx* A, cx* V, int r, int m) {
                     vp[i] = c * x - sp * y;
                     vq[i] = sq * x + c * y;
                 }
+                if (lane == 0) { nrm[p] = fmax(al - t * g, 0.0); nrm[q] = be + t * g; }
                 W::sync();
             }
         }
@@ -218,12 +238,13 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st) {
         for (int j = lane; j < m; j += W::width) s.w[j] = s.memo_w[(size_t)k * s.ncol + j];
         for (int i = lane; i < r; i += W::width) s.R[i] = s.memo_R[(size_t)k * s.cap + i];
         W::sync();
+        st.slot = k;
         return s.memo_res[k];
     }
     for (int j = 0; j < m; ++j) {
         const cx zj = s.Z[s.on[j]], fj = s.F[s.on[j]];
         for (int i = lane; i < r; i += W::width) {
-            const cx c = np_div(cx(1.0, 0.0), s.Z[s.off[i]] - zj);
+            const cx c = recip(s.Z[s.off[i]] - zj);
             s.A[i + (size_t)j * r] = (s.F[s.off[i]] - fj) * c;        // F_i C_ij - C_ij f_j
         }
     }
@@ -231,7 +252,7 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st) {
     if (r == 0) {
         for (int j = lane; j < m; j += W::width) s.w[j] = cx(j == m - 1 ? 1.0 : 0.0, 0.0);
     } else {
-        const int jmin = jacobi_smallest<W>(s.A, s.V, r, m);
+        const int jmin = jacobi_smallest<W>(s.A, s.V, s.nrm, r, m);
         for (int j = lane; j < m; j += W::width) s.w[j] = s.V[j + (size_t)jmin * m];
     }
     W::sync();
@@ -240,11 +261,11 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st) {
         const cx Zi = s.Z[s.off[i]];
         cx num(0.0, 0.0), den(0.0, 0.0);
         for (int j = 0; j < m; ++j) {
-            const cx t = np_div(s.w[j], Zi - s.Z[s.on[j]]);
+            const cx t = s.w[j] * recip(Zi - s.Z[s.on[j]]);
             num = num + t * s.F[s.on[j]];
             den = den + t;
         }
-        const double res = abs_c(s.F[s.off[i]] - np_div(num, den));
+        const double res = abs_c(s.F[s.off[i]] - num * recip(den));
         s.R[i] = res;
         rmax = fmax(rmax, res);
     }
@@ -256,8 +277,9 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st) {
         for (int i = lane; i < st.M; i += W::width) s.memo_mask[(size_t)k * s.cap + i] = s.mask[i];
         for (int j = lane; j < m; j += W::width) s.memo_w[(size_t)k * s.ncol + j] = s.w[j];
         for (int i = lane; i < r; i += W::width) s.memo_R[(size_t)k * s.cap + i] = s.R[i];
-        if (lane == 0) { s.memo_m[k] = m; s.memo_res[k] = resid; }
+        if (lane == 0) { s.memo_m[k] = m; s.memo_res[k] = resid; s.memo_np[k] = -1; s.memo_nz[k] = -1; }
         W::sync();
+        st.slot = k;
     }
     return resid;
 }
@@ -266,12 +288,11 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st) {
 PSI_HD cx aaa_eval(const AAAScratch& s, const AAAState& st, cx z) {
     cx num(0.0, 0.0), den(0.0, 0.0);
     for (int j = 0; j < st.m; ++j) {
-        cx t = s.w[j];
-        if (t.re != 0.0 || t.im != 0.0) t = np_div(t, z - s.Z[s.on[j]]);
+        const cx t = s.w[j] * recip(z - s.Z[s.on[j]]);
         num = num + t * s.F[s.on[j]];
         den = den + t;
     }
-    return np_div(num, den);
+    return num * recip(den);
 }
 
 // Roots of S(z) = sum_j a_j/(z - z_j) (a_j = w_j for the poles, w_j f_j for the zeros) by the
@@ -395,6 +416,12 @@ template <class W>
 PSI_NOINLINE int aaa_zeros(const AAAScratch& s, const AAAState& st) {
     const int lane = W::lane(), nr = st.m - 1;
     if (nr <= 0) return 0;
+    if (s.memo_nz[st.slot] >= 0) {                       // same support mask seen before: replay
+        const int n = s.memo_nz[st.slot];
+        for (int k = lane; k < n; k += W::width) s.roots[k] = s.memo_zero[(size_t)st.slot * s.ncol + k];
+        W::sync();
+        return n;
+    }
     aberth_roots<W>(s, st, true, s.roots);
     for (int k = lane; k < nr; k += W::width) {
         const cx z0 = s.roots[k];
@@ -445,6 +472,9 @@ PSI_NOINLINE int aaa_zeros(const AAAScratch& s, const AAAState& st) {
         const cx d = s.tmp[k] - s.tmp[k - 1];
         if (np_less(cx(1.0e-12, 0.0), d)) ++n;
     }
+    for (int k = lane; k < n; k += W::width) s.memo_zero[(size_t)st.slot * s.ncol + k] = s.roots[k];
+    if (lane == 0) s.memo_nz[st.slot] = n;
+    W::sync();
     return n;
 }
 
@@ -454,39 +484,43 @@ PSI_NOINLINE int aaa_zeros(const AAAScratch& s, const AAAState& st) {
 template <class W>
 PSI_NOINLINE int aaa_cleanup(const AAAScratch& s, AAAState& st) {
     const int lane = W::lane(), np_ = st.m - 1;
-    aberth_roots<W>(s, st, false, s.roots);
-    // decisions per pole (lane-parallel), collected in tmp[k].re = position to drop or -1
-    const double side = 1.0e-5;
-    const double c45 = 0.7071067811865476;
-    const cx ring[4] = {cx(side * c45, -side * c45), cx(side * c45, side * c45), cx(-side * c45, side * c45),
-                        cx(-side * c45, -side * c45)};
-    for (int k = lane; k < np_; k += W::width) {
-        const cx pole = s.roots[k];
-        double drop = -1.0;
-        if (finite_c(pole) && st.dom.is_in(pole)) {
-            cx zc[4], fc[4];
-            for (int q = 0; q < 4; ++q) { zc[q] = pole + ring[q]; fc[q] = aaa_eval(s, st, zc[q]); }
-            cx integral(0.0, 0.0);
-            for (int q = 0; q < 4; ++q) {
-                const cx dz = zc[(q + 1) & 3] - zc[q], fs = fc[(q + 1) & 3] + fc[q];
-                integral = integral + (0.5 * dz) * fs;
-            }
-            if (abs_c(integral) / st.fmax < st.clean_tol) {
+    const int slot = st.slot;
+    cx* dec = s.memo_pole + (size_t)slot * s.ncol;       // (residue ratio, sample index) per pole in the domain
+    if (s.memo_np[slot] < 0) {
+        aberth_roots<W>(s, st, false, s.roots);
+        const double side = 1.0e-5;
+        const double c45 = 0.7071067811865476;
+        const cx ring[4] = {cx(side * c45, -side * c45), cx(side * c45, side * c45), cx(-side * c45, side * c45),
+                            cx(-side * c45, -side * c45)};
+        for (int k = lane; k < np_; k += W::width) {
+            const cx pole = s.roots[k];
+            cx d(INFINITY, -1.0);
+            if (finite_c(pole) && st.dom.is_in(pole)) {
+                cx zc[4], fc[4];
+                for (int q = 0; q < 4; ++q) { zc[q] = pole + ring[q]; fc[q] = aaa_eval(s, st, zc[q]); }
+                cx integral(0.0, 0.0);
+                for (int q = 0; q < 4; ++q) {
+                    const cx dz = zc[(q + 1) & 3] - zc[q], fs = fc[(q + 1) & 3] + fc[q];
+                    integral = integral + (0.5 * dz) * fs;
+                }
                 int nearest = 0; double bd = INFINITY;
                 for (int j = 0; j < st.m; ++j) {
-                    const double d = abs_c(pole - s.Z[s.on[j]]);
-                    if (d < bd) { bd = d; nearest = j; }
+                    const double dd = abs_c(pole - s.Z[s.on[j]]);
+                    if (dd < bd) { bd = dd; nearest = j; }
                 }
-                drop = (double)s.on[nearest];
+                d = cx(abs_c(integral) / st.fmax, (double)s.on[nearest]);
             }
+            dec[k] = d;
         }
-        s.tmp[k] = cx(drop, 0.0);
+        if (lane == 0) s.memo_np[slot] = np_ > 0 ? np_ : 0;
+        W::sync();
     }
-    W::sync();
+    const int nd = s.memo_np[slot];
     int removed = 0;
-    for (int k = 0; k < np_; ++k) if (s.tmp[k].re >= 0.0) ++removed;
+    for (int k = 0; k < nd; ++k) if (dec[k].im >= 0.0 && dec[k].re < st.clean_tol) ++removed;
+    W::sync();
     if (lane == 0)
-        for (int k = 0; k < np_; ++k) if (s.tmp[k].re >= 0.0) s.mask[(int)s.tmp[k].re] = 0;
+        for (int k = 0; k < nd; ++k) if (dec[k].im >= 0.0 && dec[k].re < st.clean_tol) s.mask[(int)dec[k].im] = 0;
     W::sync();
     aaa_fit<W>(s, st);
     return removed;
@@ -522,16 +556,12 @@ PSI_NOINLINE bool aaa_calculate(const AAAScratch& s, AAAState& st, bool reuse_gr
             if (aaa_fit<W>(s, st) < st.tol) break;
         }
         for (int i = lane; i < M; i += W::width) s.g_mask[i] = s.mask[i];
-        for (int j = lane; j < st.m; j += W::width) s.g_w[j] = s.w[j];
-        for (int i = lane; i < st.r; i += W::width) s.g_R[i] = s.R[i];
         W::sync();
     } else {
+        // replay: restore the greedy mask; its fit comes out of the memo (or is recomputed if evicted)
         for (int i = lane; i < M; i += W::width) s.mask[i] = s.g_mask[i];
         W::sync();
-        aaa_index<W>(s, st);
-        for (int j = lane; j < st.m; j += W::width) s.w[j] = s.g_w[j];
-        for (int i = lane; i < st.r; i += W::width) s.R[i] = s.g_R[i];
-        W::sync();
+        aaa_fit<W>(s, st);
     }
     while (aaa_cleanup<W>(s, st) != 0) {}
     return true;
