@@ -47,15 +47,26 @@ def rank_wavenumbers(rank):
 # ---------------------------------------------------------------------------------------------
 # CPU arm: oracle port on the host cores
 # ---------------------------------------------------------------------------------------------
+def _one_blas_thread():
+    """One BLAS thread per worker process: the pool already uses every core, and LAPACK on tiny
+    matrices crawls when each of the processes spins up a full thread team."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=1)
+    except ImportError:
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def _cpu_worker(args):
-    os.environ["OMP_NUM_THREADS"] = "1"
     from oracle import psi_oracle as po
     w, kx, kz = args
     disp = _cpu_worker.cache.get("d")
     if disp is None:
         disp = po.Dispersion(po.DustDist.power_law(MU, list(STOKES)), po.NodeTable())
         _cpu_worker.cache["d"] = disp
-    return disp.calculate(w, kx, kz)
+    with _one_blas_thread():
+        return disp.calculate(w, kx, kz)
 
 
 _cpu_worker.cache = {}
@@ -131,12 +142,12 @@ def mode_grid(n_axis, rank=0, world=1):
 
 
 def _cpu_mode_worker(k):
-    os.environ["OMP_NUM_THREADS"] = "1"
     from oracle import psi_oracle as po
     item = {'__init__': dict(MODE_INIT), 'calculate': {'wave_number_x': k[0], 'wave_number_z': k[1]},
             'random_seed': 2}
     tab = _cpu_mode_worker.cache.setdefault("t", po.NodeTable())
-    return len(po.run_mode_item(item, tab))
+    with _one_blas_thread():
+        return len(po.run_mode_item(item, tab))
 
 
 _cpu_mode_worker.cache = {}
@@ -381,8 +392,14 @@ def run_b200(args):
         total_evals = float(n)*world*args.steps
         value = total_evals/(ms_total*1e-3)
         tf = FLOPS_PER_NODE*(node_evals/args.steps)/(ms_kernel*1e-3)/1e12     # rank 0's kernel
+        traffic = None
+        try:                       # DRAM bytes per K1 launch from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as fh:
+                traffic = json.load(fh)["traffic_bytes_per_launch"]
+        except Exception:
+            pass
         roof = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": tf/fp64_peak if fp64_peak else None, "traffic": None,
+                "frac": tf/fp64_peak if fp64_peak else None, "traffic": traffic,
                 "kernel": "disp_eval_kernel", "kernel_ms": ms_kernel,
                 "node_evals_per_launch": node_evals/args.steps, "flops_per_node_eval": FLOPS_PER_NODE,
                 "peak_source": "measured live by dfma_peak_kernel (MEASURED_PEAKS.json has no FP64 entry)",
