@@ -38,3 +38,24 @@ def test_no_cpu_fallback(built):
     from psitools_public_b200 import PSIDispersion
     with pytest.raises(_device.PsiError):
         PSIDispersion(3.0, [1e-8, 1e-2])
+
+
+def test_argument_checks_without_gpu(built):
+    """Entry points validate their arguments before touching the device (no compute, no GPU needed)."""
+    lib = _device.load_library()
+    null = ctypes.c_void_p()
+    assert lib.psi_ctx_create(None, 0, None, None, 0, 12, ctypes.c_double(1e-15)) == -2      # PSI_ERR_ARG
+    assert b"bad argument" in lib.psi_last_error()
+    assert lib.psi_dist_add(null, None) == -2
+    assert lib.psi_ctx_sm_count(null) == 0 and lib.psi_ctx_launch_count(null) == 0
+    lib.psi_ctx_destroy(null)                                                                # no-op on NULL
+    assert lib.psi_disp_eval_host(null, 0, 1, None, None, None, None, None, None, None, None) == -2
+    assert lib.psi_contour_batch_host(null, 0, *([None]*13)) == -2
+    assert lib.psi_polish_batch_host(null, 0, *([None]*12)) == -2
+    assert lib.psi_version().startswith(b"psi_b200")
+
+
+def test_openblas_discovery():
+    a, b = _device.openblas_paths()
+    assert os.path.exists(a) and "openblas64_" in a
+    assert os.path.exists(b) and "openblas" in b
