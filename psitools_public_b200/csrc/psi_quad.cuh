@@ -12,6 +12,11 @@
 
 namespace psi {
 
+#ifndef PSI_PAIR_UNROLL
+#define PSI_PAIR_UNROLL 1
+#endif
+constexpr int kPairUnroll = PSI_PAIR_UNROLL;    // node pairs per lane in flight in the level loop
+
 // Node table in LEVEL-MAJOR order: level 0 holds the nodes j = k*2^max_m (k = 0, 1, ...), level m
 // (1 <= m <= max_m) the odd multiples j = (2i+1)*2^(max_m-m); each entry is (x_j, w_j).  Within a
 // level a warp therefore reads consecutive 16-byte entries (no shared-memory bank conflicts).
@@ -112,6 +117,7 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
         const node_t* lv = t.nodes + t.level_off[m];
 #pragma unroll
         for (int k = 0; k < NC; ++k) acc[k] = cx(0.0, 0.0);
+#pragma unroll kPairUnroll
         for (int i = lane; i < cnt; i += W::width) {
             const node_t nd = lv[i];
             NodeVals np, nn;

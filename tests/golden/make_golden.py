@@ -386,7 +386,29 @@ def sec_refine():
     dump("refine.json", out)
 
 
-SECTIONS = dict(nodes=sec_nodes, background=sec_background, disp=sec_disp, contour=sec_contour,
+def sec_modegrid16():
+    """BASELINE config 3 parity sample: the 16x16 strided subset of the 256x256
+    logspace(-1,3) (Kx,Kz) map, MRN mu=3, tau in [1e-8,1], n_sample 20, max_zoom 1, seed 2."""
+    import multiprocessing as mp
+    ax = np.logspace(-1, 3, 256)[8::16]
+    kxg, kzg = np.meshgrid(ax, ax)
+    items = []
+    for kx, kz in zip(kxg.flatten(), kzg.flatten()):
+        items.append({'__init__': {'stokes_range': [1e-8, 1.0], 'dust_to_gas_ratio': 3.0,
+                                   'size_distribution_power': 3.5, 'real_range': [-2.0, 2.0],
+                                   'imag_range': [1e-8, 1.0], 'n_sample': 20, 'max_zoom_domains': 1,
+                                   'tol': 1.0e-13, 'clean_tol': 1e-4},
+                      'calculate': {'wave_number_x': float(kx), 'wave_number_z': float(kz)},
+                      'random_seed': 2})
+    t0 = time.time()
+    with mp.get_context("fork").Pool(PROCS) as pool:
+        res = pool.map(_grid_item, items, chunksize=1)
+    print("mode grid 16x16 strided in %.0f s" % (time.time() - t0), sum(len(r['roots']) > 0 for r in res),
+          "pixels with roots", flush=True)
+    dump("modegrid16.json", dict(axis=list(map(float, ax)), stokes_range=[1e-8, 1.0], seed=2, cases=res))
+
+
+SECTIONS = dict(modegrid16=sec_modegrid16, nodes=sec_nodes, background=sec_background, disp=sec_disp, contour=sec_contour,
                 mode=sec_mode, modegrid=sec_modegrid, refine=sec_refine)
 
 if __name__ == "__main__":

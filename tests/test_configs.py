@@ -73,3 +73,63 @@ def test_high_order_table_level13(backend):
     # levels 12 and 13 agree (the extra level only confirms convergence)
     pd12 = PSIDispersion(3.0, [1e-8, 1.0], tanhsinh_integrator=TanhSinh(15, 12))
     np.testing.assert_allclose(pd12.calculate(w[:3], 10.0, 100.0), got[:3], rtol=1e-11)
+
+
+def test_ragged_batch_and_empty(backend):
+    """One batch with different n_sample / max_zoom_domains / guess lists / seeds / distributions per
+    item: the device pipeline (engine='device'), the LAPACK engine ('native') and the Python generators
+    ('python') return the same de-duplicated root sets; an empty arg list gives an empty dict."""
+    from psitools_public_b200 import TanhSinhNoDeepCopy, psi_mode_mpi
+    ts = TanhSinhNoDeepCopy()
+    root = -1.004879704650626 + 0.0008946325671658642j
+
+    def item(tmax, kx, kz, n_sample, max_zoom, seed, guess=()):
+        return {'__init__': {'stokes_range': [1e-8, tmax], 'dust_to_gas_ratio': 3.0,
+                             'real_range': [-2.0, 2.0], 'imag_range': [1e-8, 1.0], 'n_sample': n_sample,
+                             'max_zoom_domains': max_zoom, 'tanhsinh_integrator': ts},
+                'calculate': {'wave_number_x': kx, 'wave_number_z': kz, 'guess_roots': list(guess)},
+                'random_seed': seed}
+
+    items = [item(1.0, 0.1, 10.0, 20, 1, 2), item(1.0, 0.1, 10.0, 15, 0, 5, [root*(1 + 1e-3)]),
+             item(1e-2, 10.0, 1000.0, 20, 1, 0), item(1.0, 1.0, 1.0, 12, 2, 7),
+             item(1.0, 0.1, 10.0, 20, 0, 3, [root, root + 1e-4, 0.3 + 0.1j])]
+    res = {}
+    for eng in ("device", "native", "python"):
+        ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False, engine=eng)
+        assert ms.run([]) == {}
+        res[eng] = ms.run(items)
+        assert ms.last_stats["engine"] == eng
+    for i in range(len(items)):
+        a, b, c = (distinct(res[e][i]) for e in ("device", "native", "python"))
+        assert same_root_sets(a, c) and same_root_sets(b, c), (i, res["device"][i], res["native"][i], res["python"][i])
+    assert any(abs(r - root) < 1e-9 for r in res["device"][0])
+    assert any(abs(r - root) < 1e-9 for r in res["device"][4])
+    assert abs(res["device"][2][0] - (-1.0062579942546936 + 1.3209787635623396e-05j)) < 1e-7
+
+
+@pytest.mark.parametrize("engine", ["device", "native"])
+def test_config3_strided_sample_vs_reference(backend, engine):
+    """BASELINE config 3 parity sample: the 16x16 strided subset of the 256x256 (Kx,Kz) map against the
+    UNMODIFIED reference (fixture modegrid16.json): de-duplicated root sets per pixel must be equal --
+    the root count exactly, the values to 1e-8 |omega|.  (The CPU backend checks every fourth pixel to
+    keep the suite short; the GPU run checks all 256.)"""
+    from common import carr, load
+    from psitools_public_b200 import TanhSinhNoDeepCopy, psi_mode_mpi
+    g = load("modegrid16.json")
+    cases = g["cases"] if backend == "gpu" else g["cases"][::4]
+    ts = TanhSinhNoDeepCopy()
+    items = [{'__init__': {'stokes_range': [1e-8, 1.0], 'dust_to_gas_ratio': 3.0,
+                           'size_distribution_power': 3.5, 'real_range': [-2.0, 2.0],
+                           'imag_range': [1e-8, 1.0], 'n_sample': 20, 'max_zoom_domains': 1,
+                           'tol': 1.0e-13, 'clean_tol': 1e-4, 'tanhsinh_integrator': ts},
+              'calculate': {'wave_number_x': c["kx"], 'wave_number_z': c["kz"]}, 'random_seed': 2}
+             for c in cases]
+    res = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False, engine=engine).run(items)
+    bad = [i for i, c in enumerate(cases)
+           if not same_root_sets(distinct(res[i]), distinct(carr(c["roots"])))]
+    n_ref_roots = sum(len(distinct(carr(c["roots"]))) for c in cases)
+    n_roots = sum(len(distinct(res[i])) for i in range(len(cases)))
+    print("pixels %d, with roots (reference) %d, distinct roots %d (reference %d), mismatching pixels %s"
+          % (len(cases), sum(len(c["roots"]) > 0 for c in cases), n_roots, n_ref_roots, bad))
+    assert n_roots == n_ref_roots
+    assert not bad, [(cases[i]["kx"], cases[i]["kz"], res[i], cases[i]["roots"]) for i in bad]
