@@ -26,6 +26,7 @@ static long long g_aaa_stats[8];
 #endif
 
 constexpr int kMemoSlots = 12;
+constexpr int kMaxSamples = 512;     // largest sample count (cap) the device AAA accepts
 
 // scratch layout of one warp (all sizes in elements, cap = maximum number of samples)
 struct AAAScratch {
@@ -142,8 +143,11 @@ PSI_HD void aaa_index(const AAAScratch& s, AAAState& st) {
 // One-sided Jacobi SVD of the r x m matrix A (column-major, leading dimension r): on return the
 // columns of A are orthogonal, V holds the accumulated rotations; returns the index of the column
 // with the smallest norm (the right singular vector of the smallest singular value is V[:, j]).
-template <class W>
-PSI_NOINLINE int jacobi_smallest(cx* A, cx* V, double* nrm, int r, int m) {
+// CH = row chunks of one warp width per lane: the per-rotation work is straight-line predicated code
+// (no inner loops: the rows of a column pair live in registers between the dot product and the
+// rotation), which matters because this routine is instruction-fetch bound on the GPU.
+template <class W, int CH>
+PSI_NOINLINE int jacobi_smallest_t(cx* A, cx* V, double* nrm, int r, int m) {
     const int lane = W::lane();
     for (int j = 0; j < m; ++j)
         for (int i = lane; i < m; i += W::width) V[i + (size_t)j * m] = cx(i == j ? 1.0 : 0.0, 0.0);
@@ -174,11 +178,14 @@ PSI_NOINLINE int jacobi_smallest(cx* A, cx* V, double* nrm, int r, int m) {
                 cx* aq = A + (size_t)q * r;
                 const double al = nrm[p], be = nrm[q];
                 if (al <= negligible && be <= negligible) continue;
+                cx x[CH], y[CH];
                 double gr = 0.0, gi = 0.0;
-                for (int i = lane; i < r; i += W::width) {
-                    const cx x = ap[i], y = aq[i];
-                    gr += x.re * y.re + x.im * y.im;          // conj(x)*y
-                    gi += x.re * y.im - x.im * y.re;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int i = lane + c * W::width;
+                    if (i < r) { x[c] = ap[i]; y[c] = aq[i]; } else { x[c] = cx(0.0, 0.0); y[c] = cx(0.0, 0.0); }
+                    gr += x[c].re * y[c].re + x[c].im * y[c].im;          // conj(x)*y
+                    gi += x[c].re * y[c].im - x[c].im * y[c].re;
                 }
                 gr = W::sum(gr); gi = W::sum(gi);
                 const double g = sqrt(gr * gr + gi * gi);
@@ -189,20 +196,25 @@ PSI_NOINLINE int jacobi_smallest(cx* A, cx* V, double* nrm, int r, int m) {
                 const double zeta = (be - al) / (2.0 * g);
                 const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                 const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
-                const cx ph(gr / g, gi / g);                   // gamma/|gamma|
+                const double ig = 1.0 / g;
+                const cx ph(gr * ig, gi * ig);                 // gamma/|gamma|
                 // a_p' = c*a_p - sn*conj(ph)*a_q ;  a_q' = sn*ph*a_p + c*a_q
                 const cx sp(sn * ph.re, -sn * ph.im), sq(sn * ph.re, sn * ph.im);
-                for (int i = lane; i < r; i += W::width) {
-                    const cx x = ap[i], y = aq[i];
-                    ap[i] = c * x - sp * y;
-                    aq[i] = sq * x + c * y;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const int i = lane + k * W::width;
+                    if (i < r) { ap[i] = c * x[k] - sp * y[k]; aq[i] = sq * x[k] + c * y[k]; }
                 }
                 cx* vp = V + (size_t)p * m;
                 cx* vq = V + (size_t)q * m;
-                for (int i = lane; i < m; i += W::width) {
-                    const cx x = vp[i], y = vq[i];
-                    vp[i] = c * x - sp * y;
-                    vq[i] = sq * x + c * y;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const int i = lane + k * W::width;
+                    if (i < m) {
+                        const cx vx = vp[i], vy = vq[i];
+                        vp[i] = c * vx - sp * vy;
+                        vq[i] = sq * vx + c * vy;
+                    }
                 }
                 if (lane == 0) { nrm[p] = fmax(al - t * g, 0.0); nrm[q] = be + t * g; }
                 W::sync();
@@ -220,6 +232,20 @@ PSI_NOINLINE int jacobi_smallest(cx* A, cx* V, double* nrm, int r, int m) {
         if (bn < 0.0 || n2 < bn) { bn = n2; best = j; }
     }
     return best;
+}
+
+template <class W>
+PSI_HD int jacobi_smallest(cx* A, cx* V, double* nrm, int r, int m) {
+    const int rows = r > m ? r : m;
+    if constexpr (W::width == 1) {
+        return jacobi_smallest_t<W, kMaxSamples>(A, V, nrm, r, m);           // CPU harness: one "lane"
+    } else {
+        if (rows <= W::width) return jacobi_smallest_t<W, 1>(A, V, nrm, r, m);
+        if (rows <= 2 * W::width) return jacobi_smallest_t<W, 2>(A, V, nrm, r, m);
+        if (rows <= 4 * W::width) return jacobi_smallest_t<W, 4>(A, V, nrm, r, m);
+        if (rows <= 8 * W::width) return jacobi_smallest_t<W, 8>(A, V, nrm, r, m);
+        return jacobi_smallest_t<W, kMaxSamples / 32>(A, V, nrm, r, m);
+    }
 }
 
 // Loewner fit for the current mask: weights and residuals (complex_roots.py:56-90).  Returns the

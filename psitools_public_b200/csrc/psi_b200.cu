@@ -355,7 +355,7 @@ __global__ void mode_sample_kernel(ModeDev m, int n_items, const double* __restr
 }
 
 // warp per item: AAA analysis of the current samples (mode_analyze) -> polish start values + zoom plan
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, const int* __restrict__ iparams,
                     const double* __restrict__ dparams, const int* __restrict__ guess_off,
                     unsigned char* scratch, size_t scratch_per_warp, unsigned long long* queue) {

@@ -801,6 +801,8 @@ int psi_mode_batch_device(psi_ctx* ctx, int n_items, const int* dist, const doub
         for (long long k = 0; k < kv.second; ++k) uni.push_back(rng.sample());
     }
     if (uni.size() > 0x7fffffffull) return psi_internal_fail(PSI_ERR_CAPACITY, "random streams too long");
+    if (cap > 512)
+        return psi_internal_fail(PSI_ERR_CAPACITY, "more than 512 samples per search: use psi_mode_batch_host");
     std::vector<int> uoff(n_items);
     for (int i = 0; i < n_items; ++i) uoff[i] = (int)start[seeds[i]];
     const double dummy[2] = {0.0, 0.0};

@@ -104,6 +104,11 @@ class MpiScheduler:
         for pm in pms:
             pm._sync_cfg()
         dom = [[pm.domain.xmin, pm.domain.xmax, pm.domain.ymin, pm.domain.ymax] for pm in pms]
+        device = self.engine == "device"
+        if device:      # the device AAA holds at most 512 samples per search
+            most = max(pm.cfg.n_sample*(1 + len(c.get('guess_roots', ())) + 4*pm.cfg.max_zoom_level)
+                       for pm, c in zip(pms, calc))
+            device = most <= 512
         roots, ncalls, st = ctx.mode_batch(
             [pm.psi_dispersion.dist_id for pm in pms],
             [float(c['wave_number_x']) for c in calc], [float(c['wave_number_z']) for c in calc],
@@ -112,7 +117,7 @@ class MpiScheduler:
             [pm.cfg.max_secant_iterations for pm in pms], [pm.cfg.tol for pm in pms],
             [pm.cfg.clean_tol for pm in pms],
             [int(arglist[i].get('random_seed', 0)) for i in mine],
-            [list(c.get('guess_roots', ())) for c in calc], device_aaa=self.engine == "device")
+            [list(c.get('guess_roots', ())) for c in calc], device_aaa=device)
         st["function_calls"] = int(np.sum(ncalls))
         return {i: r for i, r in zip(mine, roots)}, st
 
