@@ -188,3 +188,15 @@ def test_contour_kernel_k2_status(backend):
     gold = load("contour.json")["cases"][3]
     assert abs(npts[1] - gold["n_points"]) <= 0.05*gold["n_points"]
     assert st["evals"] >= npts[1]
+
+
+def test_mode_count_roots_true(backend):
+    """PSIMode.calculate(count_roots=True) (psi_mode.py:127-138): the contour count is stored in
+    n_roots and the contour points join the AAA samples."""
+    from psitools_public_b200 import PSIMode, TanhSinh
+    np.random.seed(0)
+    pm = PSIMode(3.0, [1e-8, 1.0], [-2, 2], [2e-7, 2], tanhsinh_integrator=TanhSinh())
+    roots = pm.calculate(0.1, 10.0, count_roots=True)
+    assert pm.n_roots == 1                                   # same contour as test_complex_roots_mpi pixel 3
+    assert len(pm.z_sample) > 200                            # 20 random samples + the contour points
+    assert min(abs(r - (-1.004879704650626 + 0.0008946325671658642j)) for r in roots) < 1e-8
