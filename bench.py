@@ -97,7 +97,7 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_step = 96*cores
+    per_step = 256*cores
     pool = mp.get_context("fork").Pool(cores)
     pool.map(_cpu_worker, [(omega_grid()[:1], K_BASE[0], K_BASE[1])]*cores)
     for i in range(args.warmup):
