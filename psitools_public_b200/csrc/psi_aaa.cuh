@@ -34,7 +34,9 @@ struct AAAScratch {
     cx* F;        // [cap]   function samples
     int* mask;    // [cap]   1 = support point
     cx* A;        // [cap * ncol]  Loewner matrix, column-major (destroyed by the SVD)
+    cx* A2;       // [cap * ncol]  Loewner matrix pre-rotated by the previous fit's V (warm start)
     cx* V;        // [ncol * ncol] right singular vectors
+    cx* V2;       // [ncol * ncol] copy of the previous V while the warm start is assembled
     cx* w;        // [ncol]  weights
     double* R;    // [cap]   residuals at the non-support points (in sample order of those points)
     int* on;      // [ncol]  sample index of the k-th support point
@@ -65,7 +67,7 @@ struct AAAScratch {
 
 PSI_HD size_t aaa_scratch_bytes(int cap) {
     const size_t ncol = (size_t)cap / 2 + 2;
-    return sizeof(cx) * (2 * (size_t)cap + (size_t)cap * ncol + ncol * ncol + (6 + 3 * kMemoSlots) * ncol) +
+    return sizeof(cx) * (2 * (size_t)cap + 2 * (size_t)cap * ncol + 2 * ncol * ncol + (6 + 3 * kMemoSlots) * ncol) +
            sizeof(double) * ((2 + kMemoSlots) * (size_t)cap + kMemoSlots + ncol) +
            sizeof(int) * ((3 + kMemoSlots) * (size_t)cap + ncol + 3 * kMemoSlots) + 256;
 }
@@ -78,7 +80,9 @@ PSI_HD AAAScratch aaa_carve(void* base, int cap) {
     s.Z = c; c += cap;
     s.F = c; c += cap;
     s.A = c; c += (size_t)cap * ncol;
+    s.A2 = c; c += (size_t)cap * ncol;
     s.V = c; c += ncol * ncol;
+    s.V2 = c; c += ncol * ncol;
     s.w = c; c += ncol;
     s.roots = c; c += ncol;
     s.tmp = c; c += ncol;
@@ -115,6 +119,8 @@ struct AAAState {
     RectDom dom;
     int memo_next;  // next memo slot to overwrite
     int slot;       // memo slot that holds the current mask (set by aaa_fit)
+    int v_m;        // s.V holds the right singular vectors of the last computed fit with v_m support
+                    // points (0 = nothing usable); lets the next greedy step start its SVD warm
 };
 
 template <class W>
@@ -147,10 +153,11 @@ PSI_HD void aaa_index(const AAAScratch& s, AAAState& st) {
 // (no inner loops: the rows of a column pair live in registers between the dot product and the
 // rotation), which matters because this routine is instruction-fetch bound on the GPU.
 template <class W, int CH>
-PSI_NOINLINE int jacobi_smallest_t(cx* A, cx* V, double* nrm, int r, int m) {
+PSI_NOINLINE int jacobi_smallest_t(cx* A, cx* V, double* nrm, int r, int m, bool warm) {
     const int lane = W::lane();
-    for (int j = 0; j < m; ++j)
-        for (int i = lane; i < m; i += W::width) V[i + (size_t)j * m] = cx(i == j ? 1.0 : 0.0, 0.0);
+    if (!warm)
+        for (int j = 0; j < m; ++j)
+            for (int i = lane; i < m; i += W::width) V[i + (size_t)j * m] = cx(i == j ? 1.0 : 0.0, 0.0);
     W::sync();
     PSI_STAT(0, 1);
     double fro2 = 0.0;
@@ -235,23 +242,23 @@ PSI_NOINLINE int jacobi_smallest_t(cx* A, cx* V, double* nrm, int r, int m) {
 }
 
 template <class W>
-PSI_HD int jacobi_smallest(cx* A, cx* V, double* nrm, int r, int m) {
+PSI_HD int jacobi_smallest(cx* A, cx* V, double* nrm, int r, int m, bool warm) {
     const int rows = r > m ? r : m;
     if constexpr (W::width == 1) {
-        return jacobi_smallest_t<W, kMaxSamples>(A, V, nrm, r, m);           // CPU harness: one "lane"
+        return jacobi_smallest_t<W, kMaxSamples>(A, V, nrm, r, m, warm);           // CPU harness: one "lane"
     } else {
-        if (rows <= W::width) return jacobi_smallest_t<W, 1>(A, V, nrm, r, m);
-        if (rows <= 2 * W::width) return jacobi_smallest_t<W, 2>(A, V, nrm, r, m);
-        if (rows <= 4 * W::width) return jacobi_smallest_t<W, 4>(A, V, nrm, r, m);
-        if (rows <= 8 * W::width) return jacobi_smallest_t<W, 8>(A, V, nrm, r, m);
-        return jacobi_smallest_t<W, kMaxSamples / 32>(A, V, nrm, r, m);
+        if (rows <= W::width) return jacobi_smallest_t<W, 1>(A, V, nrm, r, m, warm);
+        if (rows <= 2 * W::width) return jacobi_smallest_t<W, 2>(A, V, nrm, r, m, warm);
+        if (rows <= 4 * W::width) return jacobi_smallest_t<W, 4>(A, V, nrm, r, m, warm);
+        if (rows <= 8 * W::width) return jacobi_smallest_t<W, 8>(A, V, nrm, r, m, warm);
+        return jacobi_smallest_t<W, kMaxSamples / 32>(A, V, nrm, r, m, warm);
     }
 }
 
 // Loewner fit for the current mask: weights and residuals (complex_roots.py:56-90).  Returns the
 // largest residual divided by max|F|.
 template <class W>
-PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st) {
+PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample = -1) {
     aaa_index<W>(s, st);
     const int lane = W::lane(), r = st.r, m = st.m;
     // memo lookup
@@ -265,6 +272,7 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st) {
         for (int i = lane; i < r; i += W::width) s.R[i] = s.memo_R[(size_t)k * s.cap + i];
         W::sync();
         st.slot = k;
+        st.v_m = 0;                                  // V belongs to some other mask now
         return s.memo_res[k];
     }
     for (int j = 0; j < m; ++j) {
@@ -278,7 +286,42 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st) {
     if (r == 0) {
         for (int j = lane; j < m; j += W::width) s.w[j] = cx(j == m - 1 ? 1.0 : 0.0, 0.0);
     } else {
-        const int jmin = jacobi_smallest<W>(s.A, s.V, s.nrm, r, m);
+        // Warm start of the greedy chain: this mask = previous mask + one support point.  The Loewner
+        // entries depend on (sample, support point) only, so the old columns are the previous matrix
+        // minus one row; rotated by the previous V they are orthogonal up to a rank-one change, and
+        // Jacobi needs ~2-3 sweeps instead of ~9.
+        cx* mat = s.A;
+        bool warm = false;
+        if (added_sample >= 0 && st.v_m == m - 1 && m >= 3) {
+            int pnew = 0;
+            while (pnew < m && s.on[pnew] != added_sample) ++pnew;
+            if (pnew < m) {
+                warm = true;
+                const int mo = m - 1;
+                for (int e = lane; e < mo * mo; e += W::width) s.V2[e] = s.V[e];
+                W::sync();
+                for (int i = lane; i < r; i += W::width) {
+                    for (int j = 0; j < mo; ++j) {
+                        cx acc(0.0, 0.0);
+                        for (int k = 0; k < mo; ++k)
+                            acc = acc + s.A[i + (size_t)(k + (k >= pnew)) * r] * s.V2[k + (size_t)j * mo];
+                        s.A2[i + (size_t)(j + (j >= pnew)) * r] = acc;
+                    }
+                    s.A2[i + (size_t)pnew * r] = s.A[i + (size_t)pnew * r];
+                }
+                for (int e = lane; e < m * m; e += W::width) {
+                    const int i = e % m, j = e / m;
+                    cx v(0.0, 0.0);
+                    if (i == pnew || j == pnew) v = cx(i == j ? 1.0 : 0.0, 0.0);
+                    else v = s.V2[(i - (i > pnew)) + (size_t)(j - (j > pnew)) * mo];
+                    s.V[e] = v;
+                }
+                W::sync();
+                mat = s.A2;
+            }
+        }
+        const int jmin = jacobi_smallest<W>(mat, s.V, s.nrm, r, m, warm);
+        st.v_m = m;
         for (int j = lane; j < m; j += W::width) s.w[j] = s.V[j + (size_t)jmin * m];
     }
     W::sync();
@@ -570,6 +613,7 @@ PSI_NOINLINE bool aaa_calculate(const AAAScratch& s, AAAState& st, bool reuse_gr
         if (W::any(!fin)) return false;
         for (int i = lane; i < M; i += W::width) s.mask[i] = (i < 2) ? 1 : 0;
         W::sync();
+        st.v_m = 0;
         aaa_fit<W>(s, st);
         for (int k = 1; k < M / 2; ++k) {
             // promote the worst-fitted sample (first maximum, like numpy.argmax)
@@ -577,9 +621,11 @@ PSI_NOINLINE bool aaa_calculate(const AAAScratch& s, AAAState& st, bool reuse_gr
             for (int i = lane; i < st.r; i += W::width)
                 if (s.R[i] > bv) { bv = s.R[i]; best = i; }
             W::argmax(bv, best);
-            if (lane == 0) s.mask[s.off[best]] = 1;
+            const int added = s.off[best];
             W::sync();
-            if (aaa_fit<W>(s, st) < st.tol) break;
+            if (lane == 0) s.mask[added] = 1;
+            W::sync();
+            if (aaa_fit<W>(s, st, added) < st.tol) break;
         }
         for (int i = lane; i < M; i += W::width) s.g_mask[i] = s.mask[i];
         W::sync();

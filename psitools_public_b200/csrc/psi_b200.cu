@@ -374,7 +374,7 @@ mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, c
         sc.w0 = m.w0 + (size_t)idx * m.P;
         AAAState st;
         st.M = m.M[idx]; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol;
-        st.dom = cfg.dom; st.memo_next = 0;
+        st.dom = cfg.dom; st.memo_next = 0; st.slot = 0; st.v_m = 0;
         ModePlan plan;
         const bool ok = mode_analyze<WarpCuda>(cfg, m.level[idx], guess_off[idx + 1] - guess_off[idx], sc, st, plan);
         __syncwarp();

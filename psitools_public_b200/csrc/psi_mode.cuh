@@ -141,7 +141,7 @@ PSI_HD int mode_run(EVAL& f, const ModeCfg& cfg, const cx* guesses, int n_guess,
                     const AAAScratch& s, cx* out_roots, int max_roots, int* n_roots, int* n_calls) {
     AAAState st;
     st.M = 0; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol; st.dom = cfg.dom;
-    st.memo_next = 0;
+    st.memo_next = 0; st.slot = 0; st.v_m = 0;
     int upos = 0, calls = 0;
     *n_roots = 0; *n_calls = 0;
     const int n_domains_max = 1 + n_guess + 4 * cfg.max_zoom;
