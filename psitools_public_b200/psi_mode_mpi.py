@@ -109,6 +109,10 @@ class MpiScheduler:
             most = max(pm.cfg.n_sample*(1 + len(c.get('guess_roots', ())) + 4*pm.cfg.max_zoom_level)
                        for pm, c in zip(pms, calc))
             device = most <= 512
+            if not device:
+                import warnings
+                warnings.warn("a search of this batch can reach %d samples (> 512, the capacity of the "
+                              "device AAA): running the batch with engine='native'" % most)
         roots, ncalls, st = ctx.mode_batch(
             [pm.psi_dispersion.dist_id for pm in pms],
             [float(c['wave_number_x']) for c in calc], [float(c['wave_number_z']) for c in calc],

@@ -133,3 +133,46 @@ def test_config3_strided_sample_vs_reference(backend, engine):
           % (len(cases), sum(len(c["roots"]) > 0 for c in cases), n_roots, n_ref_roots, bad))
     assert n_roots == n_ref_roots
     assert not bad, [(cases[i]["kx"], cases[i]["kz"], res[i], cases[i]["roots"]) for i in bad]
+
+
+@pytest.mark.gpu
+def test_config3_full_size_properties(built):
+    """Size-independent properties at a large size (128x128 map, 16,384 searches, device engine):
+    (1) every reported root is a root of the exact dispersion relation: |D(w)| << |D(w + 1e-6) - D(w)|
+        (a first-order bound |dw| < 1e-9 on the distance to the true root), checked in ONE K1 batch;
+    (2) the argument principle agrees: on a 24x24 sub-map the number of distinct roots found inside the
+        search rectangle equals the winding number of D around that rectangle (kernel K2) wherever a
+        root was found, and pixels where the contour count is zero have no root;
+    (3) a second run returns bit-identical roots (deterministic kernels)."""
+    from psitools_public_b200 import PSIMode, TanhSinhNoDeepCopy
+    ts = TanhSinhNoDeepCopy()
+    pm = PSIMode(3.0, [1e-8, 1.0], [-2, 2], [1e-8, 1.0], tanhsinh_integrator=ts)
+    ctx, did = pm.psi_dispersion.ctx, pm.psi_dispersion.dist_id
+    n = 128
+    ax = np.logspace(-1, 3, n)
+    kxg, kzg = np.meshgrid(ax, ax)
+    kx, kz, N = kxg.ravel(), kzg.ravel(), n*n
+    dom = [[-2, 2, 1e-8, 1.0]]*N
+    run = lambda: ctx.mode_batch([did]*N, kx, kz, np.zeros(N), dom, 20, 1, 100, 1e-13, 1e-4, [2]*N, [[]]*N,
+                                 device_aaa=True)
+    roots, ncalls, st = run()
+    roots2, _, _ = run()
+    assert all(np.array_equal(a, b) for a, b in zip(roots, roots2))                      # (3)
+    idx = np.array([i for i, r in enumerate(roots) for _ in r], dtype=int)
+    w = np.array([z for r in roots for z in r])
+    assert len(w) > 2000 and np.all(w.imag > 0)
+    d0 = ctx.disp_eval(np.full(len(w), did, np.int32), kx[idx], kz[idx], np.zeros(len(w)), w)
+    d1 = ctx.disp_eval(np.full(len(w), did, np.int32), kx[idx], kz[idx], np.zeros(len(w)), w + 1e-6)
+    assert np.all(np.abs(d0) < 1e-3*np.abs(d1 - d0)), np.max(np.abs(d0)/np.abs(d1 - d0))    # (1)
+    # (2) on a 24x24 strided sub-map
+    sub = [i*n + j for i in range(2, n, 5) for j in range(2, n, 5)][:576]
+    z_list = [-2 + 1e-8j, 2 + 1e-8j, 2 + 1j, -2 + 1j]
+    counts, status, _, _ = ctx.contour_batch([did]*len(sub), kx[sub], kz[sub], np.zeros(len(sub)),
+                                             [z_list]*len(sub), 0.1, 0.1, 100)
+    assert np.all(status == 0)
+    for c, i in zip(counts, sub):
+        found = len(distinct(roots[i]))
+        if found:
+            assert found == c, (kx[i], kz[i], roots[i], c)
+        if c == 0:
+            assert found == 0
