@@ -67,13 +67,43 @@ def refine(nbase, fills, reruns):
                       "pixels_with_roots": with_roots}), flush=True)
 
 
+def sweep(n_mu, n_tau, n_axis, level):
+    """BASELINE config 5 family: n_mu x n_tau (mu, tau_max) MRN distributions x an n_axis^2 (Kx,Kz) map of
+    PSIMode solves in ONE batch, tanh-sinh table (15, level)."""
+    from psitools_public_b200 import TanhSinhNoDeepCopy, psi_mode_mpi
+    ts = TanhSinhNoDeepCopy(15, level)
+    ax = np.logspace(-1, 3, n_axis)
+    kxg, kzg = np.meshgrid(ax, ax)
+    items = []
+    for mu in np.logspace(-1, 1, n_mu):
+        for tmax in np.logspace(-3, 0, n_tau):
+            init = {'stokes_range': [1e-8, float(tmax)], 'dust_to_gas_ratio': float(mu),
+                    'real_range': [-2.0, 2.0], 'imag_range': [1e-8, 1.0], 'n_sample': 20,
+                    'max_zoom_domains': 1, 'tanhsinh_integrator': ts}
+            items += [{'__init__': init, 'calculate': {'wave_number_x': float(a), 'wave_number_z': float(b)},
+                       'random_seed': 2} for a, b in zip(kxg.ravel(), kzg.ravel())]
+    ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False)
+    ms.run_all(items[:64])
+    t0 = time.perf_counter()
+    res = ms.run_all(items)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"workload": "parameter sweep: %d x %d (mu, tau_max) distributions x %dx%d (Kx,Kz), "
+                                  "TanhSinh(15,%d), one batch" % (n_mu, n_tau, n_axis, n_axis, level),
+                      "searches": len(items), "seconds": dt, "modes_per_s": len(items)/dt,
+                      "D_evals": ms.last_stats.get("evals"), "engine": ms.last_stats.get("engine"),
+                      "searches_with_roots": int(sum(len(v) > 0 for v in res.values()))}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--count-grid", type=int, default=32)
     ap.add_argument("--nbase", type=int, default=16)
     ap.add_argument("--fills", type=int, default=2)
     ap.add_argument("--reruns", type=int, default=3)
+    ap.add_argument("--sweep", type=int, nargs=4, metavar=("N_MU", "N_TAU", "N_AXIS", "LEVEL"), default=None)
     a = ap.parse_args()
+    if a.sweep:
+        sweep(*a.sweep)
     if a.count_grid > 0:
         count_map(a.count_grid)
     if a.nbase > 0:
