@@ -185,14 +185,23 @@ PSI_NOINLINE int jacobi_smallest_t(cx* A, cx* V, double* nrm, int r, int m, bool
                 cx* aq = A + (size_t)q * r;
                 const double al = nrm[p], be = nrm[q];
                 if (al <= negligible && be <= negligible) continue;
-                cx x[CH], y[CH];
+                constexpr int NX = CH > 0 ? CH : 1;
+                cx x[NX], y[NX];
                 double gr = 0.0, gi = 0.0;
+                if (CH > 0) {
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int i = lane + c * W::width;
-                    if (i < r) { x[c] = ap[i]; y[c] = aq[i]; } else { x[c] = cx(0.0, 0.0); y[c] = cx(0.0, 0.0); }
-                    gr += x[c].re * y[c].re + x[c].im * y[c].im;          // conj(x)*y
-                    gi += x[c].re * y[c].im - x[c].im * y[c].re;
+                    for (int c = 0; c < NX; ++c) {
+                        const int i = lane + c * W::width;
+                        if (i < r) { x[c] = ap[i]; y[c] = aq[i]; } else { x[c] = cx(0.0, 0.0); y[c] = cx(0.0, 0.0); }
+                        gr += x[c].re * y[c].re + x[c].im * y[c].im;          // conj(x)*y
+                        gi += x[c].re * y[c].im - x[c].im * y[c].re;
+                    }
+                } else {                                  // CH == 0: any number of rows, looped
+                    for (int i = lane; i < r; i += W::width) {
+                        const cx xx = ap[i], yy = aq[i];
+                        gr += xx.re * yy.re + xx.im * yy.im;
+                        gi += xx.re * yy.im - xx.im * yy.re;
+                    }
                 }
                 gr = W::sum(gr); gi = W::sum(gi);
                 const double g = sqrt(gr * gr + gi * gi);
@@ -207,20 +216,31 @@ PSI_NOINLINE int jacobi_smallest_t(cx* A, cx* V, double* nrm, int r, int m, bool
                 const cx ph(gr * ig, gi * ig);                 // gamma/|gamma|
                 // a_p' = c*a_p - sn*conj(ph)*a_q ;  a_q' = sn*ph*a_p + c*a_q
                 const cx sp(sn * ph.re, -sn * ph.im), sq(sn * ph.re, sn * ph.im);
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int i = lane + k * W::width;
-                    if (i < r) { ap[i] = c * x[k] - sp * y[k]; aq[i] = sq * x[k] + c * y[k]; }
-                }
                 cx* vp = V + (size_t)p * m;
                 cx* vq = V + (size_t)q * m;
+                if (CH > 0) {
 #pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int i = lane + k * W::width;
-                    if (i < m) {
+                    for (int k = 0; k < NX; ++k) {
+                        const int i = lane + k * W::width;
+                        if (i < r) { ap[i] = c * x[k] - sp * y[k]; aq[i] = sq * x[k] + c * y[k]; }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) {
+                        const int i = lane + k * W::width;
+                        if (i < m) {
+                            const cx vx = vp[i], vy = vq[i];
+                            vp[i] = c * vx - sp * vy;
+                            vq[i] = sq * vx + c * vy;
+                        }
+                    }
+                } else {
+                    for (int i = lane; i < r; i += W::width) {
+                        const cx xx = ap[i], yy = aq[i];
+                        ap[i] = c * xx - sp * yy; aq[i] = sq * xx + c * yy;
+                    }
+                    for (int i = lane; i < m; i += W::width) {
                         const cx vx = vp[i], vy = vq[i];
-                        vp[i] = c * vx - sp * vy;
-                        vq[i] = sq * vx + c * vy;
+                        vp[i] = c * vx - sp * vy; vq[i] = sq * vx + c * vy;
                     }
                 }
                 if (lane == 0) { nrm[p] = fmax(al - t * g, 0.0); nrm[q] = be + t * g; }
@@ -245,13 +265,11 @@ template <class W>
 PSI_HD int jacobi_smallest(cx* A, cx* V, double* nrm, int r, int m, bool warm) {
     const int rows = r > m ? r : m;
     if constexpr (W::width == 1) {
-        return jacobi_smallest_t<W, kMaxSamples>(A, V, nrm, r, m, warm);           // CPU harness: one "lane"
+        return jacobi_smallest_t<W, 0>(A, V, nrm, r, m, warm);                     // CPU harness: one "lane"
     } else {
-        if (rows <= W::width) return jacobi_smallest_t<W, 1>(A, V, nrm, r, m, warm);
+        // two specialisations only: the routine is instruction-fetch bound, code size matters
         if (rows <= 2 * W::width) return jacobi_smallest_t<W, 2>(A, V, nrm, r, m, warm);
-        if (rows <= 4 * W::width) return jacobi_smallest_t<W, 4>(A, V, nrm, r, m, warm);
-        if (rows <= 8 * W::width) return jacobi_smallest_t<W, 8>(A, V, nrm, r, m, warm);
-        return jacobi_smallest_t<W, kMaxSamples / 32>(A, V, nrm, r, m, warm);
+        return jacobi_smallest_t<W, 0>(A, V, nrm, r, m, warm);
     }
 }
 
