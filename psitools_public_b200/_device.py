@@ -152,11 +152,12 @@ class EngineAPI:
         return check(rc, what)
 
     def mode_batch(self, dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
-                   seeds, guesses, max_roots=8, device_aaa=False):
+                   seeds, guesses, max_roots=8, device_aaa=False, dense=False):
         """Run len(dist) PSIMode.calculate searches.  Per-item arrays; ``guesses`` is a list of
         complex sequences.  ``device_aaa=False``: native lock-step engine (AAA with LAPACK on the host
         cores, D and the secant polish on the GPU); ``True``: kernel K4, everything on the device.
-        Returns (list of root arrays, n_function_call array, stats)."""
+        Returns (list of root arrays, n_function_call array, stats); with ``dense=True`` the roots come
+        back as an (n, max_roots) complex matrix plus the per-item root counts instead of a list."""
         if not device_aaa:
             self._bind_lapack()
         n = len(dist)
@@ -169,8 +170,11 @@ class EngineAPI:
         dp = f64(np.stack([np.broadcast_to(tol, (n,)), np.broadcast_to(clean_tol, (n,))], axis=1))
         seeds = np.ascontiguousarray(np.broadcast_to(seeds, (n,)), dtype=np.uint32)
         goff = np.zeros(n + 1, dtype=np.int32)
-        goff[1:] = np.cumsum([len(g) for g in guesses])
-        flat = [complex(z) for g in guesses for z in g]
+        if guesses is None:
+            flat = []
+        else:
+            goff[1:] = np.cumsum([len(g) for g in guesses])
+            flat = [complex(z) for g in guesses for z in g]
         gz = np.ascontiguousarray(np.array(flat, dtype=np.complex128)) if flat else np.zeros(1, np.complex128)
         fn = self.lib.psi_mode_batch_device if device_aaa else self.lib.psi_mode_batch_host
         fn.restype = C.c_int
@@ -199,9 +203,12 @@ class EngineAPI:
             bad = int(np.flatnonzero(st == 1)[0])
             raise PsiError("root search failed for item %d (Kx=%g, Kz=%g): %s"
                            % (bad, kx[bad], kz[bad], self._last_error()))
+        st_out = dict(passes=int(stats[0]), evals=int(stats[1]), logic_s=stats[3]*1e-6,
+                      eval_s=stats[4]*1e-6, launches=int(stats[5]), polish_evals=int(stats[6]))
+        if dense:
+            return (roots, nr), nc, st_out
         out = [roots[i, :nr[i]].copy() for i in range(n)]
-        return out, nc, dict(passes=int(stats[0]), evals=int(stats[1]), logic_s=stats[3]*1e-6,
-                             eval_s=stats[4]*1e-6, launches=int(stats[5]), polish_evals=int(stats[6]))
+        return out, nc, st_out
 
     def contour_batch(self, dist, kx, kz, alpha, z_lists, tol, max_step, max_iter):
         """Root counts of len(dist) closed contours with ONE launch of kernel K2.  Returns (counts,

@@ -70,6 +70,36 @@ def all_gather_records(local):
     return out
 
 
+def all_gather_dense(idx, mat, cnt):
+    """Dense variant for big maps: ``idx`` (n,) global indices, ``mat`` (n, R) complex128 root slots,
+    ``cnt`` (n,) number of valid slots per row.  Returns the concatenation over all ranks (rows in rank
+    order); one all-reduce for the common shape, one all-gather for the data, no per-item Python."""
+    td = _td()
+    idx = np.asarray(idx, dtype=np.int64)
+    cnt = np.asarray(cnt, dtype=np.int64)
+    mat = np.asarray(mat, dtype=np.complex128)
+    mat = mat.reshape(len(idx), -1) if len(idx) else np.zeros((0, max(1, mat.shape[-1] if mat.ndim == 2 else 1)), np.complex128)
+    if td is None or td.get_world_size() == 1:
+        return idx, mat, cnt
+    import torch
+    dev = _device_for_collectives()
+    shape = torch.tensor([len(idx), mat.shape[1]], dtype=torch.int64, device=dev)
+    td.all_reduce(shape, op=td.ReduceOp.MAX)
+    rows, width = int(shape[0]), int(shape[1])
+    buf = np.zeros((rows, 2 + 2*width))
+    buf[:, 0] = -1.0
+    buf[:len(idx), 0] = idx
+    buf[:len(idx), 1] = cnt
+    buf[:len(idx), 2:2 + 2*mat.shape[1]] = mat.view(np.float64)
+    mine = torch.from_numpy(buf).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(td.get_world_size())]
+    td.all_gather(parts, mine)
+    allbuf = torch.cat(parts).cpu().numpy()
+    allbuf = allbuf[allbuf[:, 0] >= 0]
+    return (allbuf[:, 0].astype(np.int64), np.ascontiguousarray(allbuf[:, 2:]).view(np.complex128),
+            allbuf[:, 1].astype(np.int64))
+
+
 def barrier():
     td = _td()
     if td is not None:

@@ -85,45 +85,59 @@ class MpiScheduler:
         return np.asarray(rec, dtype=np.float64).view(np.complex128).copy()
 
     def _run_native(self, arglist, mine):
-        """All of this rank's items through psi_mode_batch_host; None if an item needs the general
-        (Python) path."""
-        pms, calc = [], []
-        for i in mine:
-            a = arglist[i]
-            c = a['calculate']
-            pm = self._cache.get(a['__init__'])
-            if c.get('count_roots', False) or pm.verbose_flag:
-                return None
-            pms.append(pm)
-            calc.append(c)
-        if not pms:
-            return {}, {}
+        """All of this rank's items through the batched engine (K4 pipeline or C++ lock-step engine);
+        None if an item needs the general (Python) path.  Returns (root matrix, root counts, stats)."""
+        if not mine:
+            return (np.zeros((0, 1), dtype=np.complex128), np.zeros(0, dtype=np.int64)), {}
+        # PSIMode per distinct '__init__' (by identity first: map scripts share one dict between items)
+        by_id, pms, which = {}, [], np.empty(len(mine), dtype=np.int64)
+        for k, i in enumerate(mine):
+            init = arglist[i]['__init__']
+            j = by_id.get(id(init))
+            if j is None:
+                pm = self._cache.get(init)
+                for j, known in enumerate(pms):
+                    if known is pm:
+                        break
+                else:
+                    pms.append(pm)
+                    j = len(pms) - 1
+                by_id[id(init)] = j
+            which[k] = j
+        calc = [arglist[i]['calculate'] for i in mine]
+        if any(pm.verbose_flag for pm in pms) or any(c.get('count_roots', False) for c in calc):
+            return None
         ctx = pms[0].psi_dispersion.ctx
         if any(pm.psi_dispersion.ctx is not ctx for pm in pms) or not hasattr(ctx, "mode_batch"):
             return None
         for pm in pms:
             pm._sync_cfg()
-        dom = [[pm.domain.xmin, pm.domain.xmax, pm.domain.ymin, pm.domain.ymax] for pm in pms]
+        per_pm = lambda f, dt=float: np.array([f(pm) for pm in pms], dtype=dt)[which]
+        dom = np.array([[pm.domain.xmin, pm.domain.xmax, pm.domain.ymin, pm.domain.ymax] for pm in pms],
+                       dtype=float)[which]
+        n_sample = per_pm(lambda pm: pm.cfg.n_sample, int)
+        max_zoom = per_pm(lambda pm: pm.cfg.max_zoom_level, int)
+        guesses = [c.get('guess_roots', ()) for c in calc]
+        n_guess = np.fromiter((len(g) for g in guesses), dtype=np.int64, count=len(calc))
         device = self.engine == "device"
         if device:      # the device AAA holds at most 512 samples per search
-            most = max(pm.cfg.n_sample*(1 + len(c.get('guess_roots', ())) + 4*pm.cfg.max_zoom_level)
-                       for pm, c in zip(pms, calc))
+            most = int(np.max(n_sample*(1 + n_guess + 4*max_zoom)))
             device = most <= 512
             if not device:
                 import warnings
                 warnings.warn("a search of this batch can reach %d samples (> 512, the capacity of the "
                               "device AAA): running the batch with engine='native'" % most)
-        roots, ncalls, st = ctx.mode_batch(
-            [pm.psi_dispersion.dist_id for pm in pms],
-            [float(c['wave_number_x']) for c in calc], [float(c['wave_number_z']) for c in calc],
-            [float(c.get('viscous_alpha', 0)) for c in calc], dom,
-            [pm.cfg.n_sample for pm in pms], [pm.cfg.max_zoom_level for pm in pms],
-            [pm.cfg.max_secant_iterations for pm in pms], [pm.cfg.tol for pm in pms],
-            [pm.cfg.clean_tol for pm in pms],
-            [int(arglist[i].get('random_seed', 0)) for i in mine],
-            [list(c.get('guess_roots', ())) for c in calc], device_aaa=device)
+        (roots, nr), ncalls, st = ctx.mode_batch(
+            per_pm(lambda pm: pm.psi_dispersion.dist_id, int),
+            np.fromiter((c['wave_number_x'] for c in calc), dtype=float, count=len(calc)),
+            np.fromiter((c['wave_number_z'] for c in calc), dtype=float, count=len(calc)),
+            np.fromiter((c.get('viscous_alpha', 0) for c in calc), dtype=float, count=len(calc)),
+            dom, n_sample, max_zoom, per_pm(lambda pm: pm.cfg.max_secant_iterations, int),
+            per_pm(lambda pm: pm.cfg.tol), per_pm(lambda pm: pm.cfg.clean_tol),
+            np.fromiter((arglist[i].get('random_seed', 0) for i in mine), dtype=np.int64, count=len(mine)),
+            guesses if n_guess.any() else None, device_aaa=device, dense=True)
         st["function_calls"] = int(np.sum(ncalls))
-        return {i: r for i, r in zip(mine, roots)}, st
+        return (roots, nr), st
 
     def run_all(self, arglist):
         """Results of every item, on every rank."""
@@ -132,18 +146,20 @@ class MpiScheduler:
         if self.engine != "python":
             done = self._run_native(arglist, mine)
             if done is not None:
-                res, st = done
-                if self.verbose:
-                    for i in mine:
-                        print(i, 'result ', res[i])
+                (roots, nr), st = done
                 self.last_stats = dict(items=len(mine), passes=st.get("passes", 0),
                                        function_calls=st.get("function_calls", 0),
                                        evals=st.get("evals", 0), seconds=time.time() - t0,
                                        host_logic_seconds=st.get("logic_s"),
                                        device_seconds=st.get("eval_s"), launches=st.get("launches"),
                                        polish_evals=st.get("polish_evals"), engine=self.engine)
-                merged = _dist.all_gather_records({i: self._encode(r) for i, r in res.items()})
-                return {i: self._decode(merged[i]) for i in sorted(merged)}
+                idx, mat, cnt = _dist.all_gather_dense(mine, roots, nr)
+                order = np.argsort(idx, kind="stable")
+                res = {int(idx[k]): mat[k, :cnt[k]].copy() for k in order}
+                if self.verbose:
+                    for i in mine:
+                        print(i, 'result ', res[i])
+                return res
         jobs, ctx = [], None
         for i in mine:
             job, trace, pm = self._job(arglist[i])
