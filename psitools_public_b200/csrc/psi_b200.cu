@@ -123,16 +123,40 @@ __global__ void background_kernel(NodeTableView t, DistParams* dists, int id) {
 }
 
 // Copy the level-major node table into shared memory (once per persistent CTA) and return a view of it.
+// The 204 KB of (x, w) pairs move with ONE bulk asynchronous copy (TMA, cp.async.bulk) issued by thread
+// 0 and tracked by an mbarrier; the 56 bytes of level offsets go through ordinary loads.
 __device__ __forceinline__ NodeTableView stage_table(const NodeTableView& gt, bool in_smem) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     NodeTableView t = gt;
     if (in_smem) {
+        __shared__ __align__(8) unsigned long long bar;
         node_t* s_nodes = reinterpret_cast<node_t*>(smem_raw);
         int* s_off = reinterpret_cast<int*>(smem_raw + sizeof(node_t) * (size_t)gt.n_nodes);
-        const double2* src = reinterpret_cast<const double2*>(gt.nodes);
-        double2* dst = reinterpret_cast<double2*>(s_nodes);
-        for (int i = threadIdx.x; i < gt.n_nodes; i += blockDim.x) dst[i] = __ldg(src + i);
+        const unsigned bytes = (unsigned)(sizeof(node_t) * (size_t)gt.n_nodes);          // multiple of 16
+        const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&bar);
+        const unsigned dst_addr = (unsigned)__cvta_generic_to_shared(s_nodes);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_addr),
+                "l"(gt.nodes), "r"(bytes), "r"(bar_addr)
+                : "memory");
+        }
         for (int i = threadIdx.x; i < gt.max_m + 2; i += blockDim.x) s_off[i] = gt.level_off[i];
+        // every thread waits for the bulk copy to land (phase 0 of the barrier)
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_addr)
+                : "memory");
+        }
         __syncthreads();
         t.nodes = s_nodes;
         t.level_off = s_off;
@@ -821,27 +845,41 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     const int pgrid = std::min(c->sm_count, (n_items + warps - 1) / warps);
     int launches = 0;
     long long evals = 0;
+    // stage timing (sample, K1, analysis, K3, decide) with CUDA events on the context's stream
+    cudaEvent_t ev[6];
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    double stage_us[5] = {0, 0, 0, 0, 0};
+    auto collect = [&](int upto) {
+        for (int k = 0; k < upto; ++k) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) stage_us[k] += 1e3 * ms;
+        }
+    };
     for (int round = 0; round <= max_zoom; ++round) {
         CK(cudaMemsetAsync(m.counters, 0, 2 * sizeof(unsigned long long), st));
+        CK(cudaEventRecord(ev[0], st));
         mode_sample_kernel<<<tgrid, 256, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
                                                   (const double*)d[7], (const int*)d[8], (const int*)d[9],
                                                   (const double2*)d[10]);
         CK(cudaGetLastError());
         unsigned long long cnt[2] = {0, 0};
+        CK(cudaEventRecord(ev[1], st));
         CK(cudaMemcpyAsync(cnt, m.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const long long n_req = (long long)cnt[0];
-        if (n_req == 0) break;
+        if (n_req == 0) { collect(1); break; }
         evals += n_req;
         rc = launch_disp_eval(c, n_req, 0, (const int*)d[0], (const double*)d[1], (const double*)d[2],
                               (const double*)d[3], (const double*)m.Z, (double*)m.F, nullptr, c->d_counter + 4,
                               mask, st, nullptr, m.elem, cap);
         if (rc != PSI_OK) return rc;
         CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+        CK(cudaEventRecord(ev[2], st));
         mode_analyze_kernel<<<agrid, 256, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
                                                    (const double*)d[6], (const int*)d[9],
                                                    (unsigned char*)c->d_mode_scratch, per_warp, c->d_counter);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ev[3], st));
         for (int cls = 0; cls < kNumClasses; ++cls) {
             if (!(mask & (1u << cls))) continue;
             CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
@@ -854,12 +892,15 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
             ++launches;
         }
         CK(cudaMemsetAsync(m.counters, 0, 2 * sizeof(unsigned long long), st));
+        CK(cudaEventRecord(ev[4], st));
         mode_decide_kernel<<<tgrid, 256, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5]);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ev[5], st));
         launches += 4;
         c->launches += 4;
         CK(cudaMemcpyAsync(cnt, m.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        collect(5);
         if (cnt[1] == 0) break;                                          // nobody wants to zoom
     }
     unsigned long long cnt2[2] = {0, 0};
@@ -869,7 +910,11 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     CK(cudaMemcpyAsync(status, m.status, 4 * ni, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(cnt2, c->d_counter + 4, sizeof(cnt2), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (stats) { stats[0] = launches; stats[1] = evals + (long long)cnt2[1]; stats[2] = (long long)cnt2[0]; }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (stats) {
+        stats[0] = launches; stats[1] = evals + (long long)cnt2[1]; stats[2] = (long long)cnt2[0];
+        for (int k = 0; k < 5; ++k) stats[8 + k] = (long long)stage_us[k];     // stats has 16 slots
+    }
     return PSI_OK;
 }
 
