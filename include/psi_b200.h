@@ -128,7 +128,9 @@ int psi_mode_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double
  * (one-sided Jacobi SVD + Ehrlich-Aberth instead of LAPACK), the zoom logic and the secant polish
  * (csrc/psi_mode.cuh); one launch per work class, no host round trip.  status: 0 ok, 1 non-finite
  * samples (ValueError in the reference), 2 sample capacity, 3 start value on the real axis
- * (ValueError), 4 more roots than max_roots.  stats = {launches, D evaluations, node evaluations}. */
+ * (ValueError), 4 more roots than max_roots.  stats (16 slots) = {launches, D evaluations,
+ * node evaluations, -, -, -, -, -, then microseconds on the stream of the five stages sample, K1, AAA
+ * analysis, K3 polish, decide}. */
 int psi_mode_batch_device(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
                           const double* alpha, const double* domain, const int* iparams, const double* dparams,
                           const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,

@@ -183,7 +183,7 @@ class EngineAPI:
             nr = np.zeros(n, dtype=np.int32)
             nc = np.zeros(n, dtype=np.int32)
             st = np.zeros(n, dtype=np.int32)
-            stats = np.zeros(8, dtype=np.int64)
+            stats = np.zeros(16, dtype=np.int64)
             self._check(fn(self.handle, C.c_int(n), _ptr(dist), _ptr(kx), _ptr(kz), _ptr(alpha),
                            _ptr(domain), _ptr(ip), _ptr(dp), _ptr(seeds), _ptr(goff), _ptr(gz),
                            C.c_int(max_roots), _ptr(roots), _ptr(nr), _ptr(nc), _ptr(st), _ptr(stats)),
@@ -204,7 +204,8 @@ class EngineAPI:
             raise PsiError("root search failed for item %d (Kx=%g, Kz=%g): %s"
                            % (bad, kx[bad], kz[bad], self._last_error()))
         st_out = dict(passes=int(stats[0]), evals=int(stats[1]), logic_s=stats[3]*1e-6,
-                      eval_s=stats[4]*1e-6, launches=int(stats[5]), polish_evals=int(stats[6]))
+                      eval_s=stats[4]*1e-6, launches=int(stats[5]), polish_evals=int(stats[6]),
+                      stage_s=dict(zip(("sample", "k1", "analyze", "k3", "decide"), (stats[8:13]*1e-6).tolist())))
         if dense:
             return (roots, nr), nc, st_out
         out = [roots[i, :nr[i]].copy() for i in range(n)]

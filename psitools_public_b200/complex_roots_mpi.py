@@ -9,7 +9,7 @@ from . import _dist
 from ._engine import Job, run_lockstep
 from .complex_roots import contour_machine
 from .psi_dispersion import PSIDispersion
-from .psi_mode_mpi import _same_init
+from .psi_mode_mpi import _init_key
 
 FAILED_COUNT = -666
 
@@ -23,15 +23,14 @@ class MpiScheduler:
         self.nranks = _dist.world_size()
         self.wall_start = wall_start
         self.wall_limit_total = wall_limit_total
-        self._disp = []
+        self._disp = {}
 
     def _dispersion(self, init):
-        for known, pd in self._disp:
-            if _same_init(known, init):
-                return pd
-        pd = PSIDispersion(**init)
-        self._disp.append((init, pd))
-        return pd
+        key = _init_key(init)
+        hit = self._disp.get(key)
+        if hit is None:
+            hit = self._disp[key] = (PSIDispersion(**init), init)
+        return hit[0]
 
     def _job(self, args):
         pd = self._dispersion(args['PSIDispersion.__init__'])

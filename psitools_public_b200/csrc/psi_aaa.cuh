@@ -1,13 +1,14 @@
 // psi_aaa.cuh -- warp-cooperative AAA rational approximation on the device (kernel K4's building
-// blocks): Loewner-matrix fit by a one-sided complex Jacobi SVD, greedy support-point selection,
+// blocks): Loewner-matrix fit by Householder QR + inverse iteration, greedy support-point selection,
 // Froissart-doublet cleanup, zeros and poles of the barycentric form by Ehrlich-Aberth iteration.
 //
 // Replaces RationalApproximation (complex_roots.py:38-368), which leans on LAPACK (numpy.linalg.svd,
 // scipy.linalg.eig).  The mathematics is the same -- weights = right singular vector of the smallest
 // singular value of the Loewner matrix; poles/zeros = roots of sum_j w_j/(z-z_j) and
 // sum_j w_j f_j/(z-z_j) -- the numerical kernels are GPU-friendly ones:
-//   * one-sided Jacobi keeps high relative accuracy for the tiny singular values AAA lives on and
-//     needs only column operations (lanes split the rows);
+//   * the weights come from a Householder QR of the Loewner matrix (lanes split the rows, four columns
+//     per pass) followed by inverse iteration on the small triangular factor -- a fraction of the
+//     flops of a full SVD and no serial chain of plane rotations;
 //   * Aberth's simultaneous iteration works directly on the barycentric sums (O(m) per root and
 //     step, one root per lane) instead of a generalised eigenvalue problem.
 // One warp owns one approximation; all arrays live in a per-warp scratch area in global memory (L2).
@@ -18,7 +19,7 @@
 namespace psi {
 
 #if defined(PSI_AAA_STATS)
-// test-harness counters: fits, Jacobi sweeps, rotations, Aberth calls, Aberth iterations
+// test-harness counters: fits, inverse iterations, -, Aberth calls, Aberth iterations
 static long long g_aaa_stats[8];
 #define PSI_STAT(i, n) (g_aaa_stats[i] += (n))
 #else
@@ -33,10 +34,9 @@ struct AAAScratch {
     cx* Z;        // [cap]   sample points
     cx* F;        // [cap]   function samples
     int* mask;    // [cap]   1 = support point
-    cx* A;        // [cap * ncol]  Loewner matrix, column-major (destroyed by the SVD)
-    cx* A2;       // [cap * ncol]  Loewner matrix pre-rotated by the previous fit's V (warm start)
-    cx* V;        // [ncol * ncol] right singular vectors
-    cx* V2;       // [ncol * ncol] copy of the previous V while the warm start is assembled
+    cx* A;        // [cap * ncol]  Loewner matrix, column-major (destroyed by the QR)
+    cx* V;        // [ncol * ncol] triangular factor R of the Loewner matrix
+    cx* V2;       // [4 * ncol]    vectors of the inverse iteration
     cx* w;        // [ncol]  weights
     double* R;    // [cap]   residuals at the non-support points (in sample order of those points)
     int* on;      // [ncol]  sample index of the k-th support point
@@ -61,14 +61,13 @@ struct AAAScratch {
     cx* memo_zero;     // [kMemoSlots * ncol]  zeros of the approximant
     int* memo_np;      // [kMemoSlots]   number of stored pole decisions, -1 = not computed yet
     int* memo_nz;      // [kMemoSlots]   number of stored zeros, -1 = not computed yet
-    double* nrm;       // [ncol]  squared column norms (Jacobi)
     int cap, ncol;
 };
 
 PSI_HD size_t aaa_scratch_bytes(int cap) {
     const size_t ncol = (size_t)cap / 2 + 2;
-    return sizeof(cx) * (2 * (size_t)cap + 2 * (size_t)cap * ncol + 2 * ncol * ncol + (6 + 3 * kMemoSlots) * ncol) +
-           sizeof(double) * ((2 + kMemoSlots) * (size_t)cap + kMemoSlots + ncol) +
+    return sizeof(cx) * (2 * (size_t)cap + (size_t)cap * ncol + ncol * ncol + (10 + 3 * kMemoSlots) * ncol) +
+           sizeof(double) * ((2 + kMemoSlots) * (size_t)cap + kMemoSlots) +
            sizeof(int) * ((3 + kMemoSlots) * (size_t)cap + ncol + 3 * kMemoSlots) + 256;
 }
 
@@ -80,9 +79,8 @@ PSI_HD AAAScratch aaa_carve(void* base, int cap) {
     s.Z = c; c += cap;
     s.F = c; c += cap;
     s.A = c; c += (size_t)cap * ncol;
-    s.A2 = c; c += (size_t)cap * ncol;
     s.V = c; c += ncol * ncol;
-    s.V2 = c; c += ncol * ncol;
+    s.V2 = c; c += 4 * ncol;
     s.w = c; c += ncol;
     s.roots = c; c += ncol;
     s.tmp = c; c += ncol;
@@ -97,7 +95,6 @@ PSI_HD AAAScratch aaa_carve(void* base, int cap) {
     s.g_R = d; d += cap;
     s.memo_R = d; d += (size_t)kMemoSlots * cap;
     s.memo_res = d; d += kMemoSlots;
-    s.nrm = d; d += ncol;
     int* i = reinterpret_cast<int*>(d);
     s.mask = i; i += cap;
     s.off = i; i += cap;
@@ -119,8 +116,8 @@ struct AAAState {
     RectDom dom;
     int memo_next;  // next memo slot to overwrite
     int slot;       // memo slot that holds the current mask (set by aaa_fit)
-    int v_m;        // s.V holds the right singular vectors of the last computed fit with v_m support
-                    // points (0 = nothing usable); lets the next greedy step start its SVD warm
+    int v_m;        // s.w holds the weights of the last COMPUTED fit with v_m support points (0 = nothing
+                    // usable); lets the next greedy step start its inverse iteration warm
 };
 
 template <class W>
@@ -146,131 +143,165 @@ PSI_HD void aaa_index(const AAAScratch& s, AAAState& st) {
     st.m = m; st.r = st.M - m;
 }
 
-// One-sided Jacobi SVD of the r x m matrix A (column-major, leading dimension r): on return the
-// columns of A are orthogonal, V holds the accumulated rotations; returns the index of the column
-// with the smallest norm (the right singular vector of the smallest singular value is V[:, j]).
-// CH = row chunks of one warp width per lane: the per-rotation work is straight-line predicated code
-// (no inner loops: the rows of a column pair live in registers between the dot product and the
-// rotation), which matters because this routine is instruction-fetch bound on the GPU.
-template <class W, int CH>
-PSI_NOINLINE int jacobi_smallest_t(cx* A, cx* V, double* nrm, int r, int m, bool warm) {
+// Right singular vector of the smallest singular value of the r x m matrix A (column-major, leading
+// dimension r; destroyed) -- the AAA weights.  Two stages:
+//   1. Householder QR, lanes own rows i = lane (mod width), each reflector applied to four columns at a
+//      time (eight independent warp reductions in flight): A -> m x m triangle R (zero rows if r < m),
+//      written to Rm.  Column-wise backward stable, the same error class as LAPACK's zgesdd that the
+//      reference uses.
+//   2. inverse iteration on R^H R (two triangular solves per step, column oriented: the lanes update
+//      their own entries of the right-hand side, the pivot entry is re-read by everybody), started from
+//      `x0` (the previous weights of the greedy chain, or a generic vector) and stopped when the unit
+//      vector moves by less than 1e-12 or stops contracting; pivots below eps*max|R_kk| are lifted to
+//      that value, which turns an exactly singular R (wide Loewner matrix) into "some null vector".
+// vec: 3*m scratch entries.  The result (unit norm) is written to w.  Returns the iteration count.
+template <class W>
+PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m, bool have_x0) {
     const int lane = W::lane();
-    if (!warm)
-        for (int j = 0; j < m; ++j)
-            for (int i = lane; i < m; i += W::width) V[i + (size_t)j * m] = cx(i == j ? 1.0 : 0.0, 0.0);
-    W::sync();
+    const int steps = r < m ? r : m;
     PSI_STAT(0, 1);
-    double fro2 = 0.0;
-    for (int j = 0; j < m; ++j) {
-        const cx* aj = A + (size_t)j * r;
-        for (int i = lane; i < r; i += W::width) fro2 += aj[i].re * aj[i].re + aj[i].im * aj[i].im;
-    }
-    fro2 = W::sum(fro2);
-    const double negligible = 1.0e-30 * fro2;      // squared norm of a column that is pure rounding noise
-    for (int sweep = 0; sweep < 40; ++sweep) {
-        bool rotated = false;
-        PSI_STAT(1, 1);
-        // squared column norms, refreshed every sweep and updated analytically after each rotation
-        for (int j = 0; j < m; ++j) {
-            double n2 = 0.0;
-            const cx* aj = A + (size_t)j * r;
-            for (int i = lane; i < r; i += W::width) n2 += aj[i].re * aj[i].re + aj[i].im * aj[i].im;
-            n2 = W::sum(n2);
-            if (lane == 0) nrm[j] = n2;
+    for (int k = 0; k < steps; ++k) {
+        cx* ak = A + (size_t)k * r;
+        const int i0 = lane >= k ? lane : lane + ((k - lane + W::width - 1) / W::width) * W::width;   // first own row >= k
+        double n2 = 0.0;
+        for (int i = i0; i < r; i += W::width) n2 += ak[i].re * ak[i].re + ak[i].im * ak[i].im;
+        n2 = W::sum(n2);
+        const cx x0 = ak[k];
+        const double nx = sqrt(n2);
+        if (!(nx > 0.0)) {                                   // zero column: R_kk = 0, nothing to reflect
+            if (lane == 0) Rm[k + (size_t)k * m] = cx(0.0, 0.0);
+            W::sync();
+            continue;
         }
-        W::sync();
-        for (int p = 0; p < m - 1; ++p) {
-            for (int q = p + 1; q < m; ++q) {
-                cx* ap = A + (size_t)p * r;
-                cx* aq = A + (size_t)q * r;
-                const double al = nrm[p], be = nrm[q];
-                if (al <= negligible && be <= negligible) continue;
-                constexpr int NX = CH > 0 ? CH : 1;
-                cx x[NX], y[NX];
-                double gr = 0.0, gi = 0.0;
-                if (CH > 0) {
+        const double a0 = sqrt(x0.re * x0.re + x0.im * x0.im);
+        const cx ph = a0 > 0.0 ? cx(x0.re / a0, x0.im / a0) : cx(1.0, 0.0);
+        // H = I - tau v v^H with v = x + ph*nx*e_0 (no cancellation), H x = -ph*nx*e_0
+        const cx v0(ph.re * (a0 + nx), ph.im * (a0 + nx));
+        const double tau = 1.0 / (nx * (nx + a0));
+        if (lane == 0) Rm[k + (size_t)k * m] = cx(-ph.re * nx, -ph.im * nx);
+        for (int j = k + 1; j < m; j += 4) {
+            const int nj = m - j < 4 ? m - j : 4;
+            double dr[4] = {0.0, 0.0, 0.0, 0.0}, di[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int i = i0; i < r; i += W::width) {
+                const cx v = i == k ? v0 : ak[i];
 #pragma unroll
-                    for (int c = 0; c < NX; ++c) {
-                        const int i = lane + c * W::width;
-                        if (i < r) { x[c] = ap[i]; y[c] = aq[i]; } else { x[c] = cx(0.0, 0.0); y[c] = cx(0.0, 0.0); }
-                        gr += x[c].re * y[c].re + x[c].im * y[c].im;          // conj(x)*y
-                        gi += x[c].re * y[c].im - x[c].im * y[c].re;
-                    }
-                } else {                                  // CH == 0: any number of rows, looped
-                    for (int i = lane; i < r; i += W::width) {
-                        const cx xx = ap[i], yy = aq[i];
-                        gr += xx.re * yy.re + xx.im * yy.im;
-                        gi += xx.re * yy.im - xx.im * yy.re;
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nj) {
+                        const cx a = A[i + (size_t)(j + c) * r];
+                        dr[c] += v.re * a.re + v.im * a.im;                  // conj(v)*a
+                        di[c] += v.re * a.im - v.im * a.re;
                     }
                 }
-                gr = W::sum(gr); gi = W::sum(gi);
-                const double g = sqrt(gr * gr + gi * gi);
-                if (g <= 1.0e-14 * sqrt(al * be) || g == 0.0) continue;
-                rotated = true;
-                PSI_STAT(2, 1);
-                // Hermitian 2x2 [[al, gamma],[conj(gamma), be]]: rotation that annihilates gamma
-                const double zeta = (be - al) / (2.0 * g);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
-                const double ig = 1.0 / g;
-                const cx ph(gr * ig, gi * ig);                 // gamma/|gamma|
-                // a_p' = c*a_p - sn*conj(ph)*a_q ;  a_q' = sn*ph*a_p + c*a_q
-                const cx sp(sn * ph.re, -sn * ph.im), sq(sn * ph.re, sn * ph.im);
-                cx* vp = V + (size_t)p * m;
-                cx* vq = V + (size_t)q * m;
-                if (CH > 0) {
+            }
 #pragma unroll
-                    for (int k = 0; k < NX; ++k) {
-                        const int i = lane + k * W::width;
-                        if (i < r) { ap[i] = c * x[k] - sp * y[k]; aq[i] = sq * x[k] + c * y[k]; }
-                    }
+            for (int c = 0; c < 4; ++c) { dr[c] = W::sum(dr[c]); di[c] = W::sum(di[c]); }
+            for (int i = i0; i < r; i += W::width) {
+                const cx v = i == k ? v0 : ak[i];
 #pragma unroll
-                    for (int k = 0; k < NX; ++k) {
-                        const int i = lane + k * W::width;
-                        if (i < m) {
-                            const cx vx = vp[i], vy = vq[i];
-                            vp[i] = c * vx - sp * vy;
-                            vq[i] = sq * vx + c * vy;
-                        }
-                    }
-                } else {
-                    for (int i = lane; i < r; i += W::width) {
-                        const cx xx = ap[i], yy = aq[i];
-                        ap[i] = c * xx - sp * yy; aq[i] = sq * xx + c * yy;
-                    }
-                    for (int i = lane; i < m; i += W::width) {
-                        const cx vx = vp[i], vy = vq[i];
-                        vp[i] = c * vx - sp * vy; vq[i] = sq * vx + c * vy;
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nj) {
+                        const cx f(tau * dr[c], tau * di[c]);
+                        cx* a = A + i + (size_t)(j + c) * r;
+                        *a = *a - f * v;
                     }
                 }
-                if (lane == 0) { nrm[p] = fmax(al - t * g, 0.0); nrm[q] = be + t * g; }
-                W::sync();
             }
         }
-        if (!rotated) break;
+        W::sync();
     }
-    int best = 0;
-    double bn = -1.0;
-    for (int j = 0; j < m; ++j) {
+    // R: strict upper triangle from A (rows < r), diagonal already in place (zero where no step ran)
+    for (int e = lane; e < m * m; e += W::width) {
+        const int i = e % m, j = e / m;
+        if (i < j) Rm[e] = i < r ? A[i + (size_t)j * r] : cx(0.0, 0.0);
+        else if (i > j || i >= steps) Rm[e] = cx(0.0, 0.0);
+    }
+    W::sync();
+    double dmax = 0.0;
+    for (int k = 0; k < m; ++k) dmax = fmax(dmax, fabs(Rm[k + (size_t)k * m].re) + fabs(Rm[k + (size_t)k * m].im));
+    if (!(dmax > 0.0) || !(dmax < INFINITY)) {              // A = 0 (or not finite): any unit vector
+        for (int j = lane; j < m; j += W::width) w[j] = cx(j == m - 1 ? 1.0 : 0.0, 0.0);
+        W::sync();
+        return 0;
+    }
+    const double piv = 2.220446049250313e-16 * dmax;
+    cx* rinv = vec;              // reciprocals of the (guarded) diagonal
+    cx* b = vec + m;             // right-hand side, consumed by the solves
+    cx* y = vec + 2 * m;         // solution of the current solve
+    for (int k = lane; k < m; k += W::width) {
+        const cx d = Rm[k + (size_t)k * m];
+        rinv[k] = (fabs(d.re) + fabs(d.im) < piv) ? cx(1.0 / piv, 0.0) : recip(d);
+        b[k] = have_x0 ? w[k] : cx(1.0 + 0.25 * (k % 3), 0.125 * (k % 5));
+    }
+    W::sync();
+    {   // normalise the start vector; keep a copy in w for the convergence test
         double n2 = 0.0;
-        const cx* aj = A + (size_t)j * r;
-        for (int i = lane; i < r; i += W::width) n2 += aj[i].re * aj[i].re + aj[i].im * aj[i].im;
+        for (int k = lane; k < m; k += W::width) n2 += b[k].re * b[k].re + b[k].im * b[k].im;
         n2 = W::sum(n2);
-        if (bn < 0.0 || n2 < bn) { bn = n2; best = j; }
+        const double sc = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+        for (int k = lane; k < m; k += W::width) {
+            const cx v = n2 > 0.0 ? cx(b[k].re * sc, b[k].im * sc) : cx(k == 0 ? 1.0 : 0.0, 0.0);
+            b[k] = v; w[k] = v;
+        }
+        W::sync();
     }
-    return best;
-}
-
-template <class W>
-PSI_HD int jacobi_smallest(cx* A, cx* V, double* nrm, int r, int m, bool warm) {
-    const int rows = r > m ? r : m;
-    if constexpr (W::width == 1) {
-        return jacobi_smallest_t<W, 0>(A, V, nrm, r, m, warm);                     // CPU harness: one "lane"
-    } else {
-        // two specialisations only: the routine is instruction-fetch bound, code size matters
-        if (rows <= 2 * W::width) return jacobi_smallest_t<W, 2>(A, V, nrm, r, m, warm);
-        return jacobi_smallest_t<W, 0>(A, V, nrm, r, m, warm);
+    int it = 0;
+    double prev = INFINITY;
+    for (; it < 80; ++it) {
+        PSI_STAT(1, 1);
+        // R^H y = b  (forward; L_ij = conj(R_ji), row j of R is strided in memory)
+        for (int j = 0; j < m; ++j) {
+            const cx rj = rinv[j];
+            const cx yj = b[j] * cx(rj.re, -rj.im);
+            if (lane == 0) y[j] = yj;
+            const int i1 = lane > j ? lane : lane + ((j + 1 - lane + W::width - 1) / W::width) * W::width;
+            for (int i = i1; i < m; i += W::width) {
+                const cx rji = Rm[j + (size_t)i * m];
+                b[i] = b[i] - cx(rji.re, -rji.im) * yj;
+            }
+            W::sync();
+        }
+        {   // rescale (the solve can grow by 1/piv) and move y -> b
+            double n2 = 0.0;
+            for (int k = lane; k < m; k += W::width) n2 = fmax(n2, fabs(y[k].re) + fabs(y[k].im));
+            n2 = W::max(n2);
+            const double sc = n2 > 0.0 ? 1.0 / n2 : 1.0;
+            for (int k = lane; k < m; k += W::width) b[k] = cx(y[k].re * sc, y[k].im * sc);
+            W::sync();
+        }
+        // R z = b  (backward; column j of R is contiguous)
+        for (int j = m - 1; j >= 0; --j) {
+            const cx zj = b[j] * rinv[j];
+            if (lane == 0) y[j] = zj;
+            for (int i = lane; i < j; i += W::width) b[i] = b[i] - Rm[i + (size_t)j * m] * zj;
+            W::sync();
+        }
+        double n2 = 0.0;
+        for (int k = lane; k < m; k += W::width) {
+            // scale first: the entries can be ~1/piv^2
+            n2 = fmax(n2, fabs(y[k].re) + fabs(y[k].im));
+        }
+        n2 = W::max(n2);
+        const double s1 = n2 > 0.0 ? 1.0 / n2 : 1.0;
+        double q2 = 0.0;
+        for (int k = lane; k < m; k += W::width) {
+            const cx v(y[k].re * s1, y[k].im * s1);
+            q2 += v.re * v.re + v.im * v.im;
+        }
+        q2 = W::sum(q2);
+        const double sc = s1 / sqrt(q2);
+        double d2 = 0.0;
+        for (int k = lane; k < m; k += W::width) {
+            const cx v(y[k].re * sc, y[k].im * sc);
+            const cx dv = v - w[k];
+            d2 += dv.re * dv.re + dv.im * dv.im;
+            w[k] = v; b[k] = v;
+        }
+        d2 = W::sum(d2);
+        W::sync();
+        if (d2 <= 1.0e-24 || (d2 <= 1.0e-12 && d2 > 0.25 * prev)) { ++it; break; }
+        prev = d2;
     }
+    return it;
 }
 
 // Loewner fit for the current mask: weights and residuals (complex_roots.py:56-90).  Returns the
@@ -304,43 +335,25 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
     if (r == 0) {
         for (int j = lane; j < m; j += W::width) s.w[j] = cx(j == m - 1 ? 1.0 : 0.0, 0.0);
     } else {
-        // Warm start of the greedy chain: this mask = previous mask + one support point.  The Loewner
-        // entries depend on (sample, support point) only, so the old columns are the previous matrix
-        // minus one row; rotated by the previous V they are orthogonal up to a rank-one change, and
-        // Jacobi needs ~2-3 sweeps instead of ~9.
-        cx* mat = s.A;
-        bool warm = false;
+        // Start vector of the inverse iteration: along the greedy chain (this mask = previous mask + one
+        // support point) the previous weights, with a generic entry for the new column.
+        bool have_x0 = false;
         if (added_sample >= 0 && st.v_m == m - 1 && m >= 3) {
             int pnew = 0;
             while (pnew < m && s.on[pnew] != added_sample) ++pnew;
             if (pnew < m) {
-                warm = true;
-                const int mo = m - 1;
-                for (int e = lane; e < mo * mo; e += W::width) s.V2[e] = s.V[e];
+                cx* old = s.V2 + 3 * (size_t)s.ncol;
+                for (int j = lane; j < m - 1; j += W::width) old[j] = s.w[j];
                 W::sync();
-                for (int i = lane; i < r; i += W::width) {
-                    for (int j = 0; j < mo; ++j) {
-                        cx acc(0.0, 0.0);
-                        for (int k = 0; k < mo; ++k)
-                            acc = acc + s.A[i + (size_t)(k + (k >= pnew)) * r] * s.V2[k + (size_t)j * mo];
-                        s.A2[i + (size_t)(j + (j >= pnew)) * r] = acc;
-                    }
-                    s.A2[i + (size_t)pnew * r] = s.A[i + (size_t)pnew * r];
-                }
-                for (int e = lane; e < m * m; e += W::width) {
-                    const int i = e % m, j = e / m;
-                    cx v(0.0, 0.0);
-                    if (i == pnew || j == pnew) v = cx(i == j ? 1.0 : 0.0, 0.0);
-                    else v = s.V2[(i - (i > pnew)) + (size_t)(j - (j > pnew)) * mo];
-                    s.V[e] = v;
-                }
+                const double gen = 0.5 / sqrt((double)m);
+                for (int j = lane; j < m; j += W::width)
+                    s.w[j] = j == pnew ? cx(gen, 0.5 * gen) : old[j - (j > pnew)];
                 W::sync();
-                mat = s.A2;
+                have_x0 = true;
             }
         }
-        const int jmin = jacobi_smallest<W>(mat, s.V, s.nrm, r, m, warm);
+        loewner_min_vector<W>(s.A, s.V, s.V2, s.w, r, m, have_x0);
         st.v_m = m;
-        for (int j = lane; j < m; j += W::width) s.w[j] = s.V[j + (size_t)jmin * m];
     }
     W::sync();
     double rmax = 0.0;

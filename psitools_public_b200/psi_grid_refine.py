@@ -106,19 +106,37 @@ class PSIGridRefiner:
             if self.sweep_last_grid() == 0:
                 break
 
+    def _shared_init(self, max_zoom):
+        """One '__init__' dict per zoom setting, shared by every run of the campaign (the reference deep
+        copies the whole arg-dict per run, :216-219; the copies are equal, and the scheduler keys its
+        PSIMode cache on their content, so sharing changes nothing but the cost)."""
+        cache = self.__dict__.setdefault('_init_cache', {})
+        if max_zoom not in cache:
+            init = copy.deepcopy(self.baseargs['__init__'])
+            init['max_zoom_domains'] = max_zoom
+            cache[max_zoom] = init
+        return cache[max_zoom]
+
+    def _item(self, max_zoom, kx, kz, guesses=None, seed_shift=0):
+        calc = {k: copy.copy(v) for k, v in self.baseargs['calculate'].items()}
+        calc['wave_number_x'] = kx
+        calc['wave_number_z'] = kz
+        if guesses is not None:
+            calc['guess_roots'] = guesses
+        args = {k: copy.deepcopy(v) for k, v in self.baseargs.items() if k not in ('__init__', 'calculate')}
+        args['__init__'] = self._shared_init(max_zoom)
+        args['calculate'] = calc
+        if seed_shift:
+            args['random_seed'] += seed_shift
+        return args
+
     # -- public API ----------------------------------------------------------------------------
     def run_basegrid(self):
         kx_axis = self._padded_axis(self.nbase[1])
         kz_axis = self._padded_axis(self.nbase[0])
         kz_grid, kx_grid = np.meshgrid(kz_axis, kx_axis, indexing='ij')
         runs = np.arange(kx_grid.size, dtype=int).reshape(kx_grid.shape)
-        arglist = []
-        for kx, kz in zip(kx_grid.ravel(), kz_grid.ravel()):
-            args = copy.deepcopy(self.baseargs)
-            args['__init__']['max_zoom_domains'] = 1
-            args['calculate']['wave_number_x'] = kx
-            args['calculate']['wave_number_z'] = kz
-            arglist.append(args)
+        arglist = [self._item(1, kx, kz) for kx, kz in zip(kx_grid.ravel(), kz_grid.ravel())]
         results = self._run(arglist)
         self.grids.append({'Kx': kx_grid, 'Kz': kz_grid, 'runs': runs, 'results': results,
                            'nguess': np.zeros(kx_grid.shape, dtype=int)})
@@ -130,51 +148,59 @@ class PSIGridRefiner:
         kz_grid = spreadgrid(old['Kz'], const_axis=1)
         runs = -1*np.ones(kx_grid.shape, dtype=int)
         runs[::2, ::2] = old['runs']
+        # root arrays are replaced, never modified in place: a shallow copy of the map is a snapshot
         self.grids.append({'Kx': kx_grid, 'Kz': kz_grid, 'runs': runs,
-                           'results': copy.deepcopy(old['results']),
+                           'results': dict(old['results']),
                            'nguess': np.zeros(kx_grid.shape, dtype=int)})
         if self.root:
             print(' running grid sweeps')
         self._sweep_until_quiet()
 
+    @staticmethod
+    def _root_counts(runs, results):
+        """Number of roots per pixel (0 where no run exists); raises KeyError on a dangling run id like
+        the reference's validity loop (:228-229)."""
+        keys, inverse = np.unique(runs, return_inverse=True)
+        per_key = np.array([len(results[k]) if k >= 0 else 0 for k in keys], dtype=int)
+        return per_key[inverse].reshape(runs.shape)
+
     def sweep_last_grid(self):
-        """Re-run every root-less pixel that has gained neighbour roots; returns #new roots."""
+        """Re-run every root-less pixel that has gained neighbour roots; returns #new roots.
+
+        Same visiting order, guess lists and run ids as the reference (:221-334); only pixels without
+        roots that touch a pixel with roots can launch a run, and those are found with array shifts
+        instead of a Python loop over the whole map."""
         grid = self.grids[-1]
         kx_grid, kz_grid = grid['Kx'], grid['Kz']
         runs, nguess, results = grid['runs'], grid['nguess'], grid['results']
         offset = max(results)
         nz, nx = kz_grid.shape
-        for key in runs.ravel():
-            get_if(results, key)                      # validity of the mapping
+        count = self._root_counts(runs, results)
+        has = count > 0
+        touched = np.zeros_like(has)
+        for diz, dix in _NEIGHBOURS:
+            src = has[max(0, diz):nz + min(0, diz), max(0, dix):nx + min(0, dix)]
+            touched[max(0, -diz):nz + min(0, -diz), max(0, -dix):nx + min(0, -dix)] |= src
+        candidates = np.argwhere(touched & ~has)          # row-major: the reference's iz, ix order
 
         arglist = []
         bump = np.zeros_like(runs)
-        for iz in range(nz):
-            for ix in range(nx):
-                if len(get_if(results, runs[iz, ix])) > 0:
-                    continue                          # never re-run a pixel that has roots
-                near = []
-                for diz, dix in _NEIGHBOURS:
-                    jz, jx = iz + diz, ix + dix
-                    if 0 <= jz < nz and 0 <= jx < nx:
-                        near += get_if(results, runs[jz, jx])
-                if len(near) > 0:
-                    near = prune_eps(near, epsilon=np.array(near).imag.mean()*1e-4)
-                if len(near) > nguess[iz, ix]:        # only when more guesses than last time
-                    nguess[iz, ix] = len(near)
-                    args = copy.deepcopy(self.baseargs)
-                    args['__init__']['max_zoom_domains'] = 0
-                    args['calculate']['wave_number_x'] = kx_grid[iz, ix]
-                    args['calculate']['wave_number_z'] = kz_grid[iz, ix]
-                    args['calculate']['guess_roots'] = near
-                    first = len(arglist)
-                    bump[iz, ix] = offset + first - runs[iz, ix]
+        for iz, ix in candidates:
+            near = []
+            for diz, dix in _NEIGHBOURS:
+                jz, jx = iz + diz, ix + dix
+                if 0 <= jz < nz and 0 <= jx < nx and has[jz, jx]:
+                    near += list(results[runs[jz, jx]])
+            near = prune_eps(near, epsilon=np.array(near).imag.mean()*1e-4)
+            if len(near) > nguess[iz, ix]:            # only when more guesses than last time
+                nguess[iz, ix] = len(near)
+                first = len(arglist)
+                bump[iz, ix] = offset + first - runs[iz, ix]
+                arglist.append(self._item(0, kx_grid[iz, ix], kz_grid[iz, ix], near))
+                for k in range(self.reruns):
+                    args = self._item(0, kx_grid[iz, ix], kz_grid[iz, ix], near, seed_shift=k + 1)
+                    args['is_rerun'] = first          # its roots are appended to the first run's
                     arglist.append(args)
-                    for _ in range(self.reruns):
-                        args = copy.deepcopy(args)
-                        args['random_seed'] += 1
-                        args['is_rerun'] = first      # its roots are appended to the first run's
-                        arglist.append(args)
         if self.root:
             print('Will run ', len(arglist), ' new points')
 
@@ -184,15 +210,15 @@ class PSIGridRefiner:
             for irun in sorted(fresh):
                 if 'is_rerun' in arglist[irun]:
                     key = offset + arglist[irun]['is_rerun']
-                    if len(results[key]) == 0 and len(fresh[irun]) > 0 and self.root:
+                    if len(results[key]) == 0 and len(fresh[irun]) > 0 and self.root and self.verbose:
                         print('combined ', results[key], fresh[irun])
-                    results[key] = np.append(results[key], fresh[irun])
+                    if len(fresh[irun]):
+                        results[key] = np.append(results[key], fresh[irun])
                 else:
                     results[offset + irun] = fresh[irun]
                 newroots += len(fresh[irun])
             runs += bump
-            for key in runs.ravel():
-                get_if(results, key)
+            self._root_counts(runs, results)          # every pixel still maps to a stored run
             grid['runs'], grid['results'] = runs, results
         self.sweep_log.append((len(self.grids) - 1, len(arglist), newroots))
         return newroots

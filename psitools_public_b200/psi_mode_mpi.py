@@ -22,26 +22,64 @@ from .psi_mode import ModeTrace, PSIMode
 DEFAULT_ENGINE = "device"
 
 
-def _same_init(a, b):
+def _fingerprint(obj, depth=0):
+    """Structural key of a PSIMode '__init__' value.  The reference re-creates its PSIMode whenever the
+    '__init__' dict of an item differs from the previous one (psi_mode_mpi.py:168-171); deep copies of an
+    arg-dict (psi_grid_refine.py makes one per run) compare unequal there as soon as they hold an object
+    without __eq__ (a SizeDensity), although they describe the same PSIMode.  Comparing by content lets
+    such campaigns share one PSIMode (and one device distribution)."""
+    if obj is None or isinstance(obj, (bool, int, float, complex, str, bytes)):
+        return (type(obj).__name__, obj)
+    if isinstance(obj, np.generic):
+        return (type(obj).__name__, obj.item())
+    if isinstance(obj, np.ndarray):
+        return ("ndarray", obj.shape, obj.dtype.str, obj.tobytes())
+    if isinstance(obj, (list, tuple)):
+        return ("seq", tuple(_fingerprint(v, depth + 1) for v in obj))
+    if isinstance(obj, dict):
+        return ("dict", tuple(sorted((str(k), _fingerprint(v, depth + 1)) for k, v in obj.items())))
+    if depth > 6 or isinstance(obj, type):
+        return ("id", id(obj))
+    bound_to = getattr(obj, "__self__", None)
+    if bound_to is not None and callable(obj) and not isinstance(bound_to, type(np)):
+        return ("method", getattr(obj, "__name__", ""), _fingerprint(bound_to, depth + 1))   # e.g. PowerBump.sigma0
+    if hasattr(obj, "__code__") or callable(obj) and not hasattr(obj, "__dict__"):
+        return ("id", id(obj))                           # plain functions and builtins: identity
+    state = getattr(obj, "__dict__", None)
+    if isinstance(state, dict):
+        if "xj" in state and "wj" in state:               # quadrature tables: shape and level are enough
+            return ("table", type(obj).__name__, len(state["xj"]), getattr(obj, "max_m", None))
+        return ("obj", type(obj).__qualname__, _fingerprint(state, depth + 1))
+    return ("id", id(obj))
+
+
+def _init_key(init):
     try:
-        return a == b
+        key = _fingerprint(init)
+        hash(key)
     except Exception:
-        return a is b
+        key = ("id", id(init))
+    return key
+
+
+def _same_init(a, b):
+    return a is b or _init_key(a) == _init_key(b)
 
 
 class _ModeCache:
-    """PSIMode objects keyed by '__init__' dict equality (reference psi_mode_mpi.py:168-171)."""
+    """PSIMode objects keyed by the content of the '__init__' dict (reference psi_mode_mpi.py:168-171)."""
 
     def __init__(self):
-        self.entries = []
+        self.entries = {}
 
     def get(self, init):
-        for known, pm in self.entries:
-            if _same_init(known, init):
-                return pm
-        pm = PSIMode(**init)
-        self.entries.append((init, pm))
-        return pm
+        key = _init_key(init)
+        pm = self.entries.get(key)
+        if pm is None:
+            pm = PSIMode(**init)
+            self.entries[key] = (pm, init)               # keep `init` alive: ids inside the key stay unique
+            return pm
+        return pm[0]
 
 
 class MpiScheduler:
@@ -152,7 +190,8 @@ class MpiScheduler:
                                        evals=st.get("evals", 0), seconds=time.time() - t0,
                                        host_logic_seconds=st.get("logic_s"),
                                        device_seconds=st.get("eval_s"), launches=st.get("launches"),
-                                       polish_evals=st.get("polish_evals"), engine=self.engine)
+                                       polish_evals=st.get("polish_evals"), stage_s=st.get("stage_s"),
+                                       engine=self.engine)
                 idx, mat, cnt = _dist.all_gather_dense(mine, roots, nr)
                 order = np.argsort(idx, kind="stable")
                 res = {int(idx[k]): mat[k, :cnt[k]].copy() for k in order}
