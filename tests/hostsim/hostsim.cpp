@@ -127,6 +127,27 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
 extern "C" {
 
 const char* hs_last_error(void) { return g_err.c_str(); }
+// Loewner fit of psi_aaa.cuh for a given support mask: weights (m values, support points in sample order)
+// and the returned residual ratio; lets the CPU suite check the QR + inverse-iteration weights against
+// numpy's SVD.  Returns m.
+int hs_aaa_fit(int M, const double* Z, const double* F, const int* mask, double* w_out, double* resid) {
+    std::vector<unsigned char> buf(aaa_scratch_bytes(M));
+    const AAAScratch sc = aaa_carve(buf.data(), M);
+    AAAState st;
+    st.M = M; st.tol = 1e-13; st.clean_tol = 1e-4; st.dom = RectDom{-1e300, 1e300, -1e300, 1e300};
+    st.memo_next = 0; st.slot = 0; st.v_m = 0;
+    double fm = 0.0;
+    for (int i = 0; i < M; ++i) {
+        sc.Z[i] = cx(Z[2 * i], Z[2 * i + 1]); sc.F[i] = cx(F[2 * i], F[2 * i + 1]); sc.mask[i] = mask[i];
+        fm = fmax(fm, abs_c(sc.F[i]));
+    }
+    st.fmax = fm;
+    aaa_memo_clear<WarpOne>(sc, st);
+    *resid = aaa_fit<WarpOne>(sc, st);
+    for (int j = 0; j < st.m; ++j) { w_out[2 * j] = sc.w[j].re; w_out[2 * j + 1] = sc.w[j].im; }
+    return st.m;
+}
+
 void hs_aaa_stats(long long* out) { for (int i = 0; i < 8; ++i) { out[i] = g_aaa_stats[i]; g_aaa_stats[i] = 0; } }
 
 int psi_polish_batch_host(psi_ctx* c, int n_items, const int* dist, const double* kx, const double* kz,

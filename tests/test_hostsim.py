@@ -46,3 +46,45 @@ def test_disp_eval(ts):
             assert abs(D[i] - ref[i]) <= tol, (case["dist"], w[i])
         if not spec.get("single", False):
             assert nodes >= 300*len(w)
+
+
+def _loewner(Z, F, mask):
+    on, off = np.flatnonzero(mask), np.flatnonzero(~mask)
+    C = 1.0/(Z[off][:, None] - Z[on][None, :])
+    return F[off][:, None]*C - C*F[on][None, :]
+
+
+@pytest.mark.parametrize("M,m,seed", [(20, 3, 0), (20, 7, 1), (20, 11, 2), (100, 12, 3), (100, 30, 4),
+                                      (180, 25, 5), (40, 21, 6)])
+def test_aaa_weights_against_numpy_svd(M, m, seed):
+    """The device AAA takes its weights from a Householder QR + inverse iteration (csrc/psi_aaa.cuh);
+    the reference takes the last right singular vector of numpy's SVD (complex_roots.py:67-82).  On the
+    Loewner matrix of a generic function both must give the same vector up to a phase, and the fit
+    residual ||A w|| must equal the smallest singular value; for a wide matrix (more support points
+    than free samples: M=20, m=11 and M=40, m=21) any null vector is a valid answer."""
+    import ctypes as C
+    rng = np.random.RandomState(seed)
+    Z = rng.uniform(-2, 2, M) + 1j*rng.uniform(1e-3, 1, M)
+    poles = rng.uniform(-3, 3, 40) + 1j*rng.uniform(-2, 2, 40)
+    res = rng.normal(size=40) + 1j*rng.normal(size=40)
+    F = 1e7*(np.sum(res[None, :]/(Z[:, None] - poles[None, :]), axis=1) + np.exp(1j*Z))
+    mask = np.zeros(M, dtype=bool)
+    mask[rng.choice(M, m, replace=False)] = True
+    w = np.zeros(m, dtype=np.complex128)
+    resid = C.c_double(0.0)
+    lib = hs.lib()
+    Zc, Fc, mc = np.ascontiguousarray(Z), np.ascontiguousarray(F), np.ascontiguousarray(mask, dtype=np.int32)
+    got_m = lib.hs_aaa_fit(M, Zc.ctypes.data_as(C.c_void_p), Fc.ctypes.data_as(C.c_void_p),
+                           mc.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), C.byref(resid))
+    assert got_m == m
+    A = _loewner(Z, F, mask)
+    sv = np.linalg.svd(A, compute_uv=False)
+    assert abs(np.linalg.norm(w) - 1.0) < 1e-12
+    fit = np.linalg.norm(A @ w)
+    if M - m < m:                      # wide: exact null vector
+        assert fit <= 1e-12*sv[0]
+        return
+    wref = np.linalg.svd(A)[2][-1].conj()
+    assert fit <= sv[-1]*(1 + 1e-8) + 1e-15*sv[0]
+    gap = (sv[-2] - sv[-1])/sv[0]
+    assert abs(abs(np.vdot(wref, w)) - 1.0) < 1e-10 + 1e-14/max(gap, 1e-16), (abs(np.vdot(wref, w)), gap)
