@@ -26,6 +26,20 @@ static long long g_aaa_stats[8];
 #define PSI_STAT(i, n)
 #endif
 
+// Out-of-line copies of the small helpers.  The analysis kernel is instruction-fetch bound (ncu: 83 % of
+// its stall samples are "no instruction" with 315 KB of SASS and 24 warps per SM in different phases), so
+// every helper exists once instead of at each use, and the strided loops are not unrolled.
+#if defined(__CUDACC__)
+#define PSI_OUTLINE __host__ __device__ __noinline__
+#else
+#define PSI_OUTLINE inline
+#endif
+PSI_OUTLINE cx a_recip(cx a) { return recip(a); }
+PSI_OUTLINE double a_abs(cx a) { return abs_c(a); }
+PSI_OUTLINE cx a_div(cx a, cx b) { return np_div(a, b); }
+template <class W> PSI_OUTLINE double a_sum(double v) { return W::sum(v); }
+template <class W> PSI_OUTLINE double a_max(double v) { return W::max(v); }
+
 constexpr int kMemoSlots = 12;
 constexpr int kMaxSamples = 512;     // largest sample count (cap) the device AAA accepts
 
@@ -164,8 +178,9 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
         cx* ak = A + (size_t)k * r;
         const int i0 = lane >= k ? lane : lane + ((k - lane + W::width - 1) / W::width) * W::width;   // first own row >= k
         double n2 = 0.0;
+#pragma unroll 1
         for (int i = i0; i < r; i += W::width) n2 += ak[i].re * ak[i].re + ak[i].im * ak[i].im;
-        n2 = W::sum(n2);
+        n2 = a_sum<W>(n2);
         const cx x0 = ak[k];
         const double nx = sqrt(n2);
         if (!(nx > 0.0)) {                                   // zero column: R_kk = 0, nothing to reflect
@@ -182,6 +197,7 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
         for (int j = k + 1; j < m; j += 4) {
             const int nj = m - j < 4 ? m - j : 4;
             double dr[4] = {0.0, 0.0, 0.0, 0.0}, di[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
             for (int i = i0; i < r; i += W::width) {
                 const cx v = i == k ? v0 : ak[i];
 #pragma unroll
@@ -193,8 +209,8 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
                     }
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { dr[c] = W::sum(dr[c]); di[c] = W::sum(di[c]); }
+            W::sum4c(dr, di);
+#pragma unroll 1
             for (int i = i0; i < r; i += W::width) {
                 const cx v = i == k ? v0 : ak[i];
 #pragma unroll
@@ -210,6 +226,7 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
         W::sync();
     }
     // R: strict upper triangle from A (rows < r), diagonal already in place (zero where no step ran)
+#pragma unroll 1
     for (int e = lane; e < m * m; e += W::width) {
         const int i = e % m, j = e / m;
         if (i < j) Rm[e] = i < r ? A[i + (size_t)j * r] : cx(0.0, 0.0);
@@ -219,6 +236,7 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
     double dmax = 0.0;
     for (int k = 0; k < m; ++k) dmax = fmax(dmax, fabs(Rm[k + (size_t)k * m].re) + fabs(Rm[k + (size_t)k * m].im));
     if (!(dmax > 0.0) || !(dmax < INFINITY)) {              // A = 0 (or not finite): any unit vector
+#pragma unroll 1
         for (int j = lane; j < m; j += W::width) w[j] = cx(j == m - 1 ? 1.0 : 0.0, 0.0);
         W::sync();
         return 0;
@@ -227,17 +245,20 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
     cx* rinv = vec;              // reciprocals of the (guarded) diagonal
     cx* b = vec + m;             // right-hand side, consumed by the solves
     cx* y = vec + 2 * m;         // solution of the current solve
+#pragma unroll 1
     for (int k = lane; k < m; k += W::width) {
         const cx d = Rm[k + (size_t)k * m];
-        rinv[k] = (fabs(d.re) + fabs(d.im) < piv) ? cx(1.0 / piv, 0.0) : recip(d);
+        rinv[k] = (fabs(d.re) + fabs(d.im) < piv) ? cx(1.0 / piv, 0.0) : a_recip(d);
         b[k] = have_x0 ? w[k] : cx(1.0 + 0.25 * (k % 3), 0.125 * (k % 5));
     }
     W::sync();
     {   // normalise the start vector; keep a copy in w for the convergence test
         double n2 = 0.0;
+#pragma unroll 1
         for (int k = lane; k < m; k += W::width) n2 += b[k].re * b[k].re + b[k].im * b[k].im;
-        n2 = W::sum(n2);
+        n2 = a_sum<W>(n2);
         const double sc = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+#pragma unroll 1
         for (int k = lane; k < m; k += W::width) {
             const cx v = n2 > 0.0 ? cx(b[k].re * sc, b[k].im * sc) : cx(k == 0 ? 1.0 : 0.0, 0.0);
             b[k] = v; w[k] = v;
@@ -254,6 +275,7 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
             const cx yj = b[j] * cx(rj.re, -rj.im);
             if (lane == 0) y[j] = yj;
             const int i1 = lane > j ? lane : lane + ((j + 1 - lane + W::width - 1) / W::width) * W::width;
+#pragma unroll 1
             for (int i = i1; i < m; i += W::width) {
                 const cx rji = Rm[j + (size_t)i * m];
                 b[i] = b[i] - cx(rji.re, -rji.im) * yj;
@@ -262,9 +284,11 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
         }
         {   // rescale (the solve can grow by 1/piv) and move y -> b
             double n2 = 0.0;
+#pragma unroll 1
             for (int k = lane; k < m; k += W::width) n2 = fmax(n2, fabs(y[k].re) + fabs(y[k].im));
-            n2 = W::max(n2);
+            n2 = a_max<W>(n2);
             const double sc = n2 > 0.0 ? 1.0 / n2 : 1.0;
+#pragma unroll 1
             for (int k = lane; k < m; k += W::width) b[k] = cx(y[k].re * sc, y[k].im * sc);
             W::sync();
         }
@@ -272,31 +296,35 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
         for (int j = m - 1; j >= 0; --j) {
             const cx zj = b[j] * rinv[j];
             if (lane == 0) y[j] = zj;
+#pragma unroll 1
             for (int i = lane; i < j; i += W::width) b[i] = b[i] - Rm[i + (size_t)j * m] * zj;
             W::sync();
         }
         double n2 = 0.0;
+#pragma unroll 1
         for (int k = lane; k < m; k += W::width) {
             // scale first: the entries can be ~1/piv^2
             n2 = fmax(n2, fabs(y[k].re) + fabs(y[k].im));
         }
-        n2 = W::max(n2);
+        n2 = a_max<W>(n2);
         const double s1 = n2 > 0.0 ? 1.0 / n2 : 1.0;
         double q2 = 0.0;
+#pragma unroll 1
         for (int k = lane; k < m; k += W::width) {
             const cx v(y[k].re * s1, y[k].im * s1);
             q2 += v.re * v.re + v.im * v.im;
         }
-        q2 = W::sum(q2);
+        q2 = a_sum<W>(q2);
         const double sc = s1 / sqrt(q2);
         double d2 = 0.0;
+#pragma unroll 1
         for (int k = lane; k < m; k += W::width) {
             const cx v(y[k].re * sc, y[k].im * sc);
             const cx dv = v - w[k];
             d2 += dv.re * dv.re + dv.im * dv.im;
             w[k] = v; b[k] = v;
         }
-        d2 = W::sum(d2);
+        d2 = a_sum<W>(d2);
         W::sync();
         if (d2 <= 1.0e-24 || (d2 <= 1.0e-12 && d2 > 0.25 * prev)) { ++it; break; }
         prev = d2;
@@ -315,9 +343,12 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
         if (s.memo_m[k] != m) continue;
         bool same = true;
         const int* mk = s.memo_mask + (size_t)k * s.cap;
+#pragma unroll 1
         for (int i = lane; i < st.M; i += W::width) if (mk[i] != s.mask[i]) same = false;
         if (W::any(!same)) continue;
+#pragma unroll 1
         for (int j = lane; j < m; j += W::width) s.w[j] = s.memo_w[(size_t)k * s.ncol + j];
+#pragma unroll 1
         for (int i = lane; i < r; i += W::width) s.R[i] = s.memo_R[(size_t)k * s.cap + i];
         W::sync();
         st.slot = k;
@@ -326,13 +357,15 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
     }
     for (int j = 0; j < m; ++j) {
         const cx zj = s.Z[s.on[j]], fj = s.F[s.on[j]];
+#pragma unroll 1
         for (int i = lane; i < r; i += W::width) {
-            const cx c = recip(s.Z[s.off[i]] - zj);
+            const cx c = a_recip(s.Z[s.off[i]] - zj);
             s.A[i + (size_t)j * r] = (s.F[s.off[i]] - fj) * c;        // F_i C_ij - C_ij f_j
         }
     }
     W::sync();
     if (r == 0) {
+#pragma unroll 1
         for (int j = lane; j < m; j += W::width) s.w[j] = cx(j == m - 1 ? 1.0 : 0.0, 0.0);
     } else {
         // Start vector of the inverse iteration: along the greedy chain (this mask = previous mask + one
@@ -343,6 +376,7 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
             while (pnew < m && s.on[pnew] != added_sample) ++pnew;
             if (pnew < m) {
                 cx* old = s.V2 + 3 * (size_t)s.ncol;
+#pragma unroll 1
                 for (int j = lane; j < m - 1; j += W::width) old[j] = s.w[j];
                 W::sync();
                 const double gen = 0.5 / sqrt((double)m);
@@ -357,25 +391,29 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
     }
     W::sync();
     double rmax = 0.0;
+#pragma unroll 1
     for (int i = lane; i < r; i += W::width) {
         const cx Zi = s.Z[s.off[i]];
         cx num(0.0, 0.0), den(0.0, 0.0);
         for (int j = 0; j < m; ++j) {
-            const cx t = s.w[j] * recip(Zi - s.Z[s.on[j]]);
+            const cx t = s.w[j] * a_recip(Zi - s.Z[s.on[j]]);
             num = num + t * s.F[s.on[j]];
             den = den + t;
         }
-        const double res = abs_c(s.F[s.off[i]] - num * recip(den));
+        const double res = a_abs(s.F[s.off[i]] - num * a_recip(den));
         s.R[i] = res;
         rmax = fmax(rmax, res);
     }
     W::sync();
-    const double resid = W::max(rmax) / st.fmax;
+    const double resid = a_max<W>(rmax) / st.fmax;
     {   // memo insert
         const int k = st.memo_next;
         st.memo_next = (k + 1) % kMemoSlots;
+#pragma unroll 1
         for (int i = lane; i < st.M; i += W::width) s.memo_mask[(size_t)k * s.cap + i] = s.mask[i];
+#pragma unroll 1
         for (int j = lane; j < m; j += W::width) s.memo_w[(size_t)k * s.ncol + j] = s.w[j];
+#pragma unroll 1
         for (int i = lane; i < r; i += W::width) s.memo_R[(size_t)k * s.cap + i] = s.R[i];
         if (lane == 0) { s.memo_m[k] = m; s.memo_res[k] = resid; s.memo_np[k] = -1; s.memo_nz[k] = -1; }
         W::sync();
@@ -385,14 +423,14 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
 }
 
 // barycentric evaluation r(z) = sum w_j f_j/(z-z_j) / sum w_j/(z-z_j)   (complex_roots.py:331-368)
-PSI_HD cx aaa_eval(const AAAScratch& s, const AAAState& st, cx z) {
+PSI_OUTLINE cx aaa_eval(const AAAScratch& s, const AAAState& st, cx z) {
     cx num(0.0, 0.0), den(0.0, 0.0);
     for (int j = 0; j < st.m; ++j) {
-        const cx t = s.w[j] * recip(z - s.Z[s.on[j]]);
+        const cx t = s.w[j] * a_recip(z - s.Z[s.on[j]]);
         num = num + t * s.F[s.on[j]];
         den = den + t;
     }
-    return num * recip(den);
+    return num * a_recip(den);
 }
 
 // Roots of S(z) = sum_j a_j/(z - z_j) (a_j = w_j for the poles, w_j f_j for the zeros) by the
@@ -408,9 +446,10 @@ PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with
     for (int j = 0; j < m; ++j) { cre += s.Z[s.on[j]].re; cim += s.Z[s.on[j]].im; }
     cre /= m; cim /= m;
     double scale = 0.0;
-    for (int j = 0; j < m; ++j) scale = fmax(scale, abs_c(s.Z[s.on[j]] - cx(cre, cim)));
+    for (int j = 0; j < m; ++j) scale = fmax(scale, a_abs(s.Z[s.on[j]] - cx(cre, cim)));
     if (!(scale > 0.0)) scale = 1.0;
     // start values: between consecutive support points, nudged off the connecting line
+#pragma unroll 1
     for (int k = lane; k < nr; k += W::width) {
         const cx a = s.Z[s.on[k]], b = s.Z[s.on[k + 1]];
         const cx d = b - a;
@@ -430,6 +469,7 @@ PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with
         PSI_STAT(4, 1);
         bool moving = false;
         int slot = 0;
+#pragma unroll 1
         for (int k = lane; k < nr; k += W::width, ++slot) {
             const cx z = out[k];
             const int q = slot < 8 ? slot : 7;
@@ -439,7 +479,7 @@ PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with
             for (int j = 0; j < m; ++j) {
                 const cx dz = z - s.Z[s.on[j]];
                 if (dz.re == 0.0 && dz.im == 0.0) { hit = true; break; }
-                const cx inv = recip(dz);
+                const cx inv = a_recip(dz);
                 cx a = s.w[j];
                 if (with_f) a = a * s.F[s.on[j]];
                 const cx t = a * inv;
@@ -453,7 +493,7 @@ PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with
                 continue;
             }
             if (S.re == 0.0 && S.im == 0.0) { s.tmp[k] = z; frozen[q] = true; continue; }     // exact root
-            const cx newton = recip(S1 * recip(S) + T);      // p/p'
+            const cx newton = a_recip(S1 * a_recip(S) + T);      // p/p'
             cx rep(0.0, 0.0);
             for (int l = 0; l < nr; ++l) {
                 if (l == k) continue;
@@ -461,15 +501,15 @@ PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with
                 if (!finite_c(zl)) continue;
                 const cx dz = z - zl;
                 if (dz.re == 0.0 && dz.im == 0.0) continue;
-                rep = rep + recip(dz);
+                rep = rep + a_recip(dz);
             }
-            const cx step = np_div(newton, cx(1.0, 0.0) - newton * rep);
+            const cx step = a_div(newton, cx(1.0, 0.0) - newton * rep);
             cx zn = z - step;
-            const double sl = abs_c(step);
-            if (!finite_c(zn) || abs_c(zn - cx(cre, cim)) > 1.0e12 * scale) {
+            const double sl = a_abs(step);
+            if (!finite_c(zn) || a_abs(zn - cx(cre, cim)) > 1.0e12 * scale) {
                 zn = cx(INFINITY, 0.0);
-            } else if (sl <= 1.0e-15 * abs_c(zn) ||
-                       (sl <= 1.0e-9 * (abs_c(zn) + scale) && sl > 0.1 * prev_step[q])) {
+            } else if (sl <= 1.0e-15 * a_abs(zn) ||
+                       (sl <= 1.0e-9 * (a_abs(zn) + scale) && sl > 0.1 * prev_step[q])) {
                 if (slot < 8) frozen[q] = true;
                 if (sl > prev_step[q]) zn = z;              // keep the better iterate
             } else {
@@ -479,6 +519,7 @@ PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with
             s.tmp[k] = zn;
         }
         W::sync();
+#pragma unroll 1
         for (int k = lane; k < nr; k += W::width) out[k] = s.tmp[k];
         W::sync();
         if (!W::any(moving)) break;
@@ -499,6 +540,7 @@ template <class W>
 PSI_HD void sort_complex(const cx* in, cx* out, int n) {
     const int lane = W::lane();
     W::sync();
+#pragma unroll 1
     for (int k = lane; k < n; k += W::width) {
         int rank = 0;
         for (int l = 0; l < n; ++l)
@@ -518,11 +560,13 @@ PSI_NOINLINE int aaa_zeros(const AAAScratch& s, const AAAState& st) {
     if (nr <= 0) return 0;
     if (s.memo_nz[st.slot] >= 0) {                       // same support mask seen before: replay
         const int n = s.memo_nz[st.slot];
+#pragma unroll 1
         for (int k = lane; k < n; k += W::width) s.roots[k] = s.memo_zero[(size_t)st.slot * s.ncol + k];
         W::sync();
         return n;
     }
     aberth_roots<W>(s, st, true, s.roots);
+#pragma unroll 1
     for (int k = lane; k < nr; k += W::width) {
         const cx z0 = s.roots[k];
         if (!finite_c(z0)) continue;
@@ -532,20 +576,20 @@ PSI_NOINLINE int aaa_zeros(const AAAScratch& s, const AAAState& st) {
         bool ok = finite_c(q0) && finite_c(q1), flagged = false;
         cx root = z0;
         if (ok) {
-            if (abs_c(q1) < abs_c(q0)) { cx t = p0; p0 = p1; p1 = t; t = q0; q0 = q1; q1 = t; }
+            if (a_abs(q1) < a_abs(q0)) { cx t = p0; p0 = p1; p1 = t; t = q0; q0 = q1; q1 = t; }
             cx p = p1;
             bool done = false;
             for (int it = 0; it < 50 && !done; ++it) {
                 if (eq_c(q1, q0)) { flagged = !eq_c(p1, p0); root = cx(0.5 * (p1.re + p0.re), 0.5 * (p1.im + p0.im)); done = true; break; }
-                if (abs_c(q1) > abs_c(q0)) {
-                    const cx rr = np_div(q0, q1);
-                    p = np_div(np_mul(-rr, p1) + p0, cx(1.0 - rr.re, -rr.im));
+                if (a_abs(q1) > a_abs(q0)) {
+                    const cx rr = a_div(q0, q1);
+                    p = a_div(np_mul(-rr, p1) + p0, cx(1.0 - rr.re, -rr.im));
                 } else {
-                    const cx rr = np_div(q1, q0);
-                    p = np_div(np_mul(-rr, p0) + p1, cx(1.0 - rr.re, -rr.im));
+                    const cx rr = a_div(q1, q0);
+                    p = a_div(np_mul(-rr, p0) + p1, cx(1.0 - rr.re, -rr.im));
                 }
                 if (!finite_c(p)) { ok = false; break; }
-                if (abs_c(p - p1) <= 1.48e-8) { root = p; done = true; break; }
+                if (a_abs(p - p1) <= 1.48e-8) { root = p; done = true; break; }
                 p0 = p1; q0 = q1; p1 = p;
                 q1 = aaa_eval(s, st, p1);
                 if (!finite_c(q1)) { ok = false; break; }
@@ -572,6 +616,7 @@ PSI_NOINLINE int aaa_zeros(const AAAScratch& s, const AAAState& st) {
         const cx d = s.tmp[k] - s.tmp[k - 1];
         if (np_less(cx(1.0e-12, 0.0), d)) ++n;
     }
+#pragma unroll 1
     for (int k = lane; k < n; k += W::width) s.memo_zero[(size_t)st.slot * s.ncol + k] = s.roots[k];
     if (lane == 0) s.memo_nz[st.slot] = n;
     W::sync();
@@ -592,6 +637,7 @@ PSI_NOINLINE int aaa_cleanup(const AAAScratch& s, AAAState& st) {
         const double c45 = 0.7071067811865476;
         const cx ring[4] = {cx(side * c45, -side * c45), cx(side * c45, side * c45), cx(-side * c45, side * c45),
                             cx(-side * c45, -side * c45)};
+#pragma unroll 1
         for (int k = lane; k < np_; k += W::width) {
             const cx pole = s.roots[k];
             cx d(INFINITY, -1.0);
@@ -605,10 +651,10 @@ PSI_NOINLINE int aaa_cleanup(const AAAScratch& s, AAAState& st) {
                 }
                 int nearest = 0; double bd = INFINITY;
                 for (int j = 0; j < st.m; ++j) {
-                    const double dd = abs_c(pole - s.Z[s.on[j]]);
+                    const double dd = a_abs(pole - s.Z[s.on[j]]);
                     if (dd < bd) { bd = dd; nearest = j; }
                 }
-                d = cx(abs_c(integral) / st.fmax, (double)s.on[nearest]);
+                d = cx(a_abs(integral) / st.fmax, (double)s.on[nearest]);
             }
             dec[k] = d;
         }
@@ -636,12 +682,14 @@ PSI_NOINLINE bool aaa_calculate(const AAAScratch& s, AAAState& st, bool reuse_gr
     if (!reuse_greedy) {
         aaa_memo_clear<W>(s, st);
         double fm = 0.0; bool fin = true;
+#pragma unroll 1
         for (int i = lane; i < M; i += W::width) {
-            fm = fmax(fm, abs_c(s.F[i]));
+            fm = fmax(fm, a_abs(s.F[i]));
             if (!finite_c(s.F[i]) || !finite_c(s.Z[i])) fin = false;
         }
-        st.fmax = W::max(fm);
+        st.fmax = a_max<W>(fm);
         if (W::any(!fin)) return false;
+#pragma unroll 1
         for (int i = lane; i < M; i += W::width) s.mask[i] = (i < 2) ? 1 : 0;
         W::sync();
         st.v_m = 0;
@@ -658,10 +706,12 @@ PSI_NOINLINE bool aaa_calculate(const AAAScratch& s, AAAState& st, bool reuse_gr
             W::sync();
             if (aaa_fit<W>(s, st, added) < st.tol) break;
         }
+#pragma unroll 1
         for (int i = lane; i < M; i += W::width) s.g_mask[i] = s.mask[i];
         W::sync();
     } else {
         // replay: restore the greedy mask; its fit comes out of the memo (or is recomputed if evicted)
+#pragma unroll 1
         for (int i = lane; i < M; i += W::width) s.mask[i] = s.g_mask[i];
         W::sync();
         aaa_fit<W>(s, st);

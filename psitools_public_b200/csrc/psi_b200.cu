@@ -49,6 +49,17 @@ struct WarpCuda {
         for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
         return v;
     }
+    // four complex sums at once: the eight butterflies are independent, one rolled loop over the rounds
+    static __device__ __noinline__ void sum4c(double (&re)[4], double (&im)[4]) {
+#pragma unroll 1
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                re[c] += __shfl_xor_sync(0xffffffffu, re[c], o);
+                im[c] += __shfl_xor_sync(0xffffffffu, im[c], o);
+            }
+        }
+    }
     static __device__ __forceinline__ void sync() { __syncwarp(); }
     static __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
     // largest v over the lanes, ties to the smallest index (idx < 0: lane has no candidate)

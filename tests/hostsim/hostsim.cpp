@@ -23,6 +23,7 @@ struct WarpOne {
     static double sum(double v) { return v; }
     static double max(double v) { return v; }
     static void sync() {}
+    static void sum4c(double (&)[4], double (&)[4]) {}
     static bool any(bool p) { return p; }
     static void argmax(double&, int&) {}
 };
