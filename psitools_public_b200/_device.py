@@ -154,7 +154,7 @@ class EngineAPI:
     def mode_batch(self, dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
                    seeds, guesses, max_roots=8, device_aaa=False, dense=False):
         """Run len(dist) PSIMode.calculate searches.  Per-item arrays; ``guesses`` is a list of
-        complex sequences.  ``device_aaa=False``: native lock-step engine (AAA with LAPACK on the host
+        complex sequences or the CSR pair (flat values, n+1 offsets).  ``device_aaa=False``: native lock-step engine (AAA with LAPACK on the host
         cores, D and the secant polish on the GPU); ``True``: kernel K4, everything on the device.
         Returns (list of root arrays, n_function_call array, stats); with ``dense=True`` the roots come
         back as an (n, max_roots) complex matrix plus the per-item root counts instead of a list."""
@@ -172,10 +172,13 @@ class EngineAPI:
         goff = np.zeros(n + 1, dtype=np.int32)
         if guesses is None:
             flat = []
+        elif isinstance(guesses, tuple):          # CSR form: (flat complex array, n+1 offsets)
+            flat = np.asarray(guesses[0], dtype=np.complex128)
+            goff[:] = np.asarray(guesses[1], dtype=np.int64)
         else:
             goff[1:] = np.cumsum([len(g) for g in guesses])
             flat = [complex(z) for g in guesses for z in g]
-        gz = np.ascontiguousarray(np.array(flat, dtype=np.complex128)) if flat else np.zeros(1, np.complex128)
+        gz = np.ascontiguousarray(np.array(flat, dtype=np.complex128)) if len(flat) else np.zeros(1, np.complex128)
         fn = self.lib.psi_mode_batch_device if device_aaa else self.lib.psi_mode_batch_host
         fn.restype = C.c_int
         while True:

@@ -141,20 +141,27 @@ PSI_HD void aaa_memo_clear(const AAAScratch& s, AAAState& st) {
     W::sync();
 }
 
-// rebuild the index lists from the mask (every lane computes the same lists)
+// rebuild the index lists from the mask: one ballot per chunk of `width` samples, every lane places its
+// own sample behind the support / non-support points counted so far
 template <class W>
-PSI_HD void aaa_index(const AAAScratch& s, AAAState& st) {
+PSI_OUTLINE void aaa_index(const AAAScratch& s, AAAState& st) {
     W::sync();
-    if (W::lane() == 0) {
-        int m = 0, r = 0;
-        for (int i = 0; i < st.M; ++i) {
-            if (s.mask[i]) s.on[m++] = i; else s.off[r++] = i;
-        }
+    const int lane = W::lane();
+    int m = 0, r = 0;
+#pragma unroll 1
+    for (int base = 0; base < st.M; base += W::width) {
+        const int i = base + lane;
+        const bool in = i < st.M;
+        const bool on = in && s.mask[i] != 0;
+        const unsigned set = W::ballot(on), all = W::ballot(in);
+        const unsigned below = lane == 0 ? 0u : (0xffffffffu >> (32 - lane));
+        if (on) s.on[m + W::popc(set & below)] = i;
+        else if (in) s.off[r + W::popc(all & ~set & below)] = i;
+        m += W::popc(set);
+        r += W::popc(all & ~set);
     }
     W::sync();
-    int m = 0;
-    for (int i = 0; i < st.M; ++i) m += s.mask[i] ? 1 : 0;
-    st.m = m; st.r = st.M - m;
+    st.m = m; st.r = r;
 }
 
 // Right singular vector of the smallest singular value of the r x m matrix A (column-major, leading

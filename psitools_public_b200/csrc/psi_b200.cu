@@ -61,6 +61,8 @@ struct WarpCuda {
         }
     }
     static __device__ __forceinline__ void sync() { __syncwarp(); }
+    static __device__ __forceinline__ unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+    static __device__ __forceinline__ int popc(unsigned v) { return __popc(v); }
     static __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
     // largest v over the lanes, ties to the smallest index (idx < 0: lane has no candidate)
     static __device__ __forceinline__ void argmax(double& v, int& idx) {
@@ -814,10 +816,12 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     const size_t ni = (size_t)n_items, ng = (size_t)guess_off[n_items];
     const int P = cap / 2 + 2;
     // AAA scratch: one area per warp of the analysis kernel
-    const int awarps = 256 / 32;
-    const int agrid = std::min(c->sm_count * 4, (n_items + awarps - 1) / awarps);
+    static const int an_threads = getenv("PSI_AN_THREADS") ? atoi(getenv("PSI_AN_THREADS")) : 256;
+    static const int an_ctas = getenv("PSI_AN_CTAS") ? atoi(getenv("PSI_AN_CTAS")) : 4;
+    const int awarps = an_threads / 32;
+    const int agrid = std::min(c->sm_count * an_ctas, (n_items + awarps - 1) / awarps);
     const size_t per_warp = (aaa_scratch_bytes(cap) + 255) & ~(size_t)255;
-    const size_t need = per_warp * (size_t)c->sm_count * 4 * awarps;
+    const size_t need = per_warp * (size_t)c->sm_count * an_ctas * awarps;
     if (need > c->mode_scratch_bytes) {
         if (c->d_mode_scratch) CK(cudaFree(c->d_mode_scratch));
         c->d_mode_scratch = nullptr; c->mode_scratch_bytes = 0;
@@ -886,7 +890,7 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         if (rc != PSI_OK) return rc;
         CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
         CK(cudaEventRecord(ev[2], st));
-        mode_analyze_kernel<<<agrid, 256, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
+        mode_analyze_kernel<<<agrid, an_threads, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
                                                    (const double*)d[6], (const int*)d[9],
                                                    (unsigned char*)c->d_mode_scratch, per_warp, c->d_counter);
         CK(cudaGetLastError());

@@ -15,6 +15,7 @@ Out of scope: prune_kmeans (dead code in the reference, :87-98, :272-273).
 """
 import copy
 import time
+from collections.abc import MutableMapping
 
 import numpy as np
 
@@ -56,6 +57,69 @@ def prune_eps(values, epsilon=1e-5):
 
 
 _NEIGHBOURS = ((-1, -1), (0, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (0, 1), (1, 1))   # (diz, dix)
+
+
+class RootStore(MutableMapping):
+    """The reference's ``results`` dict {run id: complex array of roots} held as two dense arrays (a root
+    matrix and a count per run id, -1 = no such run), so that sweeps over million-pixel maps need no
+    per-run Python objects.  Behaves like the dict for readers (indexing, iteration in ascending id order,
+    ``max``, ``len``, ``in``)."""
+
+    def __init__(self, source=None, width=4):
+        self.mat = np.zeros((0, width), dtype=np.complex128)
+        self.cnt = np.zeros(0, dtype=np.int64)
+        if source is not None:
+            for key in sorted(source):
+                self[key] = source[key]
+
+    def _reserve(self, n_keys, width):
+        if n_keys > len(self.cnt) or width > self.mat.shape[1]:
+            rows = max(n_keys, 2*len(self.cnt)) if n_keys > len(self.cnt) else len(self.cnt)
+            mat = np.zeros((rows, max(width, self.mat.shape[1])), dtype=np.complex128)
+            mat[:len(self.cnt), :self.mat.shape[1]] = self.mat
+            cnt = np.full(rows, -1, dtype=np.int64)
+            cnt[:len(self.cnt)] = self.cnt
+            self.mat, self.cnt = mat, cnt
+
+    @property
+    def max_key(self):
+        return int(np.flatnonzero(self.cnt >= 0)[-1])
+
+    def copy(self):
+        new = RootStore(width=self.mat.shape[1])
+        new.mat, new.cnt = self.mat.copy(), self.cnt.copy()
+        return new
+
+    def counts(self, keys):
+        """Root counts for an integer array of run ids (-1 = no run: 0 roots); KeyError on unknown ids."""
+        keys = np.asarray(keys)
+        safe = np.where(keys >= 0, keys, 0)
+        if keys.size and (safe.max() >= len(self.cnt) or np.any((self.cnt[safe] < 0) & (keys >= 0))):
+            raise KeyError('run id without stored result')
+        return np.where(keys >= 0, self.cnt[safe], 0)
+
+    def __getitem__(self, key):
+        key = int(key)
+        if key < 0 or key >= len(self.cnt) or self.cnt[key] < 0:
+            raise KeyError(key)
+        return self.mat[key, :self.cnt[key]].copy()
+
+    def __setitem__(self, key, roots):
+        key = int(key)
+        roots = np.asarray(roots, dtype=np.complex128).ravel()
+        self._reserve(key + 1, len(roots))
+        self.mat[key, :len(roots)] = roots
+        self.cnt[key] = len(roots)
+
+    def __delitem__(self, key):
+        self[key]
+        self.cnt[int(key)] = -1
+
+    def __iter__(self):
+        return iter(np.flatnonzero(self.cnt >= 0).tolist())
+
+    def __len__(self):
+        return int(np.count_nonzero(self.cnt >= 0))
 
 
 class PSIGridRefiner:
@@ -106,6 +170,19 @@ class PSIGridRefiner:
             if self.sweep_last_grid() == 0:
                 break
 
+    def _array_path(self):
+        """True when sweeps can use the array form end to end: the stock scheduler (not wrapped or
+        subclassed with its own run_all), a batched engine, and a 'calculate' template that carries
+        nothing but the wave numbers, the guesses and optionally viscous_alpha."""
+        ms = self.ms
+        if type(ms) is not psi_mode_mpi.MpiScheduler or 'run_all' in ms.__dict__ or ms.engine == "python":
+            return False
+        if self.verbose or self.baseargs['__init__'].get('verbose_flag', False):
+            return False
+        extra = set(self.baseargs['calculate']) - {'wave_number_x', 'wave_number_z', 'guess_roots',
+                                                   'viscous_alpha'}
+        return not extra and set(self.baseargs) <= {'__init__', 'calculate', 'random_seed'}
+
     def _shared_init(self, max_zoom):
         """One '__init__' dict per zoom setting, shared by every run of the campaign (the reference deep
         copies the whole arg-dict per run, :216-219; the copies are equal, and the scheduler keys its
@@ -136,8 +213,19 @@ class PSIGridRefiner:
         kz_axis = self._padded_axis(self.nbase[0])
         kz_grid, kx_grid = np.meshgrid(kz_axis, kx_axis, indexing='ij')
         runs = np.arange(kx_grid.size, dtype=int).reshape(kx_grid.shape)
-        arglist = [self._item(1, kx, kz) for kx, kz in zip(kx_grid.ravel(), kz_grid.ravel())]
-        results = self._run(arglist)
+        results = None
+        if self._array_path():
+            got = self.ms.run_arrays(self._shared_init(1), kx_grid.ravel(), kz_grid.ravel(),
+                                     self.baseargs.get('random_seed', 0),
+                                     alpha=self.baseargs['calculate'].get('viscous_alpha', 0))
+            if got is not None:
+                results = RootStore(width=got[0].shape[1])
+                results._reserve(kx_grid.size, got[0].shape[1])
+                results.mat[:kx_grid.size, :got[0].shape[1]] = got[0]
+                results.cnt[:kx_grid.size] = got[1]
+        if results is None:
+            arglist = [self._item(1, kx, kz) for kx, kz in zip(kx_grid.ravel(), kz_grid.ravel())]
+            results = self._run(arglist)
         self.grids.append({'Kx': kx_grid, 'Kz': kz_grid, 'runs': runs, 'results': results,
                            'nguess': np.zeros(kx_grid.shape, dtype=int)})
         self._sweep_until_quiet()
@@ -150,7 +238,7 @@ class PSIGridRefiner:
         runs[::2, ::2] = old['runs']
         # root arrays are replaced, never modified in place: a shallow copy of the map is a snapshot
         self.grids.append({'Kx': kx_grid, 'Kz': kz_grid, 'runs': runs,
-                           'results': dict(old['results']),
+                           'results': old['results'].copy(),
                            'nguess': np.zeros(kx_grid.shape, dtype=int)})
         if self.root:
             print(' running grid sweeps')
@@ -164,6 +252,108 @@ class PSIGridRefiner:
         per_key = np.array([len(results[k]) if k >= 0 else 0 for k in keys], dtype=int)
         return per_key[inverse].reshape(runs.shape)
 
+    @staticmethod
+    def _candidates(has):
+        """Pixels without roots that touch (8-neighbourhood) a pixel with roots, in row-major order."""
+        nz, nx = has.shape
+        touched = np.zeros_like(has)
+        for diz, dix in _NEIGHBOURS:
+            src = has[max(0, diz):nz + min(0, diz), max(0, dix):nx + min(0, dix)]
+            touched[max(0, -diz):nz + min(0, -diz), max(0, -dix):nx + min(0, -dix)] |= src
+        return np.argwhere(touched & ~has)
+
+    def _sweep_arrays(self, grid):
+        """sweep_last_grid on arrays: neighbour roots are gathered, pruned (prune_eps, same greedy order)
+        and compared with ``nguess`` for all candidate pixels at once, the runs go to the scheduler as
+        arrays (run_arrays) and their roots are merged into the RootStore by run id exactly as the
+        dict-based path does (first run of a pixel assigns, its reruns append)."""
+        kx_grid, kz_grid = grid['Kx'], grid['Kz']
+        runs, nguess, store = grid['runs'], grid['nguess'], grid['results']
+        offset = store.max_key
+        nz, nx = runs.shape
+        has = store.counts(runs) > 0
+        cand = self._candidates(has)
+        cz, cx = cand[:, 0], cand[:, 1]
+        nc, width = len(cand), store.mat.shape[1]
+        # neighbour roots in the reference's order: neighbour by neighbour, each run's roots in order
+        near = np.full((nc, 8*width), np.nan + 0j)
+        slot = np.arange(width)[None, :]
+        for q, (diz, dix) in enumerate(_NEIGHBOURS):
+            jz, jx = cz + diz, cx + dix
+            ok = (jz >= 0) & (jz < nz) & (jx >= 0) & (jx < nx)
+            key = np.where(ok, runs[np.clip(jz, 0, nz - 1), np.clip(jx, 0, nx - 1)], -1)
+            ok &= key >= 0
+            key = np.where(ok, key, 0)
+            n_here = np.where(ok, store.cnt[key], 0)
+            near[:, q*width:(q + 1)*width] = np.where(slot < n_here[:, None], store.mat[key], np.nan)
+        valid = ~np.isnan(near.real)
+        n_near = valid.sum(axis=1)
+        order = np.argsort(~valid, axis=1, kind='stable')            # valid entries first, order kept
+        longest = int(n_near.max()) if nc else 0
+        near = np.take_along_axis(near, order[:, :longest], axis=1)
+        # epsilon = mean(imag)*1e-4 over exactly the pixel's values (same summation as the list version)
+        eps = np.zeros(nc)
+        for length in np.unique(n_near):
+            rows = np.flatnonzero(n_near == length)
+            eps[rows] = np.ascontiguousarray(near[rows, :length]).imag.mean(axis=1)*1e-4
+        kept = np.zeros((nc, max(longest, 1)), dtype=np.complex128)
+        n_kept = np.zeros(nc, dtype=np.int64)
+        rows_all = np.arange(nc)
+        for col in range(longest):
+            v = near[:, col]
+            keep = col < n_near
+            if col > 0:
+                top = int(n_kept.max())
+                close = np.abs(v[:, None] - kept[:, :top]) < eps[:, None]
+                close &= np.arange(top)[None, :] < n_kept[:, None]
+                keep &= ~(close.any(axis=1) & (n_near > 1))           # a single value is never pruned
+            r = rows_all[keep]
+            kept[r, n_kept[r]] = v[r]
+            n_kept[r] += 1
+        go = n_kept > nguess[cz, cx]
+        cz, cx, kept, n_kept = cz[go], cx[go], kept[go], n_kept[go]
+        nguess[cz, cx] = n_kept
+        n_run, per = len(cz), 1 + self.reruns
+        if self.root:
+            print('Will run ', n_run*per, ' new points')
+        newroots = 0
+        if n_run:
+            first = np.arange(n_run)*per
+            bump = np.zeros_like(runs)
+            bump[cz, cx] = offset + first - runs[cz, cx]
+            flat_one = kept[np.arange(kept.shape[1])[None, :] < n_kept[:, None]]      # row-major: per pixel
+            starts = np.zeros(n_run + 1, dtype=np.int64)
+            np.cumsum(n_kept, out=starts[1:])
+            # every pixel's guess list once per (re)run
+            lengths = np.repeat(n_kept, per)
+            off = np.zeros(n_run*per + 1, dtype=np.int64)
+            np.cumsum(lengths, out=off[1:])
+            take = np.repeat(np.repeat(starts[:-1], per) - off[:-1], lengths) + np.arange(off[-1])
+            seeds = self.baseargs.get('random_seed', 0) + np.tile(np.arange(per), n_run)
+            got = self.ms.run_arrays(self._shared_init(0), np.repeat(kx_grid[cz, cx], per),
+                                     np.repeat(kz_grid[cz, cx], per), seeds, guesses=(flat_one[take], off),
+                                     alpha=self.baseargs['calculate'].get('viscous_alpha', 0))
+            if got is None:
+                raise RuntimeError('scheduler refused the array batch')
+            mat, cnt = got
+            newroots = int(cnt.sum())
+            total = cnt.reshape(n_run, per).sum(axis=1)
+            keys = offset + first
+            store._reserve(int(keys[-1]) + 1, int(total.max()))
+            store.cnt[keys] = 0
+            pos = np.zeros(n_run, dtype=np.int64)
+            for q in range(per):
+                c = cnt[first + q]
+                for t in range(int(c.max()) if n_run else 0):
+                    sel = np.flatnonzero(c > t)
+                    store.mat[keys[sel], pos[sel] + t] = mat[first[sel] + q, t]
+                pos += c
+            store.cnt[keys] = pos
+            runs += bump
+            store.counts(runs)                        # every pixel still maps to a stored run
+        self.sweep_log.append((len(self.grids) - 1, n_run*per, newroots))
+        return newroots
+
     def sweep_last_grid(self):
         """Re-run every root-less pixel that has gained neighbour roots; returns #new roots.
 
@@ -171,17 +361,19 @@ class PSIGridRefiner:
         roots that touch a pixel with roots can launch a run, and those are found with array shifts
         instead of a Python loop over the whole map."""
         grid = self.grids[-1]
+        if self._array_path():
+            if not isinstance(grid['results'], RootStore):
+                grid['results'] = RootStore(grid['results'])
+            done = self._sweep_arrays(grid)
+            if done is not None:
+                return done
         kx_grid, kz_grid = grid['Kx'], grid['Kz']
         runs, nguess, results = grid['runs'], grid['nguess'], grid['results']
         offset = max(results)
         nz, nx = kz_grid.shape
         count = self._root_counts(runs, results)
         has = count > 0
-        touched = np.zeros_like(has)
-        for diz, dix in _NEIGHBOURS:
-            src = has[max(0, diz):nz + min(0, diz), max(0, dix):nx + min(0, dix)]
-            touched[max(0, -diz):nz + min(0, -diz), max(0, -dix):nx + min(0, -dix)] |= src
-        candidates = np.argwhere(touched & ~has)          # row-major: the reference's iz, ix order
+        candidates = self._candidates(has)                # row-major: the reference's iz, ix order
 
         arglist = []
         bump = np.zeros_like(runs)
@@ -227,6 +419,15 @@ class PSIGridRefiner:
     def grid_arrays(self, grid):
         """Dense arrays of one grid: Kxgrid, Kzgrid, root_real, root_imag (depth = largest root
         multiplicity) and error (= number of roots per pixel)."""
+        store, runs = grid['results'], grid['runs']
+        if isinstance(store, RootStore):               # array form: no per-pixel Python
+            n = store.counts(runs)
+            depth = max(1, int(n.max()))
+            roots = np.where(np.arange(depth)[None, None, :] < n[:, :, None],
+                             store.mat[np.where(runs >= 0, runs, 0)][:, :, :depth], 0.0)
+            return {'Kxgrid': np.array(grid['Kx']), 'Kzgrid': np.array(grid['Kz']),
+                    'root_real': roots.real.copy(), 'root_imag': roots.imag.copy(),
+                    'error': np.where(runs >= 0, n, 0).astype(int)}
         depth = max([1] + [len(grid['results'][r]) for r in grid['runs'].ravel() if r >= 0])
         shape = list(grid['runs'].shape) + [depth]
         re, im = np.zeros(shape), np.zeros(shape)

@@ -177,6 +177,64 @@ class MpiScheduler:
         st["function_calls"] = int(np.sum(ncalls))
         return (roots, nr), st
 
+    def run_arrays(self, init, kx, kz, seeds, guesses=None, alpha=0.0):
+        """Array form of ``run_all`` for campaigns whose items share one '__init__' dict (grid refinement):
+        per-item wave numbers, seeds and -- as the CSR pair (flat values, n+1 offsets) -- guess roots in,
+        (root matrix (n, R), root counts (n,)) of ALL items out on every rank.  Same sharding, engine and
+        exchange as ``run_all``; no per-item Python objects.  Returns None when the batch needs the
+        general path (verbose PSIMode, python engine)."""
+        t0 = time.time()
+        if self.engine == "python":
+            return None
+        pm = self._cache.get(init)
+        ctx = pm.psi_dispersion.ctx
+        if pm.verbose_flag or not hasattr(ctx, "mode_batch"):
+            return None
+        pm._sync_cfg()
+        n = len(kx)
+        lo, step = _dist.rank(), _dist.world_size()
+        mine = np.arange(lo, n, step)
+        kx, kz = np.asarray(kx, dtype=float)[mine], np.asarray(kz, dtype=float)[mine]
+        seeds = np.broadcast_to(np.asarray(seeds, dtype=np.int64), (n,))[mine]
+        al = np.broadcast_to(np.asarray(alpha, dtype=float), (n,))[mine]
+        gl = None
+        if guesses is not None and len(guesses[0]):
+            flat, off = np.asarray(guesses[0], dtype=np.complex128), np.asarray(guesses[1], dtype=np.int64)
+            length = (off[1:] - off[:-1])[mine]
+            myoff = np.zeros(len(mine) + 1, dtype=np.int64)
+            np.cumsum(length, out=myoff[1:])
+            take = np.repeat(off[:-1][mine] - myoff[:-1], length) + np.arange(myoff[-1])
+            gl = (flat[take], myoff)
+        device = self.engine == "device"
+        cfg = pm.cfg
+        most = cfg.n_sample*(1 + (int(np.max(gl[1][1:] - gl[1][:-1])) if gl is not None and len(mine) else 0)
+                             + 4*cfg.max_zoom_level)
+        if device and most > 512:
+            import warnings
+            warnings.warn("a search of this batch can reach %d samples (> 512, the capacity of the "
+                          "device AAA): running the batch with engine='native'" % most)
+            device = False
+        dom = np.tile(np.array([pm.domain.xmin, pm.domain.xmax, pm.domain.ymin, pm.domain.ymax], dtype=float),
+                      (len(mine), 1))
+        if len(mine):
+            (roots, nr), ncalls, st = ctx.mode_batch(
+                np.full(len(mine), pm.psi_dispersion.dist_id, dtype=np.int32), kx, kz, al, dom, cfg.n_sample,
+                cfg.max_zoom_level, cfg.max_secant_iterations, cfg.tol, cfg.clean_tol, seeds, gl,
+                device_aaa=device, dense=True)
+        else:
+            roots, nr, ncalls, st = np.zeros((0, 1), np.complex128), np.zeros(0, np.int64), np.zeros(0), {}
+        self.last_stats = dict(items=len(mine), passes=st.get("passes", 0), function_calls=int(np.sum(ncalls)),
+                               evals=st.get("evals", 0), seconds=time.time() - t0,
+                               host_logic_seconds=st.get("logic_s"), device_seconds=st.get("eval_s"),
+                               launches=st.get("launches"), polish_evals=st.get("polish_evals"),
+                               stage_s=st.get("stage_s"), engine=self.engine)
+        idx, mat, cnt = _dist.all_gather_dense(mine, roots, nr)
+        out = np.zeros((n, mat.shape[1]), dtype=np.complex128)
+        out_n = np.zeros(n, dtype=np.int64)
+        out[idx] = mat
+        out_n[idx] = cnt
+        return out, out_n
+
     def run_all(self, arglist):
         """Results of every item, on every rank."""
         t0 = time.time()

@@ -23,6 +23,8 @@ struct WarpOne {
     static double sum(double v) { return v; }
     static double max(double v) { return v; }
     static void sync() {}
+    static unsigned ballot(bool p) { return p ? 1u : 0u; }
+    static int popc(unsigned v) { return __builtin_popcount(v); }
     static void sum4c(double (&)[4], double (&)[4]) {}
     static bool any(bool p) { return p; }
     static void argmax(double&, int&) {}

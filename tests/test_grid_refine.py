@@ -122,3 +122,58 @@ def test_spreadgrid_and_prune():
     assert len(prune_eps(vals, 1e-5)) == 2 and prune_eps([], 1e-5) == []
     with pytest.raises(ValueError):
         spreadgrid(kx, const_axis=2)
+
+
+def test_root_store_behaves_like_the_dict():
+    from psitools_public_b200.psi_grid_refine import RootStore
+    d = {0: np.array([1 + 2j]), 3: np.array([]), 7: np.array([1j, 2j, 3j])}
+    st = RootStore(d, width=1)
+    assert list(st) == [0, 3, 7] and max(st) == 7 == st.max_key and len(st) == 3 and 3 in st and 4 not in st
+    assert all(np.array_equal(st[k], d[k]) for k in d)
+    with pytest.raises(KeyError):
+        st[4]
+    st[3] = np.append(st[3], [5j])
+    st[12] = [1.0]
+    assert np.array_equal(st[3], [5j]) and st.max_key == 12
+    assert np.array_equal(st.counts(np.array([[0, -1], [7, 12]])), [[1, 0], [3, 1]])
+    with pytest.raises(KeyError):
+        st.counts(np.array([5]))
+    cp = st.copy()
+    cp[0] = []
+    assert len(st[0]) == 1 and len(cp[0]) == 0
+
+
+def test_array_sweep_equals_dict_sweep(backend):
+    """PSIGridRefiner's array path (RootStore + MpiScheduler.run_arrays, used with the stock scheduler)
+    against the dict path that mirrors the reference line by line (used with any other scheduler): same
+    run grids, same run ids, same roots, same sweep history -- including reruns, whose roots are appended
+    to the first run of the pixel, and the reference's re-use of the largest run id."""
+    from psitools_public_b200 import PSIGridRefiner, TanhSinhNoDeepCopy, psi_mode_mpi
+    base = {'__init__': {'stokes_range': [1e-8, 1.0], 'dust_to_gas_ratio': 3.0, 'real_range': [-2.0, 2.0],
+                         'imag_range': [1e-8, 1.0], 'n_sample': 20, 'max_zoom_domains': 1, 'tol': 1.0e-13,
+                         'clean_tol': 1e-4, 'tanhsinh_integrator': TanhSinhNoDeepCopy()},
+            'calculate': {'wave_number_x': None, 'wave_number_z': None, 'guess_roots': []},
+            'random_seed': 2}
+
+    class Wrapped(psi_mode_mpi.MpiScheduler):          # any subclass takes the dict path
+        def run_all(self, arglist):
+            return super().run_all(arglist)
+
+    out = []
+    for cls in (psi_mode_mpi.MpiScheduler, Wrapped):
+        gr = PSIGridRefiner('x', baseargs=base, nbase=(3, 3), reruns=1, krange=(1.0, 1.6),
+                            scheduler=cls(time.time(), 1e9, verbose=False))
+        assert gr._array_path() == (cls is psi_mode_mpi.MpiScheduler)
+        gr.run_basegrid()
+        gr.fill_in_grid()
+        out.append(gr)
+    a, b = out
+    assert a.sweep_log == b.sweep_log and len(a.sweep_log) >= 3
+    assert sum(n for _, n, _ in a.sweep_log) > 0
+    for ga, gb in zip(a.grids, b.grids):
+        assert np.array_equal(ga['runs'], gb['runs']) and np.array_equal(ga['nguess'], gb['nguess'])
+        assert list(ga['results']) == sorted(gb['results'])
+        for k in gb['results']:
+            assert np.array_equal(ga['results'][k], gb['results'][k]), k
+        arr_a, arr_b = a.grid_arrays(ga), b.grid_arrays(gb)
+        assert all(np.array_equal(arr_a[k], arr_b[k]) for k in arr_b)
