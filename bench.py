@@ -121,7 +121,7 @@ def run_reference(args):
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -426,7 +426,7 @@ def run_b200(args):
                         "h2d_bytes_per_step": 16*n + 28, "d2h_bytes_per_step": 16*n + 8},
                 "gpu_launches": int(launches_all), "roofline": roof, "cpu_baseline": cpu,
                 "clocks": clocks, "modes": modes}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -443,10 +443,28 @@ def main():
     ap.add_argument("--modes-grid", type=int, default=256,
                     help="axis length of the secondary PSIMode map (0 = skip)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record: everything else a library prints there while the
+    # benchmark runs (NCCL's version banner, for one) is sent to stderr
+    sys.stdout.flush()
+    global _RESULT_FD
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    text = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(text.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text)
 
 
 if __name__ == "__main__":

@@ -251,8 +251,12 @@ class MpiScheduler:
                                        polish_evals=st.get("polish_evals"), stage_s=st.get("stage_s"),
                                        engine=self.engine)
                 idx, mat, cnt = _dist.all_gather_dense(mine, roots, nr)
-                order = np.argsort(idx, kind="stable")
-                res = {int(idx[k]): mat[k, :cnt[k]].copy() for k in order}
+                # {index: roots}: root-less items (the majority on a map) share one read-only empty array
+                none = np.zeros(0, dtype=np.complex128)
+                none.flags.writeable = False
+                res = dict.fromkeys(range(len(arglist)), none)
+                for k in np.flatnonzero(cnt > 0).tolist():
+                    res[int(idx[k])] = mat[k, :cnt[k]].copy()
                 if self.verbose:
                     for i in mine:
                         print(i, 'result ', res[i])
