@@ -36,6 +36,21 @@ def main():
     out["disp"] = {str(k): [complex(v).real, complex(v).imag] for k, v in dv.items()}
     c = complex_roots_mpi.MpiScheduler(time.time(), 3600, verbose=False).run_all(count_arglist(ts)[:4])
     out["counts"] = {str(k): v for k, v in c.items()}
+    # grid refinement through the array path (MpiScheduler.run_arrays: rank-strided slices of the item
+    # arrays and of the CSR guess lists, dense all-gather, replicated RootStore on every rank)
+    from psitools_public_b200 import PSIGridRefiner
+    base = {'__init__': {'stokes_range': [1e-8, 1.0], 'dust_to_gas_ratio': 3.0, 'real_range': [-2.0, 2.0],
+                         'imag_range': [1e-8, 1.0], 'n_sample': 20, 'max_zoom_domains': 1, 'tol': 1.0e-13,
+                         'clean_tol': 1e-4, 'tanhsinh_integrator': ts},
+            'calculate': {'wave_number_x': None, 'wave_number_z': None, 'guess_roots': []}, 'random_seed': 2}
+    gr = PSIGridRefiner('x', baseargs=base, nbase=(3, 3), reruns=1, krange=(1.0, 1.6),
+                        scheduler=psi_mode_mpi.MpiScheduler(time.time(), 3600, verbose=False))
+    assert gr._array_path()
+    gr.run_basegrid()
+    gr.fill_in_grid()
+    g = gr.grids[-1]
+    out["refine"] = {"log": [list(x) for x in gr.sweep_log], "runs": g['runs'].tolist(),
+                     "roots": {str(k): [[z.real, z.imag] for z in g['results'][k]] for k in g['results']}}
     with open(os.path.join(sys.argv[1], "rank%d.json" % _dist.rank()), "w") as fh:
         json.dump(out, fh)
     dist.barrier()

@@ -177,3 +177,58 @@ def test_array_sweep_equals_dict_sweep(backend):
             assert np.array_equal(ga['results'][k], gb['results'][k]), k
         arr_a, arr_b = a.grid_arrays(ga), b.grid_arrays(gb)
         assert all(np.array_equal(arr_a[k], arr_b[k]) for k in arr_b)
+
+
+@pytest.mark.gpu
+def test_config4_family_on_gpu(built):
+    """BASELINE config 4 family at a size the GPU does in seconds: PowerBump, nbase 16, reruns 3, two
+    fill-ins (69 x 69 map, ~15 k PSIMode runs).  (1) the array path and the dict path (the line-by-line
+    mirror of the reference) give identical run grids, run ids and roots; (2) every root of the final map
+    is a root of the exact dispersion relation (|D(w)| << |D(w+1e-6) - D(w)|, one K1 batch); (3) refinement
+    only ever adds roots: every pixel of the base grid that had roots keeps them in the refined grid."""
+    from psitools_public_b200 import (PowerBump, PSIGridRefiner, PSIMode, SizeDensity, TanhSinhNoDeepCopy,
+                                      psi_mode_mpi)
+    from psitools_public_b200.psi_grid_refine import RootStore
+    ts = TanhSinhNoDeepCopy()
+    pb = PowerBump(amin=1e-8, aP=0.1, aL=2.0/3.0*0.1, aR=0.156, bumpfac=2.0)
+    sd = SizeDensity(pb.sigma0, [1e-8, 0.156])
+    sd.poles = [pb.get_discontinuity()]
+    base = {'__init__': {'stokes_range': [1e-8, 0.156], 'dust_to_gas_ratio': 10.0, 'size_density': sd,
+                         'real_range': [-2.0, 2.0], 'imag_range': [1e-7, 1.0], 'n_sample': 20,
+                         'max_zoom_domains': 1, 'tol': 1.0e-13, 'clean_tol': 1e-4, 'tanhsinh_integrator': ts},
+            'calculate': {'wave_number_x': None, 'wave_number_z': None, 'guess_roots': []}, 'random_seed': 2}
+
+    class Wrapped(psi_mode_mpi.MpiScheduler):
+        def run_all(self, arglist):
+            return super().run_all(arglist)
+
+    out = []
+    for cls in (psi_mode_mpi.MpiScheduler, Wrapped):
+        gr = PSIGridRefiner('x', baseargs=base, nbase=(16, 16), reruns=3,
+                            scheduler=cls(time.time(), 1e9, verbose=False))
+        gr.run_basegrid()
+        gr.fill_in_grid()
+        gr.fill_in_grid()
+        out.append(gr)
+    a, b = out
+    assert isinstance(a.grids[-1]['results'], RootStore) and isinstance(b.grids[-1]['results'], dict)
+    assert a.sweep_log == b.sweep_log and sum(n for _, n, _ in a.sweep_log) > 10000
+    for ga, gb in zip(a.grids, b.grids):
+        assert np.array_equal(ga['runs'], gb['runs']) and np.array_equal(ga['nguess'], gb['nguess'])
+        assert list(ga['results']) == sorted(gb['results'])
+        assert all(np.array_equal(ga['results'][k], gb['results'][k]) for k in gb['results'])
+    g = a.grids[-1]                                                                      # (2)
+    arr = a.grid_arrays(g)
+    n = arr['error']
+    iz, ix, k = np.nonzero(np.arange(arr['root_real'].shape[2])[None, None, :] < n[:, :, None])
+    w = arr['root_real'][iz, ix, k] + 1j*arr['root_imag'][iz, ix, k]
+    assert len(w) > 3000
+    pm = PSIMode(**base['__init__'])
+    ctx, did = pm.psi_dispersion.ctx, pm.psi_dispersion.dist_id
+    kx, kz = g['Kx'][iz, ix], g['Kz'][iz, ix]
+    dist = np.full(len(w), did, np.int32)
+    d0 = ctx.disp_eval(dist, kx, kz, np.zeros(len(w)), w)
+    d1 = ctx.disp_eval(dist, kx, kz, np.zeros(len(w)), w + 1e-6)
+    assert np.all(np.abs(d0) < 1e-3*np.abs(d1 - d0)), np.max(np.abs(d0)/np.abs(d1 - d0))
+    first = a.grid_arrays(a.grids[0])['error']                                           # (3)
+    assert np.all(n[::4, ::4][first > 0] > 0)

@@ -34,3 +34,32 @@ def test_two_rank_sharding(tmp_path, built):
         assert [o["counts"][str(i)] for i in range(4)] == [0, 0, 0, 1]
         np.testing.assert_allclose(o["disp"]["0"], [-1.72733464670814e+08, 5.32484293672187e+07], rtol=1e-7)
     assert outs[0]["mode"] == outs[1]["mode"]
+    # the refinement campaign: identical on both ranks and identical to a single-rank run
+    assert outs[0]["refine"] == outs[1]["refine"]
+    assert outs[0]["refine"]["log"] == [[0, 12, 0], [1, 24, 22], [1, 24, 0]]
+    single = _single_rank_refine()
+    assert outs[0]["refine"]["runs"] == single["runs"]
+    assert outs[0]["refine"]["roots"] == single["roots"]
+
+
+def _single_rank_refine():
+    import time
+    import hostsim_util as hs
+    from psitools_public_b200 import _device, PSIGridRefiner, TanhSinhNoDeepCopy, psi_mode_mpi
+    cache, saved = {}, _device.get_context
+    _device.get_context = lambda integ, device=None: cache.setdefault("c", hs.HostsimContext(integ))
+    try:
+        base = {'__init__': {'stokes_range': [1e-8, 1.0], 'dust_to_gas_ratio': 3.0, 'real_range': [-2.0, 2.0],
+                             'imag_range': [1e-8, 1.0], 'n_sample': 20, 'max_zoom_domains': 1, 'tol': 1.0e-13,
+                             'clean_tol': 1e-4, 'tanhsinh_integrator': TanhSinhNoDeepCopy()},
+                'calculate': {'wave_number_x': None, 'wave_number_z': None, 'guess_roots': []},
+                'random_seed': 2}
+        gr = PSIGridRefiner('x', baseargs=base, nbase=(3, 3), reruns=1, krange=(1.0, 1.6),
+                            scheduler=psi_mode_mpi.MpiScheduler(time.time(), 3600, verbose=False))
+        gr.run_basegrid()
+        gr.fill_in_grid()
+        g = gr.grids[-1]
+        return {"runs": g['runs'].tolist(),
+                "roots": {str(k): [[z.real, z.imag] for z in g['results'][k]] for k in g['results']}}
+    finally:
+        _device.get_context = saved
