@@ -11,6 +11,9 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+
 
 def count_map(n_axis):
     """example_psicountgrid.py family: roots of D inside [-2,2]x[2e-7,2] on an n_axis^2 log K grid."""
@@ -51,6 +54,20 @@ def refine(nbase, fills, reruns):
                 'calculate': {'wave_number_x': None, 'wave_number_z': None, 'guess_roots': []},
                 'random_seed': 2}
     gr = PSIGridRefiner('bench', baseargs=baseargs, nbase=(nbase, nbase), reruns=reruns, krange=(-1, 3))
+    sched = {"s": 0.0}
+    inner = gr.ms.run_arrays                      # time spent inside the scheduler (device + exchange)
+
+    def timed(*a, **k):
+        t = time.perf_counter()
+        out = inner(*a, **k)
+        sched["s"] += time.perf_counter() - t
+        st = gr.ms.last_stats
+        for key in ("prep_seconds", "batch_seconds", "exchange_seconds"):
+            sched[key] = sched.get(key, 0.0) + (st.get(key) or 0.0)
+        for key, v in (st.get("stage_s") or {}).items():
+            sched["dev_" + key] = sched.get("dev_" + key, 0.0) + v
+        return out
+    gr.ms.run_arrays = timed
     t0 = time.perf_counter()
     gr.run_basegrid()
     times = [time.perf_counter() - t0]
@@ -59,12 +76,15 @@ def refine(nbase, fills, reruns):
         times.append(time.perf_counter() - t0)
     g = gr.grids[-1]
     runs = sum(n for _, n, _ in gr.sweep_log) + gr.grids[0]['runs'].size
-    with_roots = int(sum(len(g['results'][r]) > 0 for r in g['runs'].ravel() if r >= 0))
-    print(json.dumps({"workload": "PSIGridRefiner PowerBump nbase=%d, %d fill-ins, reruns=%d -> %dx%d map"
-                                  % (nbase, fills, reruns, g['runs'].shape[0], g['runs'].shape[1]),
-                      "seconds_cumulative": times, "psimode_runs": int(runs),
-                      "runs_per_s": runs/times[-1], "sweeps": len(gr.sweep_log),
-                      "pixels_with_roots": with_roots}), flush=True)
+    with_roots = int(np.count_nonzero(gr.grid_arrays(g)['error'] > 0))
+    if RANK == 0:
+        print(json.dumps({"workload": "PSIGridRefiner PowerBump nbase=%d, %d fill-ins, reruns=%d -> %dx%d map"
+                                      % (nbase, fills, reruns, g['runs'].shape[0], g['runs'].shape[1]),
+                          "n_gpus": WORLD, "seconds_cumulative": times, "psimode_runs": int(runs),
+                          "runs_per_s": runs/times[-1], "sweeps": len(gr.sweep_log),
+                          "seconds_in_scheduler": sched["s"], "seconds_host_bookkeeping": times[-1] - sched["s"],
+                          "scheduler_split": {k: round(v, 3) for k, v in sched.items() if k != "s"},
+                          "pixels_with_roots": with_roots}), flush=True)
 
 
 def sweep(n_mu, n_tau, n_axis, level):
@@ -102,9 +122,18 @@ if __name__ == "__main__":
     ap.add_argument("--reruns", type=int, default=3)
     ap.add_argument("--sweep", type=int, nargs=4, metavar=("N_MU", "N_TAU", "N_AXIS", "LEVEL"), default=None)
     a = ap.parse_args()
+    if WORLD > 1:                                  # torchrun: one rank per GPU, NCCL for the exchanges
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+        os.dup2(2, 1) if RANK else None            # only rank 0 reports
     if a.sweep:
         sweep(*a.sweep)
     if a.count_grid > 0:
         count_map(a.count_grid)
     if a.nbase > 0:
         refine(a.nbase, a.fills, a.reruns)
+    if WORLD > 1:
+        dist.barrier()
+        dist.destroy_process_group()

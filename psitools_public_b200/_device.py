@@ -153,6 +153,61 @@ class EngineAPI:
 
     def mode_batch(self, dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
                    seeds, guesses, max_roots=8, device_aaa=False, dense=False):
+        """``_mode_batch`` in chunks: the K4 pipeline keeps every search's samples and work lists resident
+        (~50 B per sample slot), so a multi-million-item batch with guess domains is cut into pieces that
+        fit ``PSI_B200_BATCH_BYTES`` (default 48 GiB of the 180 GB).  Items are independent: results do not
+        depend on the cut."""
+        n = len(dist)
+        ns = np.broadcast_to(np.asarray(n_sample, dtype=np.int64), (n,))
+        mz = np.broadcast_to(np.asarray(max_zoom, dtype=np.int64), (n,))
+        if guesses is None:
+            goff = np.zeros(n + 1, dtype=np.int64)
+        elif isinstance(guesses, tuple):
+            goff = np.asarray(guesses[1], dtype=np.int64)
+        else:
+            goff = np.concatenate(([0], np.cumsum([len(g) for g in guesses]))).astype(np.int64)
+        ng = goff[1:] - goff[:-1]
+        cap = int(np.max(ns*(1 + ng + 4*mz))) if n else 0
+        per_item = 50*cap + 8*int(np.max(ns*np.maximum(1 + ng, 4))) + 16*max_roots + 256 if n else 1
+        budget = int(os.environ.get("PSI_B200_BATCH_BYTES", str(48 << 30)))
+        chunk = max(1, budget//per_item)
+        if not device_aaa or n <= chunk:
+            return self._mode_batch(dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol,
+                                    clean_tol, seeds, guesses, max_roots, device_aaa, dense)
+        per = lambda a, lo, hi: np.broadcast_to(np.asarray(a), (n,) + np.shape(a)[1:])[lo:hi]
+        domain = np.asarray(domain, dtype=float).reshape(n, 4)
+        if guesses is not None and not isinstance(guesses, tuple):
+            guesses = (np.array([complex(z) for g in guesses for z in g], dtype=np.complex128), goff)
+        parts = []
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            g = None if guesses is None else (guesses[0][goff[lo]:goff[hi]], goff[lo:hi + 1] - goff[lo])
+            parts.append(self._mode_batch(per(dist, lo, hi), per(kx, lo, hi), per(kz, lo, hi), per(alpha, lo, hi),
+                                          domain[lo:hi], per(n_sample, lo, hi), per(max_zoom, lo, hi),
+                                          per(max_secant, lo, hi), per(tol, lo, hi), per(clean_tol, lo, hi),
+                                          per(seeds, lo, hi), g, max_roots, device_aaa, True))
+        width = max(p[0][0].shape[1] for p in parts)
+        roots = np.zeros((n, width), dtype=np.complex128)
+        at = 0
+        for (r, _), _, _ in parts:
+            roots[at:at + len(r), :r.shape[1]] = r
+            at += len(r)
+        nr = np.concatenate([p[0][1] for p in parts])
+        nc = np.concatenate([p[1] for p in parts])
+        st = dict(parts[0][2])
+        for p in parts[1:]:
+            for k, v in p[2].items():
+                if isinstance(v, dict):
+                    st[k] = {kk: st[k][kk] + vv for kk, vv in v.items()}
+                elif k != "passes":
+                    st[k] = st[k] + v
+        st["chunks"] = len(parts)
+        if dense:
+            return (roots, nr), nc, st
+        return [roots[i, :nr[i]].copy() for i in range(n)], nc, st
+
+    def _mode_batch(self, dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
+                    seeds, guesses, max_roots=8, device_aaa=False, dense=False):
         """Run len(dist) PSIMode.calculate searches.  Per-item arrays; ``guesses`` is a list of
         complex sequences or the CSR pair (flat values, n+1 offsets).  ``device_aaa=False``: native lock-step engine (AAA with LAPACK on the host
         cores, D and the secant polish on the GPU); ``True``: kernel K4, everything on the device.

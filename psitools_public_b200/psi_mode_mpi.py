@@ -216,6 +216,7 @@ class MpiScheduler:
             device = False
         dom = np.tile(np.array([pm.domain.xmin, pm.domain.xmax, pm.domain.ymin, pm.domain.ymax], dtype=float),
                       (len(mine), 1))
+        t1 = time.time()
         if len(mine):
             (roots, nr), ncalls, st = ctx.mode_batch(
                 np.full(len(mine), pm.psi_dispersion.dist_id, dtype=np.int32), kx, kz, al, dom, cfg.n_sample,
@@ -223,8 +224,10 @@ class MpiScheduler:
                 device_aaa=device, dense=True)
         else:
             roots, nr, ncalls, st = np.zeros((0, 1), np.complex128), np.zeros(0, np.int64), np.zeros(0), {}
+        t2 = time.time()
         self.last_stats = dict(items=len(mine), passes=st.get("passes", 0), function_calls=int(np.sum(ncalls)),
-                               evals=st.get("evals", 0), seconds=time.time() - t0,
+                               evals=st.get("evals", 0), seconds=time.time() - t0, prep_seconds=t1 - t0,
+                               batch_seconds=t2 - t1,
                                host_logic_seconds=st.get("logic_s"), device_seconds=st.get("eval_s"),
                                launches=st.get("launches"), polish_evals=st.get("polish_evals"),
                                stage_s=st.get("stage_s"), engine=self.engine)
@@ -233,6 +236,7 @@ class MpiScheduler:
         out_n = np.zeros(n, dtype=np.int64)
         out[idx] = mat
         out_n[idx] = cnt
+        self.last_stats["exchange_seconds"] = time.time() - t2
         return out, out_n
 
     def run_all(self, arglist):

@@ -213,3 +213,24 @@ def test_device_vs_lapack_engine_other_distributions(built):
                 assert len(big) - len(small) <= 1, (i, a, b)
                 assert all(any(abs(x - y) <= 1e-8*abs(y) for x in big) for y in small), (i, a, b)
         assert differ <= 0.005*N, differ
+
+
+def test_mode_batch_chunking_is_invisible(backend, monkeypatch):
+    """Ctx.mode_batch cuts batches that would not fit the device budget into pieces; items are independent,
+    so the result must not depend on the cut (here: a budget that forces three pieces, with guess lists
+    in CSR form, against the uncut call)."""
+    from psitools_public_b200 import PSIMode, TanhSinhNoDeepCopy
+    pm = PSIMode(3.0, [1e-8, 1e-2], [-2, 2], [1e-8, 1.0], tanhsinh_integrator=TanhSinhNoDeepCopy())
+    ctx, did = pm.psi_dispersion.ctx, pm.psi_dispersion.dist_id
+    kx = np.array([10.0, 10.0, 30.0, 10.0, 3.0])
+    kz = np.array([1000.0, 100.0, 300.0, 1000.0, 30.0])
+    guesses = (np.array([-1.0 + 1e-5j, 0.5 + 0.1j, -1.0 + 2e-5j]), np.array([0, 1, 1, 3, 3, 3]))
+    call = lambda: ctx.mode_batch([did]*5, kx, kz, np.zeros(5), [[-2, 2, 1e-8, 1.0]]*5, 20, 1, 100, 1e-13,
+                                  1e-4, [0, 1, 2, 0, 1], guesses, device_aaa=True, dense=True)
+    (r0, n0), c0, s0 = call()
+    monkeypatch.setenv("PSI_B200_BATCH_BYTES", "17000")
+    (r1, n1), c1, s1 = call()
+    assert s1.get("chunks") == 3 and "chunks" not in s0
+    assert np.array_equal(n0, n1) and np.array_equal(c0, c1) and n0.sum() >= 2
+    assert all(np.array_equal(r0[i, :n0[i]], r1[i, :n1[i]]) for i in range(5))
+    assert s0["evals"] == s1["evals"]
