@@ -164,6 +164,27 @@ int psi_polish_batch_host(psi_ctx* ctx, int n_items, const int* dist, const doub
  * runs a register-resident DFMA chain kernel `reps` times and returns the best TFLOP/s. */
 int psi_measure_fp64_peak(psi_ctx* ctx, int reps, double* tflops);
 
+/* ---- grid refinement (csrc/psi_refine.cu): the cell queue of PSIGridRefiner.sweep_last_grid
+ * (psi_grid_refine.py:218-290) built on the device from a mirror of the root map.
+ *   runs    : nz*nx run id per pixel (-1 = never run), row-major [iz][ix]
+ *   nguess  : nz*nx number of guesses the pixel was last run with
+ *   cnt/mat : per run id 0..n_keys-1 the number of roots (-1 = no such run) and `width` complex root slots
+ *   key_capacity >= n_keys: room for run ids added by psi_refine_update
+ * psi_refine_sweep decides for every root-less pixel that touches a pixel with roots whether it runs (more
+ * pruned neighbour roots than nguess) and returns the number of running pixels and of their guesses
+ * (n_run = -1: a pixel collected more than 128 neighbour roots, nothing was changed, sweep on the host);
+ * psi_refine_fetch writes the compact row-major work list {pixel index, guess count, guesses} (and makes
+ * the guess count the pixel's new nguess); psi_refine_update stores the roots of finished runs (`width`
+ * slots per changed run id) and re-points pixels to their new run ids. */
+typedef struct psi_refine psi_refine;
+int psi_refine_open(psi_refine** out, int device, int nz, int nx, const int* runs, const int* nguess,
+                    long long n_keys, long long key_capacity, int width, const double* mat, const int* cnt);
+int psi_refine_sweep(psi_refine* map, long long* n_run, long long* n_guess);
+int psi_refine_fetch(psi_refine* map, int* pix, int* n_kept, double* guesses);
+int psi_refine_update(psi_refine* map, long long n_changed, const long long* keys, const int* cnt,
+                      const double* rows, long long n_pix, const int* pix, const int* run_ids);
+void psi_refine_close(psi_refine* map);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,12 @@ _SIGNATURES = {
     "psi_mode_batch_device": (C.c_int, [_vp, C.c_int] + [_vp]*10 + [C.c_int] + [_vp]*5),
     "psi_contour_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*13),
     "psi_polish_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*12),
+    "psi_refine_open": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_longlong,
+                                  C.c_longlong, C.c_int, _vp, _vp]),
+    "psi_refine_sweep": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "psi_refine_fetch": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "psi_refine_update": (C.c_int, [_vp, C.c_longlong, _vp, _vp, _vp, C.c_longlong, _vp, _vp]),
+    "psi_refine_close": (None, [_vp]),
 }
 
 
@@ -320,6 +326,62 @@ class EngineAPI:
 
     def _last_error(self):
         return load_library().psi_last_error().decode()
+
+
+class RefineMap:
+    """Device mirror of a PSIGridRefiner grid (run ids, nguess, RootStore) and its sweep kernels
+    (csrc/psi_refine.cu).  ``sweep()`` returns the pixels that run next with their pruned guesses;
+    ``update()`` stores the finished runs."""
+
+    def __init__(self, device, runs, nguess, store_mat, store_cnt, key_capacity):
+        self.lib = load_library()
+        self.shape = runs.shape
+        self.width = int(store_mat.shape[1])
+        self.key_capacity = int(key_capacity)
+        n_keys = len(store_cnt)
+        runs32 = np.ascontiguousarray(runs, dtype=np.int32)
+        ng32 = np.ascontiguousarray(nguess, dtype=np.int32)
+        cnt32 = np.ascontiguousarray(store_cnt, dtype=np.int32)
+        mat = np.ascontiguousarray(store_mat, dtype=np.complex128)
+        h = _vp()
+        check(self.lib.psi_refine_open(C.byref(h), int(device), int(runs.shape[0]), int(runs.shape[1]),
+                                       _ptr(runs32), _ptr(ng32), n_keys, self.key_capacity, self.width,
+                                       _ptr(mat), _ptr(cnt32)), "psi_refine_open")
+        self.handle = h
+
+    def sweep(self):
+        """(iz, ix, guess counts, flat guesses) of the pixels that run, in row-major pixel order; None when a
+        pixel collects more neighbour roots than the kernel's buffer holds (nothing changed on the device)."""
+        n_run, n_guess = C.c_longlong(0), C.c_longlong(0)
+        check(self.lib.psi_refine_sweep(self.handle, C.byref(n_run), C.byref(n_guess)), "psi_refine_sweep")
+        if n_run.value < 0:
+            return None
+        pix = np.zeros(n_run.value, dtype=np.int32)
+        nk = np.zeros(n_run.value, dtype=np.int32)
+        g = np.zeros(max(1, n_guess.value), dtype=np.complex128)
+        check(self.lib.psi_refine_fetch(self.handle, _ptr(pix), _ptr(nk), _ptr(g)), "psi_refine_fetch")
+        return pix//self.shape[1], pix % self.shape[1], nk.astype(np.int64), g[:n_guess.value]
+
+    def update(self, keys, cnt, rows, iz, ix, run_ids):
+        keys = np.ascontiguousarray(keys, dtype=np.int64)
+        cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+        rows = np.ascontiguousarray(rows, dtype=np.complex128)
+        assert rows.shape == (len(keys), self.width)
+        pix = np.ascontiguousarray(np.asarray(iz)*self.shape[1] + np.asarray(ix), dtype=np.int32)
+        ids = np.ascontiguousarray(run_ids, dtype=np.int32)
+        check(self.lib.psi_refine_update(self.handle, len(keys), _ptr(keys), _ptr(cnt), _ptr(rows), len(pix),
+                                         _ptr(pix), _ptr(ids)), "psi_refine_update")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.psi_refine_close(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context(EngineAPI):

@@ -262,14 +262,10 @@ class PSIGridRefiner:
             touched[max(0, -diz):nz + min(0, -diz), max(0, -dix):nx + min(0, -dix)] |= src
         return np.argwhere(touched & ~has)
 
-    def _sweep_arrays(self, grid):
-        """sweep_last_grid on arrays: neighbour roots are gathered, pruned (prune_eps, same greedy order)
-        and compared with ``nguess`` for all candidate pixels at once, the runs go to the scheduler as
-        arrays (run_arrays) and their roots are merged into the RootStore by run id exactly as the
-        dict-based path does (first run of a pixel assigns, its reruns append)."""
-        kx_grid, kz_grid = grid['Kx'], grid['Kz']
+    def _queue_numpy(self, grid):
+        """Host form of the sweep's cell queue (the device form is csrc/psi_refine.cuh: refine_pixel): the
+        pixels that run this sweep (row-major), their guess counts and the guesses, flat; updates nguess."""
         runs, nguess, store = grid['runs'], grid['nguess'], grid['results']
-        offset = store.max_key
         nz, nx = runs.shape
         has = store.counts(runs) > 0
         cand = self._candidates(has)
@@ -313,6 +309,55 @@ class PSIGridRefiner:
         go = n_kept > nguess[cz, cx]
         cz, cx, kept, n_kept = cz[go], cx[go], kept[go], n_kept[go]
         nguess[cz, cx] = n_kept
+        flat = kept[np.arange(kept.shape[1])[None, :] < n_kept[:, None]]          # row-major: pixel by pixel
+        return cz, cx, n_kept, flat
+
+    def _close_device_map(self):
+        dev = self.__dict__.pop('_dev', None)
+        if dev is not None:
+            dev[1].close()
+
+    def _device_map(self, grid):
+        """RefineMap mirror of the last grid on this rank's GPU, opened lazily and re-opened when the
+        RootStore outgrew it; None when there is no device library behind the scheduler (CPU harness) or
+        ``device_sweep`` is off."""
+        if not getattr(self, 'device_sweep', True):
+            return None
+        from . import _device
+        ctx = self.ms._cache.get(self._shared_init(0)).psi_dispersion.ctx
+        store = grid['results']
+        if not isinstance(ctx, _device.Context):
+            return None
+        held = self.__dict__.get('_dev')
+        if held is not None and held[0] is grid and held[1].width == store.mat.shape[1]:
+            return held[1]
+        self._close_device_map()
+        n_keys = store.max_key + 1
+        capacity = n_keys + 2*(1 + self.reruns)*grid['runs'].size
+        dev = _device.RefineMap(ctx.device, grid['runs'], grid['nguess'], store.mat[:n_keys], store.cnt[:n_keys],
+                                capacity)
+        self._dev = (grid, dev)
+        return dev
+
+    def _sweep_arrays(self, grid):
+        """sweep_last_grid on arrays: neighbour roots are gathered, pruned (prune_eps, same greedy order)
+        and compared with ``nguess`` for all candidate pixels at once, the runs go to the scheduler as
+        arrays (run_arrays) and their roots are merged into the RootStore by run id exactly as the
+        dict-based path does (first run of a pixel assigns, its reruns append)."""
+        kx_grid, kz_grid = grid['Kx'], grid['Kz']
+        runs, nguess, store = grid['runs'], grid['nguess'], grid['results']
+        offset = store.max_key
+        nz, nx = runs.shape
+        dev = self._device_map(grid)
+        queue = dev.sweep() if dev is not None else None
+        if queue is not None:                     # the cell queue comes from the device mirror of the map
+            cz, cx, n_kept, flat_one = queue
+            nguess[cz, cx] = n_kept
+        else:
+            if dev is not None:                   # a pixel overflowed the kernel's neighbour buffer: this
+                self._close_device_map()          # sweep runs on the host, the mirror is rebuilt afterwards
+                dev = None
+            cz, cx, n_kept, flat_one = self._queue_numpy(grid)
         n_run, per = len(cz), 1 + self.reruns
         if self.root:
             print('Will run ', n_run*per, ' new points')
@@ -321,7 +366,6 @@ class PSIGridRefiner:
             first = np.arange(n_run)*per
             bump = np.zeros_like(runs)
             bump[cz, cx] = offset + first - runs[cz, cx]
-            flat_one = kept[np.arange(kept.shape[1])[None, :] < n_kept[:, None]]      # row-major: per pixel
             starts = np.zeros(n_run + 1, dtype=np.int64)
             np.cumsum(n_kept, out=starts[1:])
             # every pixel's guess list once per (re)run
@@ -351,6 +395,11 @@ class PSIGridRefiner:
             store.cnt[keys] = pos
             runs += bump
             store.counts(runs)                        # every pixel still maps to a stored run
+            if dev is not None:
+                if store.mat.shape[1] == dev.width and int(keys[-1]) < dev.key_capacity:
+                    dev.update(keys, store.cnt[keys], store.mat[keys], cz, cx, runs[cz, cx])
+                else:                                 # the map outgrew its mirror: re-opened next sweep
+                    self._close_device_map()
         self.sweep_log.append((len(self.grids) - 1, n_run*per, newroots))
         return newroots
 

@@ -12,6 +12,7 @@
 #define PSI_AAA_STATS 1
 
 #include "../../psitools_public_b200/csrc/psi_mode.cuh"
+#include "../../psitools_public_b200/csrc/psi_refine.cuh"
 #include "../../psitools_public_b200/csrc/psi_internal.hpp"
 #include "../../psitools_public_b200/csrc/psi_table.hpp"
 
@@ -149,6 +150,16 @@ int hs_aaa_fit(int M, const double* Z, const double* F, const int* mask, double*
     *resid = aaa_fit<WarpOne>(sc, st);
     for (int j = 0; j < st.m; ++j) { w_out[2 * j] = sc.w[j].re; w_out[2 * j + 1] = sc.w[j].im; }
     return st.m;
+}
+
+// the per-pixel sweep logic of csrc/psi_refine.cuh over a whole map: nk[p] = guesses pixel p runs with (0 = it
+// does not run), kept[p*128 ..] = those guesses
+void hs_refine_count(int nz, int nx, const int* runs, const int* nguess, int width, const double* mat,
+                     const int* cnt, int* nk, double* kept) {
+    RefineView g{nz, nx, width, runs, cnt, reinterpret_cast<const cx*>(mat), nguess};
+    std::vector<cx> near(kRefineMaxNear);
+    for (int p = 0; p < nz * nx; ++p)
+        nk[p] = refine_pixel(g, p / nx, p % nx, near.data(), reinterpret_cast<cx*>(kept) + (size_t)p * kRefineMaxNear);
 }
 
 void hs_aaa_stats(long long* out) { for (int i = 0; i < 8; ++i) { out[i] = g_aaa_stats[i]; g_aaa_stats[i] = 0; } }

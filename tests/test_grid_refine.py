@@ -182,8 +182,9 @@ def test_array_sweep_equals_dict_sweep(backend):
 @pytest.mark.gpu
 def test_config4_family_on_gpu(built):
     """BASELINE config 4 family at a size the GPU does in seconds: PowerBump, nbase 16, reruns 3, two
-    fill-ins (69 x 69 map, ~15 k PSIMode runs).  (1) the array path and the dict path (the line-by-line
-    mirror of the reference) give identical run grids, run ids and roots; (2) every root of the final map
+    fill-ins (69 x 69 map, ~15 k PSIMode runs).  (1) the array path with the cell queue built on the device
+    (csrc/psi_refine.cu), the array path with the numpy queue and the dict path (the line-by-line mirror of
+    the reference) give identical run grids, run ids and roots; (2) every root of the final map
     is a root of the exact dispersion relation (|D(w)| << |D(w+1e-6) - D(w)|, one K1 batch); (3) refinement
     only ever adds roots: every pixel of the base grid that had roots keeps them in the refined grid."""
     from psitools_public_b200 import (PowerBump, PSIGridRefiner, PSIMode, SizeDensity, TanhSinhNoDeepCopy,
@@ -203,14 +204,22 @@ def test_config4_family_on_gpu(built):
             return super().run_all(arglist)
 
     out = []
-    for cls in (psi_mode_mpi.MpiScheduler, Wrapped):
+    for cls, device_sweep in ((psi_mode_mpi.MpiScheduler, True), (Wrapped, False), (psi_mode_mpi.MpiScheduler, False)):
         gr = PSIGridRefiner('x', baseargs=base, nbase=(16, 16), reruns=3,
                             scheduler=cls(time.time(), 1e9, verbose=False))
+        gr.device_sweep = device_sweep
         gr.run_basegrid()
         gr.fill_in_grid()
         gr.fill_in_grid()
+        assert ('_dev' in gr.__dict__) == device_sweep       # the cell queue really came from the GPU
         out.append(gr)
-    a, b = out
+    a, b, c = out
+    # the numpy queue (device_sweep off) and the device queue give the same campaign
+    assert a.sweep_log == c.sweep_log
+    for ga, gc in zip(a.grids, c.grids):
+        assert np.array_equal(ga['runs'], gc['runs']) and np.array_equal(ga['nguess'], gc['nguess'])
+        assert list(ga['results']) == list(gc['results'])
+        assert all(np.array_equal(ga['results'][k], gc['results'][k]) for k in gc['results'])
     assert isinstance(a.grids[-1]['results'], RootStore) and isinstance(b.grids[-1]['results'], dict)
     assert a.sweep_log == b.sweep_log and sum(n for _, n, _ in a.sweep_log) > 10000
     for ga, gb in zip(a.grids, b.grids):
@@ -232,3 +241,42 @@ def test_config4_family_on_gpu(built):
     assert np.all(np.abs(d0) < 1e-3*np.abs(d1 - d0)), np.max(np.abs(d0)/np.abs(d1 - d0))
     first = a.grid_arrays(a.grids[0])['error']                                           # (3)
     assert np.all(n[::4, ::4][first > 0] > 0)
+
+
+@pytest.mark.parametrize("seed,width", [(0, 2), (1, 4), (2, 9), (3, 16)])
+def test_refine_pixel_logic_equals_numpy_queue(seed, width):
+    """csrc/psi_refine.cuh (the sweep's per-pixel device logic, run here by the CPU harness) against
+    PSIGridRefiner._queue_numpy on random root maps: same running pixels in the same order, same guess
+    counts, bit-identical guesses -- including epsilon = mean(Im)*1e-4, whose summation order follows
+    numpy's pairwise sum (more than eight neighbour roots occur for width >= 2)."""
+    import ctypes as C
+    import hostsim_util as hs
+    from psitools_public_b200.psi_grid_refine import PSIGridRefiner, RootStore
+    rng = np.random.RandomState(seed)
+    nz, nx = 23, 31
+    runs = np.where(rng.uniform(size=(nz, nx)) < 0.8, rng.permutation(nz*nx).reshape(nz, nx), -1)
+    store = RootStore(width=width)
+    blob = np.hypot(*np.meshgrid(np.arange(nx) - 12.0, np.arange(nz) - 9.0)) < 7.5
+    for key in np.unique(runs[runs >= 0]):
+        iz, ix = np.argwhere(runs == key)[0]
+        n = rng.randint(1, width + 1) if blob[iz, ix] and rng.uniform() < 0.8 else 0
+        base = 0.3 + 0.05j + 1e-3*(rng.normal() + 1j*abs(rng.normal()))
+        near = base*(1 + 1e-6*rng.normal(size=n)*(rng.uniform(size=n) < 0.5))       # some nearly equal roots
+        store[key] = near + (rng.uniform(size=n) < 0.3)*rng.normal(size=n)*0.1
+    nguess = rng.randint(0, 3, size=(nz, nx))
+    grid = {'runs': runs.copy(), 'nguess': nguess.copy(), 'results': store}
+    ref = PSIGridRefiner.__new__(PSIGridRefiner)
+    cz, cx, n_kept, flat = ref._queue_numpy(grid)
+    assert len(cz) > 20 and n_kept.max() > 8 - 6*(width == 2)
+    lib = hs.lib()
+    nk = np.zeros(nz*nx, dtype=np.int32)
+    kept = np.zeros((nz*nx, 128), dtype=np.complex128)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    runs32, ng32 = np.ascontiguousarray(runs, np.int32), np.ascontiguousarray(nguess, np.int32)
+    cnt32, mat = np.ascontiguousarray(store.cnt, np.int32), np.ascontiguousarray(store.mat)
+    lib.hs_refine_count(nz, nx, p(runs32), p(ng32), width, p(mat), p(cnt32), p(nk), p(kept))
+    run = np.flatnonzero(nk > 0)
+    assert np.array_equal(run, cz*nx + cx)
+    assert np.array_equal(nk[run], n_kept)
+    assert np.array_equal(np.concatenate([kept[q, :nk[q]] for q in run]), flat)
+    assert np.array_equal(grid['nguess'][cz, cx], n_kept)
