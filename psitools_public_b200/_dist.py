@@ -100,6 +100,39 @@ def all_gather_dense(idx, mat, cnt):
             allbuf[:, 1].astype(np.int64))
 
 
+def all_gather_ragged(cnt, flat):
+    """Per-rank ragged results: ``cnt`` (n_local,) values per local item, ``flat`` their concatenation
+    (complex128).  Returns the lists [cnt of rank 0, ...], [flat of rank 0, ...].  Three collectives: the two
+    lengths, the counts, the values -- only items that HAVE values cost bandwidth (on a growth-rate map most
+    searches return nothing)."""
+    td = _td()
+    cnt = np.ascontiguousarray(cnt, dtype=np.int64)
+    flat = np.ascontiguousarray(flat, dtype=np.complex128)
+    if td is None or td.get_world_size() == 1:
+        return [cnt], [flat]
+    import torch
+    dev = _device_for_collectives()
+    world = td.get_world_size()
+    sizes = torch.tensor([len(cnt), len(flat)], dtype=torch.int64, device=dev)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    td.all_gather(all_sizes, sizes)
+    all_sizes = [[int(v) for v in t.tolist()] for t in all_sizes]
+    n_max = max(a for a, _ in all_sizes)
+    f_max = max(b for _, b in all_sizes)
+    cbuf = np.zeros(max(n_max, 1), dtype=np.int64)
+    cbuf[:len(cnt)] = cnt
+    fbuf = np.zeros(2*max(f_max, 1))
+    fbuf[:2*len(flat)] = flat.view(np.float64)
+    mine_c, mine_f = torch.from_numpy(cbuf).to(dev), torch.from_numpy(fbuf).to(dev)
+    parts_c = [torch.empty_like(mine_c) for _ in range(world)]
+    parts_f = [torch.empty_like(mine_f) for _ in range(world)]
+    td.all_gather(parts_c, mine_c)
+    td.all_gather(parts_f, mine_f)
+    cnts = [p.cpu().numpy()[:a] for p, (a, _) in zip(parts_c, all_sizes)]
+    flats = [np.ascontiguousarray(p.cpu().numpy()[:2*b]).view(np.complex128) for p, (_, b) in zip(parts_f, all_sizes)]
+    return cnts, flats
+
+
 def barrier():
     td = _td()
     if td is not None:

@@ -231,11 +231,18 @@ class MpiScheduler:
                                host_logic_seconds=st.get("logic_s"), device_seconds=st.get("eval_s"),
                                launches=st.get("launches"), polish_evals=st.get("polish_evals"),
                                stage_s=st.get("stage_s"), engine=self.engine)
-        idx, mat, cnt = _dist.all_gather_dense(mine, roots, nr)
-        out = np.zeros((n, mat.shape[1]), dtype=np.complex128)
+        # exchange: per item a count, and the roots of the items that have any (rank q owns items q::world)
+        nr = np.asarray(nr, dtype=np.int64)
+        valid = np.arange(roots.shape[1])[None, :] < nr[:, None]
+        cnts, flats = _dist.all_gather_ragged(nr, roots[valid])
+        width = max([1] + [int(c.max()) for c in cnts if len(c)])
+        out = np.zeros((n, width), dtype=np.complex128)
         out_n = np.zeros(n, dtype=np.int64)
-        out[idx] = mat
-        out_n[idx] = cnt
+        for q, (c, f) in enumerate(zip(cnts, flats)):
+            out_n[q::step] = c
+            rows = np.repeat(np.arange(q, n, step), c)
+            cols = np.arange(len(f)) - np.repeat(np.cumsum(c) - c, c)
+            out[rows, cols] = f
         self.last_stats["exchange_seconds"] = time.time() - t2
         return out, out_n
 
