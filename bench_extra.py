@@ -127,6 +127,10 @@ if __name__ == "__main__":
         import torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
+        warm = torch.zeros(8, device="cuda")
+        dist.all_gather([torch.empty_like(warm) for _ in range(WORLD)], warm)    # communicator set-up is
+        dist.all_reduce(warm)                                                    # not part of any workload
+        torch.cuda.synchronize()
         os.dup2(2, 1) if RANK else None            # only rank 0 reports
     if a.sweep:
         sweep(*a.sweep)
