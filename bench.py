@@ -348,8 +348,10 @@ def run_b200(args):
                      'random_seed': 2} for a, b in zip(kxg.ravel(), kzg.ravel())]
 
         ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False)
-        ms.run_all(arglist(min(32, args.modes_grid)))            # warm-up (LAPACK binding, staging buffers)
         items = arglist(args.modes_grid)
+        ms.run_all(arglist(min(32, args.modes_grid)))            # warm-up: library binding, communicator,
+        ms.run_all(items)                                         # ... and one untimed pass (device buffers grow
+                                                                  # to the batch size on first use)
         barrier()
         l0 = ctx.launch_count
         t0 = time.perf_counter()
