@@ -11,6 +11,7 @@
 #include <string.h>
 #include <algorithm>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/psi_b200.h"
@@ -73,6 +74,49 @@ struct WarpCuda {
             if (oi >= 0 && (idx < 0 || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
         }
     }
+};
+
+// CTA policy: ALL threads of the block cooperate on one evaluation (the quadrature code only sees lane(),
+// width and the reductions).  Used by K3 when a launch has too few root searches to fill the GPU with one
+// warp each: a secant polish is a serial chain of D evaluations, and the slowest chain sets the launch time.
+// Reductions: butterfly inside each warp, one shared-memory slot per warp, one barrier, then every thread
+// adds the slots in the same order (all threads get bit-identical sums; two slot sets alternate so that one
+// barrier per reduction is enough).
+template <int THREADS>
+struct CtaCuda {
+    static constexpr int width = THREADS;
+    static constexpr int kWarps = THREADS / 32;
+    static __device__ __forceinline__ int lane() { return threadIdx.x; }
+    static __device__ __forceinline__ double* slots() {
+        __shared__ double s[2][kWarps];
+        return &s[0][0];
+    }
+    static __device__ __forceinline__ unsigned& phase() {
+        __shared__ unsigned ph[THREADS];      // per-thread toggle (threads stay in lock step through the barriers)
+        return ph[threadIdx.x];
+    }
+    template <class OP>
+    static __device__ __forceinline__ double reduce(double v, OP op) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+        unsigned& ph = phase();
+        double* s = slots() + (ph & 1u) * kWarps;
+        ph ^= 1u;
+        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double r = s[0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) r = op(r, s[w]);
+        return r;
+    }
+    static __device__ __forceinline__ double sum(double v) {
+        return reduce(v, [](double a, double b) { return a + b; });
+    }
+    static __device__ __forceinline__ double max(double v) {
+        return reduce(v, [](double a, double b) { return fmax(a, b); });
+    }
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+    static __device__ __forceinline__ bool any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -177,6 +221,16 @@ __device__ __forceinline__ NodeTableView stage_table(const NodeTableView& gt, bo
     return t;
 }
 
+// the same for a whole block (thread 0 pulls, everybody reads it after the barrier)
+__device__ __forceinline__ bool next_item_cta(unsigned long long* queue, long long n, long long& idx) {
+    __shared__ unsigned long long pulled;
+    __syncthreads();                                    // everybody is done with the previous item
+    if (threadIdx.x == 0) pulled = atomicAdd(queue, 1ull);
+    __syncthreads();
+    idx = (long long)pulled;
+    return pulled < (unsigned long long)n;
+}
+
 __device__ __forceinline__ bool next_item(unsigned long long* queue, long long n, long long& idx) {
     unsigned long long v = 0;
     if ((threadIdx.x & 31) == 0) v = atomicAdd(queue, 1ull);
@@ -250,7 +304,9 @@ enum ModePhase { kPhaseSample = 0, kPhaseAnalyze = 1, kPhasePolish = 2, kPhaseDe
 
 // K3 polish_kernel: one warp per root search; the whole two-stage secant polish of all its start
 // values runs on the device, every D evaluated inline (psi_batch.cuh, polish_run).
-template <int NK, bool VISC>
+// CTA = true: the whole block takes one root search at a time (every D evaluation spread over all its
+// threads, the scalar secant logic executed redundantly by all of them).
+template <int NK, bool VISC, bool CTA = false>
 __global__ void __launch_bounds__(kEvalThreads, 1)
 polish_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, int n_items,
               const int* __restrict__ pidx, const int* __restrict__ dist, const double* __restrict__ kx,
@@ -260,16 +316,18 @@ polish_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict_
               unsigned long long* queue, unsigned long long* counters, int stride, const int* __restrict__ cnt,
               const int* __restrict__ phase) {
     const NodeTableView t = stage_table(gt, table_in_smem != 0);
-    const int lane = threadIdx.x & 31;
+    const int lane = CTA ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+    if (CTA) CtaCuda<kEvalThreads>::phase() = 0u;
     unsigned long long nodes = 0, evals = 0;
     long long idx;
-    while (next_item(queue, n_items, idx)) {
+    while (CTA ? next_item_cta(queue, n_items, idx) : next_item(queue, n_items, idx)) {
         if (phase != nullptr && phase[idx] != kPhasePolish) continue;       // mode pipeline: not this item's turn
         const int pi = pidx != nullptr ? pidx[idx] : (int)idx;
         const DistParams& d = dists[dist[pi]];
         const double al = alpha[pi];
         if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
-        WarpEvalClass<WarpCuda, NK, VISC> f;
+        typedef typename std::conditional<CTA, CtaCuda<kEvalThreads>, WarpCuda>::type Policy;
+        WarpEvalClass<Policy, NK, VISC> f;
         f.t = &t; f.d = &d; f.kx = kx[pi]; f.kz = kz[pi]; f.alpha = al; f.nodes = 0; f.evals = 0;
         const RectDom rd{dom[4 * idx], dom[4 * idx + 1], dom[4 * idx + 2], dom[4 * idx + 3]};
         // start values: packed with offsets (batch API) or strided per item (mode pipeline)
@@ -395,7 +453,8 @@ __global__ void mode_sample_kernel(ModeDev m, int n_items, const double* __restr
 __global__ void __launch_bounds__(256, 3)
 mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, const int* __restrict__ iparams,
                     const double* __restrict__ dparams, const int* __restrict__ guess_off,
-                    unsigned char* scratch, size_t scratch_per_warp, unsigned long long* queue) {
+                    unsigned char* scratch, size_t scratch_per_warp, unsigned long long* queue,
+                    unsigned long long* n_polish) {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     AAAScratch sc = aaa_carve(scratch + (size_t)warp_global * scratch_per_warp, m.cap);
@@ -424,6 +483,7 @@ mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, c
                 for (int q = 0; q < plan.n_zoom; ++q) m.zoom[4 * (size_t)idx + q] = plan.zoom[q];
                 m.pcalls[idx] = 0; m.pconv[idx] = 0; m.pstat[idx] = 0;
                 m.phase[idx] = plan.n0 > 0 ? kPhasePolish : kPhaseDecide;
+                if (plan.n0 > 0) atomicAdd(n_polish, 1ull);
             }
         }
     }
@@ -462,9 +522,18 @@ __global__ void mode_decide_kernel(ModeDev m, int n_items, const double* __restr
 #define PSI_CLASS_TABLE(NAME)                                                                      \
     {NAME<0, false>, NAME<0, true>, NAME<1, false>, NAME<1, true>, NAME<2, false>, NAME<2, true>,    \
      NAME<3, false>, NAME<3, true>}
-typedef decltype(&polish_kernel<0, false>) polish_kernel_t;
+typedef decltype(&polish_kernel<0, false, false>) polish_kernel_t;
+#define PSI_CLASS_TABLE_CTA(NAME)                                                                          \
+    {NAME<0, false, true>, NAME<0, true, true>, NAME<1, false, true>, NAME<1, true, true>, NAME<2, false, true>, \
+     NAME<2, true, true>, NAME<3, false, true>, NAME<3, true, true>}
 typedef decltype(&contour_kernel<0, false>) contour_kernel_t;
 static const polish_kernel_t kPolishKernels[kNumClasses] = PSI_CLASS_TABLE(polish_kernel);
+static const polish_kernel_t kPolishKernelsCta[kNumClasses] = PSI_CLASS_TABLE_CTA(polish_kernel);
+// K3 takes one block per root search when a launch has at most this many searches (PSI_K3_CTA_ITEMS)
+static long long k3_cta_items() {
+    static const long long v = getenv("PSI_K3_CTA_ITEMS") ? atoll(getenv("PSI_K3_CTA_ITEMS")) : 4096;
+    return v;
+}
 static const contour_kernel_t kContourKernels[kNumClasses] = PSI_CLASS_TABLE(contour_kernel);
 
 // DFMA-pipe peak: 8 independent FMA chains per thread, all in registers.
@@ -523,13 +592,14 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
     CK(cudaMemcpy(c->d_nodes, lv.data(), sizeof(node_t) * n_nodes, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_level_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
     c->table_smem = sizeof(node_t) * (size_t)n_nodes + sizeof(int) * off.size();
-    c->table_in_smem = c->table_smem + 1024 <= (size_t)c->smem_optin;
+    c->table_in_smem = c->table_smem + 4096 <= (size_t)c->smem_optin;
     if (c->table_in_smem) {
         for (int cls = 0; cls < kNumClasses; ++cls)
             CK(cudaFuncSetAttribute(eval_kernel_for(cls), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)c->table_smem));
         for (int cls = 0; cls < kNumClasses; ++cls) {
             CK(cudaFuncSetAttribute(kPolishKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
+            CK(cudaFuncSetAttribute(kPolishKernelsCta[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
             CK(cudaFuncSetAttribute(kContourKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
         }
     }
@@ -777,7 +847,9 @@ int psi_internal_polish(psi_ctx* c, int n_items, const int* pidx, int n_params, 
     for (int cls = 0; cls < kNumClasses; ++cls) {
     if (!(mask & (1u << cls))) continue;
     CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
-    kPolishKernels[cls]<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+    const bool k3_cta = n_items <= k3_cta_items();
+    (k3_cta ? kPolishKernelsCta : kPolishKernels)[cls]<<<k3_cta ? std::min(c->sm_count, n_items) : grid, kEvalThreads,
+                                                         c->table_in_smem ? c->table_smem : 0, st>>>(
         t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, (const int*)d[0], (const int*)d[1],
         (const double*)d[2], (const double*)d[3], (const double*)d[4], (const double*)d[5], (const int*)d[6],
         (double2*)d[7], (const int*)d[8], (double2*)d[9], (int*)d[10], (int*)d[11], (int*)d[12], c->d_counter,
@@ -889,16 +961,25 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
                               mask, st, nullptr, m.elem, cap);
         if (rc != PSI_OK) return rc;
         CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(c->d_counter + 8, 0, sizeof(unsigned long long), st));
         CK(cudaEventRecord(ev[2], st));
         mode_analyze_kernel<<<agrid, an_threads, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
                                                    (const double*)d[6], (const int*)d[9],
-                                                   (unsigned char*)c->d_mode_scratch, per_warp, c->d_counter);
+                                                   (unsigned char*)c->d_mode_scratch, per_warp, c->d_counter,
+                                                   c->d_counter + 8);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ev[3], st));
+        // few root searches to polish: one BLOCK per search instead of one warp (the slowest serial secant
+        // chain sets the launch time; spreading each D evaluation over the block shortens it ~5x)
+        unsigned long long n_polish = 0;
+        CK(cudaMemcpyAsync(&n_polish, c->d_counter + 8, sizeof(n_polish), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const bool k3_cta = n_polish > 0 && (long long)n_polish <= k3_cta_items();
         for (int cls = 0; cls < kNumClasses; ++cls) {
             if (!(mask & (1u << cls))) continue;
             CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
-            kPolishKernels[cls]<<<pgrid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+            (k3_cta ? kPolishKernelsCta : kPolishKernels)[cls]<<<k3_cta ? c->sm_count : pgrid, kEvalThreads,
+                                                                 c->table_in_smem ? c->table_smem : 0, st>>>(
                 t, c->table_in_smem ? 1 : 0, c->d_dists, n_items, nullptr, (const int*)d[0],
                 (const double*)d[1], (const double*)d[2], (const double*)d[3], (const double*)d[4], nullptr,
                 (double2*)m.w0, m.max_iter, (double2*)m.pol, m.pcalls, m.pconv, m.pstat, c->d_counter,
