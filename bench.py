@@ -154,10 +154,10 @@ _cpu_mode_worker.cache = {}
 
 def cpu_mode_rate(n_axis, cores):
     """modes/s of the oracle port of PSIMode.calculate on `cores` processes over a strided subset of
-    the map (2 pixels per core)."""
+    the map (6 pixels per core, ~8 s)."""
     import multiprocessing as mp
     kx, kz = mode_grid(n_axis)
-    want = min(len(kx), 2*cores)
+    want = min(len(kx), 6*cores)
     idx = np.linspace(0, len(kx) - 1, want).astype(int)
     with mp.get_context("fork").Pool(cores) as pool:
         t0 = time.perf_counter()
@@ -409,7 +409,7 @@ def run_b200(args):
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu:
-            n_cpu = min(n, 600*cores)
+            n_cpu = min(n, 2000*cores)                  # ~12 s of CPU work on all cores
             rate, dt = cpu_sample_rate(n_cpu, cores)
             cpu = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                    "sample": "%d random points of the 1024^2 omega grid (%.1f s)" % (n_cpu, dt)}
