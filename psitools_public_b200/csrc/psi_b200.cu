@@ -531,8 +531,8 @@ static const polish_kernel_t kPolishKernels[kNumClasses] = PSI_CLASS_TABLE(polis
 static const polish_kernel_t kPolishKernelsCta[kNumClasses] = PSI_CLASS_TABLE_CTA(polish_kernel);
 // K3 takes one block per root search when a launch has at most this many searches (PSI_K3_CTA_ITEMS)
 static long long k3_cta_items() {
-    static const long long v = getenv("PSI_K3_CTA_ITEMS") ? atoll(getenv("PSI_K3_CTA_ITEMS")) : 4096;
-    return v;
+    const char* v = getenv("PSI_K3_CTA_ITEMS");       // read per call: tests switch it
+    return v ? atoll(v) : 4096;
 }
 static const contour_kernel_t kContourKernels[kNumClasses] = PSI_CLASS_TABLE(contour_kernel);
 

@@ -234,3 +234,32 @@ def test_mode_batch_chunking_is_invisible(backend, monkeypatch):
     assert np.array_equal(n0, n1) and np.array_equal(c0, c1) and n0.sum() >= 2
     assert all(np.array_equal(r0[i, :n0[i]], r1[i, :n1[i]]) for i in range(5))
     assert s0["evals"] == s1["evals"]
+
+
+@pytest.mark.gpu
+def test_k3_block_mode_equals_warp_mode(built, monkeypatch):
+    """K3 polishes a launch with few root searches with one 384-thread block per search (CtaCuda policy)
+    instead of one warp: same code, different summation order inside each D evaluation.  On a 24x24 map the
+    two modes must find the same roots (1e-11 relative -- the iteration stops at |step| < 1e-8..1e-13, so
+    last-bit differences in D move the converged value by far less) with the same number of D
+    evaluations on all but a few searches, and both must match the LAPACK engine."""
+    from psitools_public_b200 import PSIMode, TanhSinhNoDeepCopy
+    pm = PSIMode(3.0, [1e-8, 1.0], [-2, 2], [1e-8, 1.0], tanhsinh_integrator=TanhSinhNoDeepCopy())
+    ctx, did = pm.psi_dispersion.ctx, pm.psi_dispersion.dist_id
+    n = 24
+    ax = np.logspace(-1, 3, n)
+    kxg, kzg = np.meshgrid(ax, ax)
+    N = n*n
+    run = lambda dev=True: ctx.mode_batch([did]*N, kxg.ravel(), kzg.ravel(), np.zeros(N), [[-2, 2, 1e-8, 1.0]]*N, 20, 1,
+                                          100, 1e-13, 1e-4, [2]*N, [[]]*N, device_aaa=dev)
+    monkeypatch.setenv("PSI_K3_CTA_ITEMS", "0")
+    warp, calls_w, _ = run()
+    monkeypatch.setenv("PSI_K3_CTA_ITEMS", "4096")
+    block, calls_b, _ = run()
+    lapack, _, _ = run(False)
+    assert sum(len(r) > 0 for r in warp) > 50
+    for a, b, c in zip(warp, block, lapack):
+        assert len(a) == len(b)
+        assert np.allclose(a, b, rtol=1e-11, atol=0)
+        assert same_root_sets(distinct(b), distinct(c))
+    assert np.count_nonzero(calls_w != calls_b) <= 0.02*N
