@@ -172,7 +172,9 @@ def workload_config(n_gpus):
             "points_per_gpu": GRID*GRID,
             "sharding": "rank r owns the 1024^2 sub-grid shifted by r/N of a grid step (interleaved shards)",
             "parallelism": "dp%d" % n_gpus,
-            "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+            "l2": "256 MiB buffer written between timed steps (L2 flush)",
+            "exit_rule": "tanh-sinh level loop: reference rule + quadratic-collapse predictor (default); the "
+                         "same steps under the literal reference rule are in literal_exit_rule"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -315,6 +317,34 @@ def run_b200(args):
     node_evals = int(nodes_dev.item())
     D_resident = D_dev.cpu().numpy().view(np.complex128)
 
+    # the same steps under the reference's LITERAL exit rule (tanhsinh.py:120-126), for the record: the
+    # default rule stops the level loop once the increments have collapsed quadratically
+    literal = None
+    if rank == 0:
+        ctx.exit_rule = "reference"
+        step_resident()
+        torch.cuda.synchronize()
+        nodes_dev.zero_()
+        lev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        for a, b in lev:
+            flush.fill_(1)
+            a.record(stream)
+            ctx.disp_eval_dev(n, 1, dist_dev.data_ptr(), par.data_ptr(), par.data_ptr() + 8,
+                              par.data_ptr() + 16, w_dev.data_ptr(), D_dev.data_ptr(), 0,
+                              nodes_dev.data_ptr(), cmask, stream.cuda_stream)
+            b.record(stream)
+        torch.cuda.synchronize()
+        lit_ms = float(np.mean([a.elapsed_time(b) for a, b in lev]))
+        lit_nodes = int(nodes_dev.item())/3
+        D_lit = D_dev.cpu().numpy().view(np.complex128)
+        dev_rel = np.abs(D_lit - D_resident)/np.abs(D_lit)
+        literal = {"evals_per_s_per_gpu": n/(lit_ms*1e-3), "kernel_ms": lit_ms, "node_evals_per_launch": lit_nodes,
+                   "fp64_frac": FLOPS_PER_NODE*lit_nodes/(lit_ms*1e-3)/1e12/fp64_peak,
+                   "max_rel_difference_of_D": float(dev_rel.max()),
+                   "points_differing_by_more_than_1e-12": int(np.count_nonzero(dev_rel > 1e-12))}
+        ctx.exit_rule = "predicted"
+    nodes_dev.zero_()
+
     # end to end through the public API: host buffers, H2D + D2H inside the timed region
     w_np = w_host.numpy().view(np.complex128)
     out_pinned = torch.empty(2*n, dtype=torch.float64).pin_memory()
@@ -427,7 +457,7 @@ def run_b200(args):
                 "e2e": {"value": total_evals/e2e_s, "unit": "evals/s",
                         "h2d_bytes_per_step": 16*n + 28, "d2h_bytes_per_step": 16*n + 8},
                 "gpu_launches": int(launches_all), "roofline": roof, "cpu_baseline": cpu,
-                "clocks": clocks, "modes": modes}
+                "clocks": clocks, "literal_exit_rule": literal, "modes": modes}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -62,6 +62,13 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
                    int max_level, double eps);
 void psi_ctx_destroy(psi_ctx* ctx);
 int psi_ctx_sm_count(psi_ctx* ctx);
+/* Exit rule of the tanh-sinh level loop in K1-K4 (tanhsinh.py:120-126: stop when an increment is below
+ * 1e-15 ABSOLUTE, discarding it).  predict = 0: that rule, literally.  predict = 1 (default; environment
+ * PSI_B200_EXIT_RULE=reference selects 0): additionally stop as soon as the last two increments show the
+ * quadratic collapse of the rule and the extrapolated next increment is 1e4 times below the tolerance --
+ * the levels skipped only resolve rounding noise (csrc/psi_quad.cuh). */
+int psi_ctx_set_exit_rule(psi_ctx* ctx, int predict);
+int psi_ctx_get_exit_rule(psi_ctx* ctx);
 int psi_ctx_synchronize(psi_ctx* ctx);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 long long psi_ctx_launch_count(psi_ctx* ctx);

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "psi_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_double]),
     "psi_ctx_destroy": (None, [_vp]),
     "psi_ctx_sm_count": (C.c_int, [_vp]),
+    "psi_ctx_set_exit_rule": (C.c_int, [_vp, C.c_int]),
+    "psi_ctx_get_exit_rule": (C.c_int, [_vp]),
     "psi_ctx_synchronize": (C.c_int, [_vp]),
     "psi_ctx_launch_count": (C.c_longlong, [_vp]),
     "psi_dist_add": (C.c_int, [_vp, C.POINTER(DistDesc)]),
@@ -415,6 +417,19 @@ class Context(EngineAPI):
     @property
     def sm_count(self):
         return self.lib.psi_ctx_sm_count(self.handle)
+
+    @property
+    def exit_rule(self):
+        """'predicted' (default): the tanh-sinh level loop stops once the increments have collapsed
+        quadratically and the next one is predicted far below the tolerance; 'reference': the literal rule of
+        tanhsinh.py:120-126 (increment below 1e-15 absolute), which spends its last levels on rounding noise."""
+        return "predicted" if self.lib.psi_ctx_get_exit_rule(self.handle) else "reference"
+
+    @exit_rule.setter
+    def exit_rule(self, rule):
+        if rule not in ("predicted", "reference"):
+            raise ValueError("exit_rule must be 'predicted' or 'reference'")
+        check(self.lib.psi_ctx_set_exit_rule(self.handle, 1 if rule == "predicted" else 0), "psi_ctx_set_exit_rule")
 
     @property
     def launch_count(self):

@@ -155,6 +155,7 @@ struct psi_ctx {
     void* d_mode_scratch = nullptr;
     size_t mode_scratch_bytes = 0;
     long long launches = 0;
+    int predict_exit = 1;                  // quadrature exit rule of K1-K4 (psi_ctx_set_exit_rule)
 };
 
 extern "C" { static int ensure_stage(psi_ctx* c, size_t bytes); }
@@ -163,6 +164,7 @@ static NodeTableView table_view(const psi_ctx* c) {
     NodeTableView t;
     t.nodes = c->d_nodes; t.level_off = c->d_level_off; t.n_nodes = c->n_nodes; t.max_m = c->max_m;
     t.eps = c->eps;
+    t.predict_exit = c->predict_exit;
     return t;
 }
 
@@ -172,6 +174,7 @@ static NodeTableView table_view(const psi_ctx* c) {
 __global__ void background_kernel(NodeTableView t, DistParams* dists, int id) {
     DistParams d = dists[id];
     unsigned long long nodes = 0;
+    t.predict_exit = 0;                    // the background integrals always run the reference's literal rule
     background_warp<WarpCuda>(t, d, nodes);
     if (threadIdx.x == 0) {
         dists[id].j0 = d.j0; dists[id].j1 = d.j1; dists[id].denom = d.denom;
@@ -580,6 +583,10 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
     CK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->n_nodes = n_nodes; c->max_m = max_level; c->eps = eps;
+    {
+        const char* rule = getenv("PSI_B200_EXIT_RULE");          // "reference" = the literal rule of tanhsinh.py
+        c->predict_exit = (rule && std::string(rule) == "reference") ? 0 : 1;
+    }
     // level-major reordering of the caller's table
     std::vector<node_t> lv;
     std::vector<int> off;
@@ -621,6 +628,12 @@ void psi_ctx_destroy(psi_ctx* c) {
 }
 
 int psi_ctx_sm_count(psi_ctx* c) { return c ? c->sm_count : 0; }
+int psi_ctx_set_exit_rule(psi_ctx* c, int predict) {
+    if (!c) return fail(PSI_ERR_ARG, "null context");
+    c->predict_exit = predict ? 1 : 0;
+    return PSI_OK;
+}
+int psi_ctx_get_exit_rule(psi_ctx* c) { return c ? c->predict_exit : 0; }
 long long psi_ctx_launch_count(psi_ctx* c) { return c ? c->launches : 0; }
 
 int psi_ctx_synchronize(psi_ctx* c) {

@@ -28,6 +28,7 @@ struct NodeTableView {
     int n_nodes;              // total number of nodes (original index j in [0, n_nodes))
     int max_m;
     double eps;               // 10^-precision_digit: end-point guard AND default tolerance
+    int predict_exit;         // 1: skip confirming levels whose increment is predicted far below tol (below)
 };
 
 PSI_HD int ctz_int(int v) {
@@ -108,6 +109,10 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
         res[k].im = half * W::sum(acc[k].im);
     }
     // ---- levels 1..max_m: odd multiples of stride 2^(max_m-m) (tanhsinh.py:107-126)
+    double prev[NC], prev2[NC];            // the two previous increments of every component
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { prev[k] = INFINITY; prev2[k] = INFINITY; }
+    const bool predict = t.predict_exit != 0;
     double h = 1.0;
     for (int m = 1; m <= t.max_m; ++m) {
         h *= 0.5;
@@ -132,8 +137,27 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
             if (active & (1u << k)) {
                 cx dres(-0.5 * res[k].re + hh * W::sum(acc[k].re),
                         -0.5 * res[k].im + hh * W::sum(acc[k].im));
-                if (cabs(dres) * cscale[k] < tol) active &= ~(1u << k);
-                else { res[k].re += dres.re; res[k].im += dres.im; }
+                const double a = cabs(dres) * cscale[k];
+                if (a < tol) active &= ~(1u << k);
+                else {
+                    res[k].re += dres.re; res[k].im += dres.im;
+                    // Convergence predictor (predict_exit).  The reference's rule evaluates levels until an
+                    // increment falls below tol = 1e-15 ABSOLUTE and then discards it; for |I| >~ 1 that is
+                    // below the rounding noise of the sums, so the last levels -- each as expensive as all
+                    // earlier ones together -- only resolve noise.  Tanh-sinh increments collapse
+                    // quadratically (d_{m+1} ~ d_m^2/|I|).  When the last two increments SHOW that collapse
+                    // (d_m < 1e-3 d_{m-1}, d_{m-1} < 0.1 d_{m-2}, d_m |I| <= 100 d_{m-1}^2) and the
+                    // extrapolated next one, 1e4 d_m^2/|I|, is below tol, the remaining levels are skipped.
+                    // The value returned is the one the reference's rule returns when its next increment
+                    // is indeed below tol (the sum after THIS level).
+                    if (predict) {
+                        const double s = cabs(res[k]) * cscale[k];
+                        if (a < 1e-3 * prev[k] && prev[k] < 0.1 * prev2[k] && 1e4 * a * a < tol * s &&
+                            a * s <= 100.0 * prev[k] * prev[k]) active &= ~(1u << k);
+                    }
+                    prev2[k] = prev[k];
+                    prev[k] = a;
+                }
             }
         }
         if (active == 0u) break;

@@ -201,15 +201,18 @@ psi_ctx* hs_ctx_create(const double* xj, const double* wj, int n, int max_m, dou
     psi_ctx* c = new psi_ctx();
     build_level_major(xj, wj, n, max_m, c->lv, c->off);
     c->view.nodes = c->lv.data(); c->view.level_off = c->off.data();
-    c->view.n_nodes = n; c->view.max_m = max_m; c->view.eps = eps;
+    c->view.n_nodes = n; c->view.max_m = max_m; c->view.eps = eps; c->view.predict_exit = 0;
     return c;
 }
 void hs_ctx_destroy(psi_ctx* c) { delete c; }
+void hs_set_exit_rule(psi_ctx* c, int predict) { c->view.predict_exit = predict ? 1 : 0; }
 
 int hs_dist_add(psi_ctx* c, const psi_dist_desc* desc) {
     DistParams d = dist_from_desc(*desc);
     unsigned long long nodes = 0;
-    background_warp<WarpOne>(c->view, d, nodes);
+    NodeTableView literal = c->view;
+    literal.predict_exit = 0;                 // like the product: background integrals use the literal rule
+    background_warp<WarpOne>(literal, d, nodes);
     c->dists.push_back(d);
     return (int)c->dists.size() - 1;
 }

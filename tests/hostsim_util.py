@@ -68,6 +68,18 @@ class HostsimContext(EngineAPI):
             raise PsiError("%s failed (code %d): %s" % (what, rc, self._last_error()))
         return rc
 
+    _exit_rule = "reference"
+
+    @property
+    def exit_rule(self):
+        return self._exit_rule
+
+    @exit_rule.setter
+    def exit_rule(self, rule):
+        assert rule in ("predicted", "reference")
+        self.lib.hs_set_exit_rule(self.handle, 1 if rule == "predicted" else 0)
+        self._exit_rule = rule
+
     def _last_error(self):
         return self.lib.hs_last_error().decode()
 

@@ -14,10 +14,17 @@ from common import carr, det_extended, load, lu_noise_floor, oracle_dist, produc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ts(built):
-    from psitools_public_b200 import TanhSinh
-    return TanhSinh()
+@pytest.fixture(scope="module", params=["predicted", "reference"])
+def ts(built, request):
+    """Every parity test of this module runs under both exit rules of the quadrature's level loop: the
+    default ('predicted': stop once the increments have collapsed quadratically) and the literal rule of
+    tanhsinh.py:120-126 ('reference')."""
+    from psitools_public_b200 import TanhSinh, _device
+    integ = TanhSinh()
+    ctx = _device.get_context(integ)
+    ctx.exit_rule = request.param
+    yield integ
+    ctx.exit_rule = "predicted"
 
 
 def make(spec, ts):

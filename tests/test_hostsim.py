@@ -88,3 +88,34 @@ def test_aaa_weights_against_numpy_svd(M, m, seed):
     assert fit <= sv[-1]*(1 + 1e-8) + 1e-15*sv[0]
     gap = (sv[-2] - sv[-1])/sv[0]
     assert abs(abs(np.vdot(wref, w)) - 1.0) < 1e-10 + 1e-14/max(gap, 1e-16), (abs(np.vdot(wref, w)), gap)
+
+
+def test_exit_predictor_against_literal_rule(ts):
+    """The level loop's convergence predictor (csrc/psi_quad.cuh: stop once the last two increments show the
+    quadratic collapse of the tanh-sinh rule and the extrapolated next one is 1e4 below the tolerance)
+    against the reference's literal rule (tanhsinh.py:120-126) on every fixture point: M and D agree to far
+    better than the 1e-10 of the parity contract, with fewer nodes."""
+    bg = load("background.json")
+    worst_m, worst_d, nodes = 0.0, 0.0, {"reference": 0, "predicted": 0}
+    for case in load("disp.json")["cases"]:
+        desc = product_desc(bg[case["dist"]]["spec"])
+        w = carr(case["w"])
+        out = {}
+        for rule in ("reference", "predicted"):
+            ctx = hs.HostsimContext(ts)
+            ctx.exit_rule = rule
+            did = ctx.add_dist(desc)
+            out[rule] = ctx.disp_eval(did, case["kx"], case["kz"], case["alpha"], w, want_M=True)
+            nodes[rule] += ctx.node_evals
+        (d0, m0), (d1, m1) = out["reference"], out["predicted"]
+        worst_m = max(worst_m, float(np.max(np.abs(m1 - m0)/np.max(np.abs(m0), axis=1, keepdims=True))))
+        for i in range(len(w)):
+            has_res = len(case["poles"][i]) > len(bg[case["dist"]]["poles"])
+            rt = max(1e-11, resonant_floor(w[i]) if has_res else 0.0)
+            scale = np.median(np.abs(d0))
+            assert abs(d1[i] - d0[i]) <= rt*(abs(d0[i]) + scale), (case["dist"], w[i])
+            worst_d = max(worst_d, abs(d1[i] - d0[i])/(abs(d0[i]) + scale))
+    assert worst_m < 1e-11, worst_m
+    assert nodes["predicted"] < 0.8*nodes["reference"], nodes
+    print("predictor vs literal rule: worst M %.1e, worst D %.1e, nodes %d -> %d"
+          % (worst_m, worst_d, nodes["reference"], nodes["predicted"]))
