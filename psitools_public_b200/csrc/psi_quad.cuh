@@ -109,9 +109,10 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
         res[k].im = half * W::sum(acc[k].im);
     }
     // ---- levels 1..max_m: odd multiples of stride 2^(max_m-m) (tanhsinh.py:107-126)
-    double prev[NC], prev2[NC];            // the two previous increments of every component
+    double prev[NC];                       // previous increment of every component
+    unsigned falling = 0u;                 // bit k: that increment was already < 0.1 of the one before it
 #pragma unroll
-    for (int k = 0; k < NC; ++k) { prev[k] = INFINITY; prev2[k] = INFINITY; }
+    for (int k = 0; k < NC; ++k) prev[k] = INFINITY;
     const bool predict = t.predict_exit != 0;
     double h = 1.0;
     for (int m = 1; m <= t.max_m; ++m) {
@@ -152,10 +153,10 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
                     // is indeed below tol (the sum after THIS level).
                     if (predict) {
                         const double s = cabs(res[k]) * cscale[k];
-                        if (a < 1e-3 * prev[k] && prev[k] < 0.1 * prev2[k] && 1e4 * a * a < tol * s &&
+                        if (a < 1e-3 * prev[k] && (falling & (1u << k)) && 1e4 * a * a < tol * s &&
                             a * s <= 100.0 * prev[k] * prev[k]) active &= ~(1u << k);
                     }
-                    prev2[k] = prev[k];
+                    if (a < 0.1 * prev[k]) falling |= 1u << k; else falling &= ~(1u << k);
                     prev[k] = a;
                 }
             }
