@@ -76,6 +76,16 @@ struct WarpCuda {
     }
 };
 
+// Thread policy: one thread = one evaluation, no cooperation (fast path of K1, below).
+struct ThreadCuda {
+    static constexpr int width = 1;
+    static __device__ __forceinline__ int lane() { return 0; }
+    static __device__ __forceinline__ double sum(double v) { return v; }
+    static __device__ __forceinline__ double max(double v) { return v; }
+    static __device__ __forceinline__ void sync() {}
+    static __device__ __forceinline__ bool any(bool p) { return p; }
+};
+
 // CTA policy: ALL threads of the block cooperate on one evaluation (the quadrature code only sees lane(),
 // width and the reductions).  Used by K3 when a launch has too few root searches to fill the GPU with one
 // warp each: a secant polish is a serial chain of D evaluations, and the slowest chain sets the launch time.
@@ -156,6 +166,9 @@ struct psi_ctx {
     size_t mode_scratch_bytes = 0;
     long long launches = 0;
     int predict_exit = 1;                  // quadrature exit rule of K1-K4 (psi_ctx_set_exit_rule)
+    int fast_cap = 8;                      // K1 fast path: last level a thread-per-point evaluation may use (0 = off)
+    long long* d_hard = nullptr;           // indices of the points the fast path handed to the warp kernel
+    size_t hard_cap = 0;
 };
 
 extern "C" { static int ensure_stage(psi_ctx* c, size_t bytes); }
@@ -165,6 +178,7 @@ static NodeTableView table_view(const psi_ctx* c) {
     t.nodes = c->d_nodes; t.level_off = c->d_level_off; t.n_nodes = c->n_nodes; t.max_m = c->max_m;
     t.eps = c->eps;
     t.predict_exit = c->predict_exit;
+    t.level_cap = 0;
     return t;
 }
 
@@ -253,15 +267,19 @@ disp_eval_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restri
                  const int* __restrict__ pidx, const double2* __restrict__ w, double2* __restrict__ D,
                  double2* __restrict__ M, unsigned long long* __restrict__ queue,
                  unsigned long long* __restrict__ node_evals, const long long* __restrict__ elem,
-                 int elem_cap) {
+                 int elem_cap, const long long* __restrict__ remap,
+                 const unsigned long long* __restrict__ n_dev) {
     const NodeTableView t = stage_table(gt, table_in_smem != 0);
     const int lane = threadIdx.x & 31;
     unsigned long long nodes = 0;
+    // second stage of the fast path: the work list is the `remap` array, its length sits in device memory
+    const unsigned long long n_work = n_dev != nullptr ? *n_dev : (unsigned long long)n;
     while (true) {
         unsigned long long idx = 0;
         if (lane == 0) idx = atomicAdd(queue, 1ull);
         idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= (unsigned long long)n) break;
+        if (idx >= n_work) break;
+        if (remap != nullptr) idx = (unsigned long long)remap[idx];
         // element mode (mode pipeline): point = entry e of the per-item sample buffers, item = e / cap
         const long long e = elem != nullptr ? elem[idx] : (long long)idx;
         const long long pi = elem != nullptr ? e / elem_cap
@@ -286,7 +304,74 @@ disp_eval_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restri
 
 typedef void (*eval_kernel_t)(NodeTableView, int, const DistParams*, long long, int, const int*, const double*,
                               const double*, const double*, const int*, const double2*, double2*, double2*,
-                              unsigned long long*, unsigned long long*, const long long*, int);
+                              unsigned long long*, unsigned long long*, const long long*, int, const long long*,
+                              const unsigned long long*);
+
+// K1 fast path.  Most evaluations converge within the first few levels of the rule (a few hundred nodes: the
+// exit predictor of psi_quad.cuh); for them a whole warp per point spends most of its time in per-level
+// reductions and exit tests over a handful of nodes per lane.  Here ONE THREAD evaluates one point -- the same
+// quadrature code instantiated with the one-lane policy, all partial sums in registers, no shuffles -- using
+// levels 0..cap only; a point that has not converged by then (|Im w| tiny next to a resonance) is appended to
+// `hard_idx` and evaluated from scratch by the warp-per-point kernel above.  Warps take 32 consecutive points,
+// so the lanes walk the node table together (shared-memory broadcasts) and finish at similar levels.
+template <int NK, bool VISC>
+__global__ void __launch_bounds__(kEvalThreads, 1)
+disp_eval_thread_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, long long n,
+                        int broadcast, const int* __restrict__ dist, const double* __restrict__ kx,
+                        const double* __restrict__ kz, const double* __restrict__ alpha,
+                        const int* __restrict__ pidx, const double2* __restrict__ w, double2* __restrict__ D,
+                        unsigned long long* __restrict__ queue, unsigned long long* __restrict__ node_evals,
+                        const long long* __restrict__ elem, int elem_cap, int level_cap,
+                        long long* __restrict__ hard_idx, unsigned long long* __restrict__ hard_count) {
+    NodeTableView t = stage_table(gt, table_in_smem != 0);
+    t.predict_exit = 2;
+    t.level_cap = level_cap;
+    const int lane = threadIdx.x & 31;
+    unsigned long long nodes = 0;
+    while (true) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(queue, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned long long)n) break;
+        const unsigned long long idx = base + lane;
+        if (idx >= (unsigned long long)n) continue;
+        const long long e = elem != nullptr ? elem[idx] : (long long)idx;
+        const long long pi = elem != nullptr ? e / elem_cap
+                             : (pidx != nullptr ? (long long)pidx[idx] : (broadcast ? 0 : (long long)idx));
+        const DistParams& d = dists[dist[pi]];
+        const double al = alpha[pi];
+        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
+        const double2 wv = w[e];
+        const cx val = disp_eval_warp<ThreadCuda, NK, VISC>(t, d, cx(wv.x, wv.y), kx[pi], kz[pi], al, nullptr, nodes);
+        if (val.re != val.re || val.im != val.im) {          // not converged within the cap (or genuinely NaN)
+            hard_idx[atomicAdd(hard_count, 1ull)] = (long long)idx;
+        } else {
+            D[e] = make_double2(val.re, val.im);
+        }
+    }
+    if (node_evals != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nodes += __shfl_xor_sync(0xffffffffu, nodes, o);
+        if (lane == 0 && nodes) atomicAdd(node_evals, nodes);
+    }
+}
+
+typedef void (*thread_kernel_t)(NodeTableView, int, const DistParams*, long long, int, const int*, const double*,
+                                const double*, const double*, const int*, const double2*, double2*,
+                                unsigned long long*, unsigned long long*, const long long*, int, int, long long*,
+                                unsigned long long*);
+static thread_kernel_t thread_kernel_for(int cls) {
+    switch (cls) {
+    case 0: return disp_eval_thread_kernel<0, false>;
+    case 1: return disp_eval_thread_kernel<0, true>;
+    case 2: return disp_eval_thread_kernel<1, false>;
+    case 3: return disp_eval_thread_kernel<1, true>;
+    case 4: return disp_eval_thread_kernel<2, false>;
+    case 5: return disp_eval_thread_kernel<2, true>;
+    case 6: return disp_eval_thread_kernel<3, false>;
+    default: return disp_eval_thread_kernel<3, true>;
+    }
+}
 
 static eval_kernel_t eval_kernel_for(int cls) {
     switch (cls) {
@@ -586,6 +671,8 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
     {
         const char* rule = getenv("PSI_B200_EXIT_RULE");          // "reference" = the literal rule of tanhsinh.py
         c->predict_exit = (rule && std::string(rule) == "reference") ? 0 : 1;
+        const char* cap = getenv("PSI_K1_FAST_CAP");               // 0 switches the thread-per-point fast path off
+        if (cap) c->fast_cap = atoi(cap);
     }
     // level-major reordering of the caller's table
     std::vector<node_t> lv;
@@ -603,6 +690,9 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
     if (c->table_in_smem) {
         for (int cls = 0; cls < kNumClasses; ++cls)
             CK(cudaFuncSetAttribute(eval_kernel_for(cls), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)c->table_smem));
+        for (int cls = 0; cls < kNumClasses; ++cls)
+            CK(cudaFuncSetAttribute(thread_kernel_for(cls), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)c->table_smem));
         for (int cls = 0; cls < kNumClasses; ++cls) {
             CK(cudaFuncSetAttribute(kPolishKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
@@ -622,7 +712,7 @@ void psi_ctx_destroy(psi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_nodes); cudaFree(c->d_level_off); cudaFree(c->d_dists); cudaFree(c->d_counter);
-    cudaFree(c->d_stage); cudaFree(c->d_contour_scratch); cudaFree(c->d_mode_scratch);
+    cudaFree(c->d_stage); cudaFree(c->d_contour_scratch); cudaFree(c->d_mode_scratch); cudaFree(c->d_hard);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -690,13 +780,39 @@ static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* d
     int grid = (int)(want < c->sm_count ? want : c->sm_count);
     NodeTableView t = table_view(c);
     if ((class_mask & 0xffu) == 0) class_mask = 0xffu;
+    // fast path: thread per point first, the warp kernel only for what that leaves (needs the predictor rule,
+    // no M output, and enough points to fill the machine with one thread each)
+    const bool fast = c->predict_exit != 0 && c->fast_cap > 0 && M == nullptr && n >= 4096;
+    if (fast && (size_t)n > c->hard_cap) {
+        if (c->d_hard) CK(cudaFree(c->d_hard));
+        c->d_hard = nullptr; c->hard_cap = 0;
+        CK(cudaMalloc(&c->d_hard, sizeof(long long) * (size_t)n));
+        c->hard_cap = (size_t)n;
+    }
     for (int cls = 0; cls < kNumClasses; ++cls) {
         if (!(class_mask & (1u << cls))) continue;
         CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
         eval_kernel_t k = eval_kernel_for(cls);
+        if (fast) {
+            CK(cudaMemsetAsync(c->d_counter + 9, 0, sizeof(unsigned long long), st));
+            const long long want_t = (n + kEvalThreads - 1) / kEvalThreads;
+            const int grid_t = (int)(want_t < c->sm_count ? want_t : c->sm_count);
+            thread_kernel_for(cls)<<<grid_t, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+                t, c->table_in_smem ? 1 : 0, c->d_dists, n, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w,
+                (double2*)D, c->d_counter, node_evals_dev, elem, elem_cap, c->fast_cap, c->d_hard, c->d_counter + 9);
+            c->launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+            k<<<c->sm_count, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+                t, c->table_in_smem ? 1 : 0, c->d_dists, n, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w,
+                (double2*)D, nullptr, c->d_counter, node_evals_dev, elem, elem_cap, c->d_hard, c->d_counter + 9);
+            c->launches++;
+            CK(cudaGetLastError());
+            continue;
+        }
         k<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
             t, c->table_in_smem ? 1 : 0, c->d_dists, n, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w, (double2*)D,
-            (double2*)M, c->d_counter, node_evals_dev, elem, elem_cap);
+            (double2*)M, c->d_counter, node_evals_dev, elem, elem_cap, nullptr, nullptr);
         c->launches++;
         CK(cudaGetLastError());
     }

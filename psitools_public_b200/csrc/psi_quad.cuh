@@ -28,7 +28,9 @@ struct NodeTableView {
     int n_nodes;              // total number of nodes (original index j in [0, n_nodes))
     int max_m;
     double eps;               // 10^-precision_digit: end-point guard AND default tolerance
-    int predict_exit;         // 1: skip confirming levels whose increment is predicted far below tol (below)
+    int predict_exit;         // 1: skip confirming levels whose increment is predicted far below tol (below);
+                              // 2: the same without the noise-floor check (thread-per-point fast path of K1)
+    int level_cap;            // > 0: give up after this level if a component is still running (results = NaN)
 };
 
 PSI_HD int ctz_int(int v) {
@@ -114,8 +116,10 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
 #pragma unroll
     for (int k = 0; k < NC; ++k) prev[k] = INFINITY;
     const bool predict = t.predict_exit != 0;
+    const bool loose = t.predict_exit == 2;
+    const int last_level = (t.level_cap > 0 && t.level_cap < t.max_m) ? t.level_cap : t.max_m;
     double h = 1.0;
-    for (int m = 1; m <= t.max_m; ++m) {
+    for (int m = 1; m <= last_level; ++m) {
         h *= 0.5;
         const int sh = t.max_m - m;
         // (2i+1) << sh < nsel  <=>  i < ((nsel-1 >> sh) + 1) >> 1
@@ -154,7 +158,7 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
                     if (predict) {
                         const double s = cabs(res[k]) * cscale[k];
                         if (a < 1e-3 * prev[k] && (falling & (1u << k)) && 1e4 * a * a < tol * s &&
-                            a * s <= 100.0 * prev[k] * prev[k]) active &= ~(1u << k);
+                            (loose || a * s <= 100.0 * prev[k] * prev[k])) active &= ~(1u << k);
                     }
                     if (a < 0.1 * prev[k]) falling |= 1u << k; else falling &= ~(1u << k);
                     prev[k] = a;
@@ -162,6 +166,10 @@ PSI_HD void tanhsinh_warp(const NodeTableView& t, double a, double b, double tol
             }
         }
         if (active == 0u) break;
+    }
+    if (last_level < t.max_m && active != 0u) {          // capped run that did not converge: say so
+#pragma unroll
+        for (int k = 0; k < NC; ++k) res[k] = cx(NAN, NAN);
     }
     nodes_done += evals;
 }

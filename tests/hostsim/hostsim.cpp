@@ -201,7 +201,7 @@ psi_ctx* hs_ctx_create(const double* xj, const double* wj, int n, int max_m, dou
     psi_ctx* c = new psi_ctx();
     build_level_major(xj, wj, n, max_m, c->lv, c->off);
     c->view.nodes = c->lv.data(); c->view.level_off = c->off.data();
-    c->view.n_nodes = n; c->view.max_m = max_m; c->view.eps = eps; c->view.predict_exit = 0;
+    c->view.n_nodes = n; c->view.max_m = max_m; c->view.eps = eps; c->view.predict_exit = 0; c->view.level_cap = 0;
     return c;
 }
 void hs_ctx_destroy(psi_ctx* c) { delete c; }
