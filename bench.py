@@ -432,7 +432,8 @@ def run_b200(args):
             pass
         roof = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": tf/fp64_peak if fp64_peak else None, "traffic": traffic,
-                "kernel": "disp_eval_kernel", "kernel_ms": ms_kernel,
+                "kernel": "disp_eval_thread_kernel (thread per point, levels 0-8) + disp_eval_kernel (warp per point, "
+                          "the points left over); timed together", "kernel_ms": ms_kernel,
                 "node_evals_per_launch": node_evals/args.steps, "flops_per_node_eval": FLOPS_PER_NODE,
                 "peak_source": "measured live by dfma_peak_kernel (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm_gbs_algorithmic": 32.0*n/(ms_kernel*1e-3)/1e9}
