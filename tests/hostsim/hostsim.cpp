@@ -205,7 +205,8 @@ psi_ctx* hs_ctx_create(const double* xj, const double* wj, int n, int max_m, dou
     return c;
 }
 void hs_ctx_destroy(psi_ctx* c) { delete c; }
-void hs_set_exit_rule(psi_ctx* c, int predict) { c->view.predict_exit = predict ? 1 : 0; }
+void hs_set_exit_rule(psi_ctx* c, int predict) { c->view.predict_exit = predict; }      // 0, 1 or 2 (fast path)
+void hs_set_level_cap(psi_ctx* c, int cap) { c->view.level_cap = cap; }
 
 int hs_dist_add(psi_ctx* c, const psi_dist_desc* desc) {
     DistParams d = dist_from_desc(*desc);

@@ -76,9 +76,14 @@ class HostsimContext(EngineAPI):
 
     @exit_rule.setter
     def exit_rule(self, rule):
-        assert rule in ("predicted", "reference")
-        self.lib.hs_set_exit_rule(self.handle, 1 if rule == "predicted" else 0)
+        assert rule in ("predicted", "reference", "fast")
+        self.lib.hs_set_exit_rule(self.handle, {"reference": 0, "predicted": 1, "fast": 2}[rule])
         self._exit_rule = rule
+
+    def set_level_cap(self, cap):
+        """Fast-path emulation: with exit_rule 'fast' and a cap the one-lane code is exactly what one thread
+        of disp_eval_thread_kernel runs (NaN = not converged within the cap)."""
+        self.lib.hs_set_level_cap(self.handle, int(cap))
 
     def _last_error(self):
         return self.lib.hs_last_error().decode()

@@ -119,3 +119,38 @@ def test_exit_predictor_against_literal_rule(ts):
     assert nodes["predicted"] < 0.8*nodes["reference"], nodes
     print("predictor vs literal rule: worst M %.1e, worst D %.1e, nodes %d -> %d"
           % (worst_m, worst_d, nodes["reference"], nodes["predicted"]))
+
+
+def test_fast_path_thread_logic(ts):
+    """What one thread of K1's fast path computes (the one-lane instantiation of the quadrature with the
+    loose predictor and a level cap -- exactly the code of disp_eval_thread_kernel): on every fixture point
+    the result is either NaN ("not converged by level 8": the point goes to the warp-per-point kernel) or
+    agrees with the literal rule to 1e-11, and with the cap lifted every point converges to that accuracy."""
+    bg = load("background.json")
+    n_fast = n_hard = nodes_fast = nodes_lit = 0
+    for case in load("disp.json")["cases"]:
+        desc = product_desc(bg[case["dist"]]["spec"])
+        w = carr(case["w"])
+        lit, fast, nocap = hs.HostsimContext(ts), hs.HostsimContext(ts), hs.HostsimContext(ts)
+        fast.exit_rule = "fast"
+        fast.set_level_cap(8)
+        nocap.exit_rule = "fast"
+        d0 = lit.disp_eval(lit.add_dist(desc), case["kx"], case["kz"], case["alpha"], w)
+        d1 = fast.disp_eval(fast.add_dist(desc), case["kx"], case["kz"], case["alpha"], w)
+        d2 = nocap.disp_eval(nocap.add_dist(desc), case["kx"], case["kz"], case["alpha"], w)
+        scale = np.median(np.abs(d0))
+        assert np.all(np.isfinite(d2))
+        for i in range(len(w)):
+            has_res = len(case["poles"][i]) > len(bg[case["dist"]]["poles"])
+            rt = max(1e-11, resonant_floor(w[i]) if has_res else 0.0)
+            assert abs(d2[i] - d0[i]) <= rt*(abs(d0[i]) + scale), (case["dist"], w[i])
+            if np.isnan(d1[i].real):
+                n_hard += 1
+            else:
+                n_fast += 1
+                assert abs(d1[i] - d0[i]) <= rt*(abs(d0[i]) + scale), (case["dist"], w[i])
+        nodes_fast += fast.node_evals
+        nodes_lit += lit.node_evals
+    assert nodes_fast < 0.25*nodes_lit
+    assert n_fast > n_hard > 0, (n_fast, n_hard)
+    print("fast path on the fixture points: %d converge within the cap, %d go to the warp kernel" % (n_fast, n_hard))
