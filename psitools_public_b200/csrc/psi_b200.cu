@@ -403,7 +403,8 @@ polish_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict_
               const int* __restrict__ max_iter, double2* out, int* n_calls, int* max_conv, int* status,
               unsigned long long* queue, unsigned long long* counters, int stride, const int* __restrict__ cnt,
               const int* __restrict__ phase) {
-    const NodeTableView t = stage_table(gt, table_in_smem != 0);
+    NodeTableView t = stage_table(gt, table_in_smem != 0);
+    if (t.predict_exit == 1) t.predict_exit = 2;      // the looser predictor of K1's fast path (psi_quad.cuh)
     const int lane = CTA ? (int)threadIdx.x : (int)(threadIdx.x & 31);
     if (CTA) CtaCuda<kEvalThreads>::phase() = 0u;
     unsigned long long nodes = 0, evals = 0;
@@ -444,7 +445,8 @@ contour_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict
                const double* __restrict__ max_step, const int* __restrict__ max_iter, double2* scratch,
                int cap, int* counts, int* status, int* n_points, unsigned long long* queue,
                unsigned long long* counters) {
-    const NodeTableView t = stage_table(gt, table_in_smem != 0);
+    NodeTableView t = stage_table(gt, table_in_smem != 0);
+    if (t.predict_exit == 1) t.predict_exit = 2;      // the looser predictor of K1's fast path (psi_quad.cuh)
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     cx* base = reinterpret_cast<cx*>(scratch) + (size_t)warp_global * 4 * cap;
