@@ -6,7 +6,8 @@ yields batches of frequencies and receives D there.  ``PSIMode.calculate`` drive
 ``solve_modes`` drives thousands of them in lock-step (one K1 launch per pass, see _engine.py), which
 is what ``MpiScheduler.run`` and ``PSIGridRefiner`` use for maps.
 
-Out of scope: find_minimum (unused), plot_dispersion (matplotlib).
+``plot_dispersion(show_exact=True)`` (reference psi_mode.py:493-558) evaluates the exact D on the whole
+plot grid in ONE K1 launch (``dispersion_map``); matplotlib is imported only when a figure is drawn.
 """
 import numpy as np
 
@@ -277,3 +278,53 @@ class PSIMode:
         run_lockstep(self.psi_dispersion.ctx, [job])
         self.n_function_call += trace.n_function_call
         return job.result
+
+    def find_minimum(self):
+        """Location of the minimum of |rational approximation| in the domain (reference
+        psi_mode.py:399-409; host-side scipy differential evolution on the approximant, no D calls)."""
+        from scipy import optimize as opt
+        bounds = ((self.domain.xmin, self.domain.xmax), (self.domain.ymin, self.domain.ymax))
+        ret = opt.differential_evolution(lambda x: np.abs(self.ra.evaluate(x[0] + 1j*x[1])), bounds)
+        self.log_print(ret)
+        return ret.x[0] + 1j*ret.x[1]
+
+    def dispersion_map(self, wave_number_x, wave_number_z, viscous_alpha=0, N=100, show_exact=False,
+                       x=None, y=None):
+        """The arrays ``plot_dispersion`` draws (reference psi_mode.py:507-517): ``x, y``, the rational
+        approximation on the meshgrid and, with ``show_exact``, the exact D there -- one K1 launch over
+        the N*N frequencies instead of the reference's per-frequency Python loop."""
+        if x is None or y is None:
+            x, y = self.domain.grid_xy(N=N)
+        xv, yv = np.meshgrid(x, y)
+        z = xv + 1j*yv
+        f_appro = self.ra.evaluate(z)
+        f_exact = None
+        if show_exact:
+            f_exact = self.dispersion(z, wave_number_x, wave_number_z, viscous_alpha=viscous_alpha)
+        return x, y, f_appro, f_exact
+
+    def plot_dispersion(self, wave_number_x, wave_number_z, viscous_alpha=0, N=100, show_exact=False,
+                        x=None, y=None):
+        """Plot the approximate dispersion relation over the domain and, with ``show_exact``, the exact
+        one beside it (reference psi_mode.py:493-558).  Needs matplotlib."""
+        import matplotlib.pyplot as plt
+        x, y, f_appro, f_exact = self.dispersion_map(wave_number_x, wave_number_z, viscous_alpha, N,
+                                                     show_exact, x, y)
+        if show_exact:
+            plt.subplot(122)
+            plt.contourf(x, y, np.log10(np.abs(f_exact)), 20)
+            plt.colorbar()
+            plt.subplot(121)
+        plt.contourf(x, y, np.log10(np.abs(f_appro)), 20)
+        plt.colorbar()
+
+        def inside(zs):
+            zs = np.asarray(zs)
+            sel = (zs.real > x[0]) & (zs.real < x[-1]) & (zs.imag > y[0]) & (zs.imag < y[-1])
+            return zs[sel]
+
+        nodes = inside(self.z_sample)
+        plt.plot(nodes.real, nodes.imag, linestyle='', marker='.', color='black')
+        nodes = inside(np.asarray(self.z_sample)[np.asarray(self.ra.maskF).astype(bool)])
+        plt.plot(nodes.real, nodes.imag, linestyle='', marker='.', color='red')
+        plt.show()

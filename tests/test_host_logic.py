@@ -200,3 +200,31 @@ def test_mode_count_roots_true(backend):
     assert pm.n_roots == 1                                   # same contour as test_complex_roots_mpi pixel 3
     assert len(pm.z_sample) > 200                            # 20 random samples + the contour points
     assert min(abs(r - (-1.004879704650626 + 0.0008946325671658642j)) for r in roots) < 1e-8
+
+
+def test_mode_dispersion_map_and_minimum(backend):
+    """plot_dispersion's arrays (psi_mode.py:507-517): the exact D of the whole plot grid comes from
+    one batched evaluation and equals per-frequency calls; the rational approximation reproduces it in
+    the domain; find_minimum (psi_mode.py:399-409) returns a point of the domain below every grid value."""
+    from psitools_public_b200 import PSIMode, TanhSinh
+    np.random.seed(0)
+    pm = PSIMode(3.0, [1e-8, 0.01], [-2, 2], [1e-8, 1], tanhsinh_integrator=TanhSinh())
+    roots = pm.calculate(10, 1000)
+    assert len(roots) == 1
+    x, y, f_appro, f_exact = pm.dispersion_map(10, 1000, N=6, show_exact=True)
+    assert f_appro.shape == f_exact.shape == (6, 6) and x[0] == -2 and y[-1] == 1
+    for (i, j) in [(0, 0), (2, 3), (5, 5)]:
+        one = pm.dispersion(x[j] + 1j*y[i], 10, 1000)
+        assert abs(f_exact[i, j] - one) <= 1e-12*abs(one)
+    inner = f_exact[1:, :]                                      # rows with Im w > 1e-8 (off the branch cut)
+    assert np.max(np.abs(f_appro[1:, :] - inner)/np.abs(inner)) < 1e-6
+    _, _, fa, fe = pm.dispersion_map(10, 1000, x=np.array([-1.0, 0.5]), y=np.array([0.1, 0.2]))
+    assert fa.shape == (2, 2) and fe is None
+    zmin = pm.find_minimum()                                    # a root, or the trace of one just outside
+    assert pm.domain.xmin <= zmin.real <= pm.domain.xmax and pm.domain.ymin <= zmin.imag <= pm.domain.ymax
+    assert abs(pm.ra.evaluate(zmin)) <= np.min(np.abs(f_appro))
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            pm.plot_dispersion(10, 1000, N=4)
