@@ -274,6 +274,59 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
     }
     int it = 0;
     double prev = INFINITY;
+    if (W::width > 1 && m <= W::width) {
+        // Small systems (the common case: m <= 10 for 20 samples): lane L owns entry L of the right-hand side in
+        // registers and the pivot entry is broadcast with shuffles -- the same operations in the same order as
+        // the general loop below (bit-identical results) without its store / warp barrier / load per step.
+        const bool own = lane < m;
+        cx bl = own ? b[lane] : cx(0.0, 0.0);
+        for (; it < 80; ++it) {
+            PSI_STAT(1, 1);
+            cx yl(0.0, 0.0);
+#pragma unroll 1
+            for (int j = 0; j < m; ++j) {                      // R^H y = b
+                const cx rj = rinv[j];
+                const cx yj = cx(W::bcast(bl.re, j), W::bcast(bl.im, j)) * cx(rj.re, -rj.im);
+                if (lane == j) yl = yj;
+                if (own && lane > j) {
+                    const cx rji = Rm[j + (size_t)lane * m];
+                    bl = bl - cx(rji.re, -rji.im) * yj;
+                }
+            }
+            {
+                const double n2 = a_max<W>(own ? fabs(yl.re) + fabs(yl.im) : 0.0);
+                const double sc = n2 > 0.0 ? 1.0 / n2 : 1.0;
+                bl = cx(yl.re * sc, yl.im * sc);
+            }
+#pragma unroll 1
+            for (int j = m - 1; j >= 0; --j) {                 // R z = b
+                const cx zj = cx(W::bcast(bl.re, j), W::bcast(bl.im, j)) * rinv[j];
+                if (lane == j) yl = zj;
+                if (lane < j) bl = bl - Rm[lane + (size_t)j * m] * zj;
+            }
+            const double n2 = a_max<W>(own ? fabs(yl.re) + fabs(yl.im) : 0.0);
+            const double s1 = n2 > 0.0 ? 1.0 / n2 : 1.0;
+            double q2 = 0.0;
+            if (own) {
+                const cx v(yl.re * s1, yl.im * s1);
+                q2 += v.re * v.re + v.im * v.im;
+            }
+            q2 = a_sum<W>(q2);
+            const double sc = s1 / sqrt(q2);
+            double d2 = 0.0;
+            if (own) {
+                const cx v(yl.re * sc, yl.im * sc);
+                const cx dv = v - w[lane];
+                d2 += dv.re * dv.re + dv.im * dv.im;
+                w[lane] = v; bl = v;
+            }
+            d2 = a_sum<W>(d2);
+            if (d2 <= 1.0e-24 || (d2 <= 1.0e-12 && d2 > 0.25 * prev)) { ++it; break; }
+            prev = d2;
+        }
+        W::sync();
+        return it;
+    }
     for (; it < 80; ++it) {
         PSI_STAT(1, 1);
         // R^H y = b  (forward; L_ij = conj(R_ji), row j of R is strided in memory)

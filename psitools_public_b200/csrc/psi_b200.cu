@@ -62,6 +62,7 @@ struct WarpCuda {
         }
     }
     static __device__ __forceinline__ void sync() { __syncwarp(); }
+    static __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
     static __device__ __forceinline__ unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
     static __device__ __forceinline__ int popc(unsigned v) { return __popc(v); }
     static __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }

@@ -24,6 +24,7 @@ struct WarpOne {
     static double sum(double v) { return v; }
     static double max(double v) { return v; }
     static void sync() {}
+    static double bcast(double v, int) { return v; }
     static unsigned ballot(bool p) { return p ? 1u : 0u; }
     static int popc(unsigned v) { return __builtin_popcount(v); }
     static void sum4c(double (&)[4], double (&)[4]) {}
