@@ -11,6 +11,7 @@ not depend on the schedule.
 """
 import os
 import time
+from operator import itemgetter
 
 import numpy as np
 
@@ -20,6 +21,8 @@ from .psi_mode import ModeTrace, PSIMode
 
 
 DEFAULT_ENGINE = "device"
+_GET_INIT, _GET_CALC, _GET_SEED = itemgetter('__init__'), itemgetter('calculate'), itemgetter('random_seed')
+_GET_KX, _GET_KZ = itemgetter('wave_number_x'), itemgetter('wave_number_z')
 
 
 def _fingerprint(obj, depth=0):
@@ -127,23 +130,30 @@ class MpiScheduler:
         None if an item needs the general (Python) path.  Returns (root matrix, root counts, stats)."""
         if not mine:
             return (np.zeros((0, 1), dtype=np.complex128), np.zeros(0, dtype=np.int64)), {}
+        # One C-speed pass per field (map + itemgetter) instead of Python loops over the items: on a 256^2 map
+        # the arg-dict handling was 30-50 ms of a 0.3 s batch.
+        sub = [arglist[i] for i in mine] if len(mine) != len(arglist) else arglist
+        n = len(sub)
         # PSIMode per distinct '__init__' (by identity first: map scripts share one dict between items)
-        by_id, pms, which = {}, [], np.empty(len(mine), dtype=np.int64)
-        for k, i in enumerate(mine):
-            init = arglist[i]['__init__']
-            j = by_id.get(id(init))
-            if j is None:
-                pm = self._cache.get(init)
-                for j, known in enumerate(pms):
-                    if known is pm:
-                        break
-                else:
-                    pms.append(pm)
-                    j = len(pms) - 1
-                by_id[id(init)] = j
-            which[k] = j
-        calc = [arglist[i]['calculate'] for i in mine]
-        if any(pm.verbose_flag for pm in pms) or any(c.get('count_roots', False) for c in calc):
+        inits = list(map(_GET_INIT, sub))
+        ids = np.fromiter(map(id, inits), dtype=np.int64, count=n)
+        uniq, first, inverse = np.unique(ids, return_index=True, return_inverse=True)
+        pms, slot = [], np.empty(len(uniq), dtype=np.int64)
+        for u, k in enumerate(first.tolist()):
+            pm = self._cache.get(inits[k])
+            for j, known in enumerate(pms):
+                if known is pm:
+                    break
+            else:
+                pms.append(pm)
+                j = len(pms) - 1
+            slot[u] = j
+        which = slot[inverse]
+        calc = list(map(_GET_CALC, sub))
+        # items that carry nothing but the two wave numbers (the usual map) need no further passes
+        plain = max(map(len, calc)) == 2
+        if any(pm.verbose_flag for pm in pms) or \
+                (not plain and any(c.get('count_roots', False) for c in calc)):
             return None
         ctx = pms[0].psi_dispersion.ctx
         if any(pm.psi_dispersion.ctx is not ctx for pm in pms) or not hasattr(ctx, "mode_batch"):
@@ -155,8 +165,17 @@ class MpiScheduler:
                        dtype=float)[which]
         n_sample = per_pm(lambda pm: pm.cfg.n_sample, int)
         max_zoom = per_pm(lambda pm: pm.cfg.max_zoom_level, int)
-        guesses = [c.get('guess_roots', ()) for c in calc]
-        n_guess = np.fromiter((len(g) for g in guesses), dtype=np.int64, count=len(calc))
+        if plain:
+            guesses, n_guess = None, np.zeros(n, dtype=np.int64)
+            alpha = np.zeros(n)
+        else:
+            guesses = [c.get('guess_roots', ()) for c in calc]
+            n_guess = np.fromiter(map(len, guesses), dtype=np.int64, count=n)
+            alpha = np.fromiter((c.get('viscous_alpha', 0) for c in calc), dtype=float, count=n)
+        try:
+            seeds = np.fromiter(map(_GET_SEED, sub), dtype=np.int64, count=n)
+        except KeyError:
+            seeds = np.fromiter((a.get('random_seed', 0) for a in sub), dtype=np.int64, count=n)
         device = self.engine == "device"
         if device:      # the device AAA holds at most 512 samples per search
             most = int(np.max(n_sample*(1 + n_guess + 4*max_zoom)))
@@ -167,12 +186,10 @@ class MpiScheduler:
                               "device AAA): running the batch with engine='native'" % most)
         (roots, nr), ncalls, st = ctx.mode_batch(
             per_pm(lambda pm: pm.psi_dispersion.dist_id, int),
-            np.fromiter((c['wave_number_x'] for c in calc), dtype=float, count=len(calc)),
-            np.fromiter((c['wave_number_z'] for c in calc), dtype=float, count=len(calc)),
-            np.fromiter((c.get('viscous_alpha', 0) for c in calc), dtype=float, count=len(calc)),
+            np.fromiter(map(_GET_KX, calc), dtype=float, count=n),
+            np.fromiter(map(_GET_KZ, calc), dtype=float, count=n), alpha,
             dom, n_sample, max_zoom, per_pm(lambda pm: pm.cfg.max_secant_iterations, int),
-            per_pm(lambda pm: pm.cfg.tol), per_pm(lambda pm: pm.cfg.clean_tol),
-            np.fromiter((arglist[i].get('random_seed', 0) for i in mine), dtype=np.int64, count=len(mine)),
+            per_pm(lambda pm: pm.cfg.tol), per_pm(lambda pm: pm.cfg.clean_tol), seeds,
             guesses if n_guess.any() else None, device_aaa=device, dense=True)
         st["function_calls"] = int(np.sum(ncalls))
         return (roots, nr), st
