@@ -22,8 +22,12 @@ namespace psi {
 // test-harness counters: fits, inverse iterations, -, Aberth calls, Aberth iterations
 static long long g_aaa_stats[8];
 #define PSI_STAT(i, n) (g_aaa_stats[i] += (n))
+// test-harness switch: run the general (memory) form of the triangular solves also for small systems
+static bool g_aaa_general_solves = false;
+#define PSI_GENERAL_SOLVES g_aaa_general_solves
 #else
 #define PSI_STAT(i, n)
+#define PSI_GENERAL_SOLVES false
 #endif
 
 // Out-of-line copies of the small helpers.  The analysis kernel is instruction-fetch bound (ncu: 83 % of
@@ -274,7 +278,7 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
     }
     int it = 0;
     double prev = INFINITY;
-    if (W::width > 1 && m <= W::width) {
+    if (W::width > 1 && m <= W::width && !PSI_GENERAL_SOLVES) {
         // Small systems (the common case: m <= 10 for 20 samples): lane L owns entry L of the right-hand side in
         // registers and the pivot entry is broadcast with shuffles -- the same operations in the same order as
         // the general loop below (bit-identical results) without its store / warp barrier / load per step.

@@ -6,7 +6,10 @@
 // the oracle.  Built by tests/hostsim_util.py into tests/hostsim/_build/, never loaded by the
 // psitools_public_b200 package, and not a fallback: the product library fails with PSI_ERR_NODEVICE
 // when no GPU is present.
+#include <pthread.h>
+
 #include <string>
+#include <thread>
 #include <vector>
 
 #define PSI_AAA_STATS 1
@@ -30,6 +33,59 @@ struct WarpOne {
     static void sum4c(double (&)[4], double (&)[4]) {}
     static bool any(bool p) { return p; }
     static void argmax(double&, int&) {}
+};
+
+// 32-lane emulation of the device's warp policy (WarpCuda in psi_b200.cu): every lane is a host thread, the
+// shuffles and reductions exchange through a slot array between two barriers, in the butterfly order of the
+// device code.  Slow (a barrier per exchange) but it runs the multi-lane paths of the warp kernels -- lane-strided
+// loops, shuffle broadcasts, ballots -- in the GPU-less container.  Used for single AAA fits only.
+struct WarpEmu {
+    static constexpr int width = 32;
+    static inline thread_local int tl_lane = 0;
+    static inline pthread_barrier_t bar;
+    static inline double slot[32][8];
+    static inline int islot[32];
+    static int lane() { return tl_lane; }
+    static void sync() { pthread_barrier_wait(&bar); }
+    static double bcast(double v, int src) {
+        slot[tl_lane][0] = v; sync();
+        const double r = slot[src][0]; sync();
+        return r;
+    }
+    static double sum(double v) {
+        for (int o = 16; o > 0; o >>= 1) { slot[tl_lane][0] = v; sync(); v += slot[tl_lane ^ o][0]; sync(); }
+        return v;
+    }
+    static double max(double v) {
+        for (int o = 16; o > 0; o >>= 1) { slot[tl_lane][0] = v; sync(); v = fmax(v, slot[tl_lane ^ o][0]); sync(); }
+        return v;
+    }
+    static void sum4c(double (&re)[4], double (&im)[4]) {
+        for (int o = 16; o > 0; o >>= 1) {
+            for (int c = 0; c < 4; ++c) { slot[tl_lane][c] = re[c]; slot[tl_lane][4 + c] = im[c]; }
+            sync();
+            for (int c = 0; c < 4; ++c) { re[c] += slot[tl_lane ^ o][c]; im[c] += slot[tl_lane ^ o][4 + c]; }
+            sync();
+        }
+    }
+    static unsigned ballot(bool p) {
+        islot[tl_lane] = p ? 1 : 0; sync();
+        unsigned m = 0;
+        for (int i = 0; i < 32; ++i) m |= (unsigned)islot[i] << i;
+        sync();
+        return m;
+    }
+    static int popc(unsigned v) { return __builtin_popcount(v); }
+    static bool any(bool p) { return ballot(p) != 0; }
+    static void argmax(double& v, int& idx) {
+        for (int o = 16; o > 0; o >>= 1) {
+            slot[tl_lane][0] = v; islot[tl_lane] = idx; sync();
+            const double ov = slot[tl_lane ^ o][0];
+            const int oi = islot[tl_lane ^ o];
+            sync();
+            if (oi >= 0 && (idx < 0 || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
+        }
+    }
 };
 
 // test stand-in for the library's context
@@ -99,6 +155,35 @@ int psi_internal_polish(psi_ctx* c, int n_items, const int* pidx, int n_params, 
     return PSI_OK;
 }
 
+// >1: psi_internal_mode_device runs every search on 32 emulated lanes (WarpEmu) instead of one lane
+static int g_mode_lanes = 1;
+
+static int mode_run_emulated(psi_ctx* c, int dist, double kx, double kz, double alpha, const ModeCfg& cfg,
+                             const cx* guesses, int ng, const double* uni, int cap, cx* roots, int max_roots,
+                             int* nr_out, int* nc_out, long long* evals) {
+    std::vector<unsigned char> buf(aaa_scratch_bytes(cap));
+    const AAAScratch sc = aaa_carve(buf.data(), cap);
+    pthread_barrier_init(&WarpEmu::bar, nullptr, 32);
+    int status = 0;
+    std::vector<std::thread> lanes;
+    std::vector<cx> lane_roots((size_t)32 * max_roots);       // every lane keeps its own copy of the outputs
+    for (int l = 0; l < 32; ++l)
+        lanes.emplace_back([&, l]() {
+            WarpEmu::tl_lane = l;
+            WarpEval<WarpEmu> ev;
+            ev.t = &c->view; ev.d = &c->dists[dist]; ev.kx = kx; ev.kz = kz; ev.alpha = alpha; ev.nodes = 0; ev.evals = 0;
+            int nr = 0, nc = 0;
+            const int st = mode_run<WarpEmu>(ev, cfg, guesses, ng, uni, sc, lane_roots.data() + (size_t)l * max_roots,
+                                             max_roots, &nr, &nc);
+            WarpEmu::sync();
+            if (l == 0) { status = st; *nr_out = nr; *nc_out = nc; *evals = ev.evals; }
+        });
+    for (auto& t : lanes) t.join();
+    pthread_barrier_destroy(&WarpEmu::bar);
+    for (int k = 0; k < max_roots; ++k) roots[k] = lane_roots[k];
+    return status;
+}
+
 int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const double* kx, const double* kz,
                              const double* alpha, const double* domain, const int* iparams,
                              const double* dparams, const double* uni, long long n_uni, const int* uni_off,
@@ -106,6 +191,23 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
                              double* roots, int* n_roots, int* n_calls, int* status, long long* stats) {
     (void)n_uni;
     long long total = 0;
+    if (g_mode_lanes > 1) {
+        for (int i = 0; i < n_items; ++i) {
+            ModeCfg cfg;
+            cfg.dom = RectDom{domain[4 * i], domain[4 * i + 1], domain[4 * i + 2], domain[4 * i + 3]};
+            cfg.n_sample = iparams[3 * i]; cfg.max_zoom = iparams[3 * i + 1]; cfg.max_secant = iparams[3 * i + 2];
+            cfg.tol = dparams[2 * i]; cfg.clean_tol = dparams[2 * i + 1];
+            const int g0 = guess_off[i], ng = guess_off[i + 1] - g0;
+            long long ev_n = 0;
+            status[i] = mode_run_emulated(c, dist[i], kx[i], kz[i], alpha[i], cfg,
+                                          reinterpret_cast<const cx*>(guesses) + g0, ng, uni + uni_off[i], cap,
+                                          reinterpret_cast<cx*>(roots) + (size_t)i * max_roots, max_roots,
+                                          &n_roots[i], &n_calls[i], &ev_n);
+            total += ev_n;
+        }
+        if (stats) { stats[0] = 1; stats[1] = total; stats[2] = 0; }
+        return PSI_OK;
+    }
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
     for (int i = 0; i < n_items; ++i) {
         with_eval(c, dist[i], kx[i], kz[i], alpha[i], [&](auto& ev) {
@@ -151,6 +253,45 @@ int hs_aaa_fit(int M, const double* Z, const double* F, const int* mask, double*
     *resid = aaa_fit<WarpOne>(sc, st);
     for (int j = 0; j < st.m; ++j) { w_out[2 * j] = sc.w[j].re; w_out[2 * j + 1] = sc.w[j].im; }
     return st.m;
+}
+
+void hs_set_mode_lanes(int lanes) { g_mode_lanes = lanes; }
+
+// The same fit run by 32 emulated lanes (WarpEmu); general_solves != 0 forces the memory form of the inverse
+// iteration's triangular solves, which must give bit-identical weights to the register form.
+int hs_aaa_fit_warp(int M, const double* Z, const double* F, const int* mask, double* w_out, double* resid,
+                    int general_solves) {
+    std::vector<unsigned char> buf(aaa_scratch_bytes(M));
+    const AAAScratch sc = aaa_carve(buf.data(), M);
+    double fm = 0.0;
+    for (int i = 0; i < M; ++i) {
+        sc.Z[i] = cx(Z[2 * i], Z[2 * i + 1]); sc.F[i] = cx(F[2 * i], F[2 * i + 1]); sc.mask[i] = mask[i];
+        fm = fmax(fm, abs_c(sc.F[i]));
+    }
+    g_aaa_general_solves = general_solves != 0;
+    pthread_barrier_init(&WarpEmu::bar, nullptr, 32);
+    int m_out = 0;
+    double res_out = 0.0;
+    std::vector<std::thread> lanes;
+    for (int l = 0; l < 32; ++l)
+        lanes.emplace_back([&, l]() {
+            WarpEmu::tl_lane = l;
+            AAAState st;                      // per lane, like the registers of a device thread
+            st.M = M; st.m = 0; st.r = 0; st.tol = 1e-13; st.clean_tol = 1e-4;
+            st.dom = RectDom{-1e300, 1e300, -1e300, 1e300};
+            st.memo_next = 0; st.slot = 0; st.v_m = 0; st.fmax = fm;
+            aaa_memo_clear<WarpEmu>(sc, st);
+            WarpEmu::sync();
+            const double r = aaa_fit<WarpEmu>(sc, st);
+            WarpEmu::sync();
+            if (l == 0) { m_out = st.m; res_out = r; }
+        });
+    for (auto& t : lanes) t.join();
+    pthread_barrier_destroy(&WarpEmu::bar);
+    g_aaa_general_solves = false;
+    *resid = res_out;
+    for (int j = 0; j < m_out; ++j) { w_out[2 * j] = sc.w[j].re; w_out[2 * j + 1] = sc.w[j].im; }
+    return m_out;
 }
 
 // the per-pixel sweep logic of csrc/psi_refine.cuh over a whole map: nk[p] = guesses pixel p runs with (0 = it

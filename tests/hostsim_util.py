@@ -24,7 +24,7 @@ def build(force=False):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-fopenmp",
-                           "-x", "c++", "-o", OUT, SRC, "-ldl"])
+                           "-x", "c++", "-o", OUT, SRC, "-ldl", "-lpthread"])
     return OUT
 
 

@@ -90,6 +90,92 @@ def test_aaa_weights_against_numpy_svd(M, m, seed):
     assert abs(abs(np.vdot(wref, w)) - 1.0) < 1e-10 + 1e-14/max(gap, 1e-16), (abs(np.vdot(wref, w)), gap)
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("M,m,seed", [(20, 3, 0), (20, 7, 1), (20, 10, 7), (20, 11, 2), (40, 21, 6), (100, 40, 8)])
+def test_aaa_fit_on_32_emulated_lanes(M, m, seed):
+    """The warp form of the Loewner fit (lane-strided Householder QR, butterfly reductions, and -- for m <= 32 --
+    the inverse iteration whose right-hand side lives in registers with the pivot entry broadcast by shuffle)
+    run by 32 emulated lanes (tests/hostsim/hostsim.cpp: WarpEmu): (a) the register form and the general
+    (memory) form of the triangular solves give BIT-IDENTICAL weights -- the claim behind enabling the
+    register form on the device; (b) the weights satisfy the same numpy-SVD checks as the one-lane run;
+    (c) for m > 32 the general form is what runs."""
+    import ctypes as C
+    rng = np.random.RandomState(seed)
+    Z = rng.uniform(-2, 2, M) + 1j*rng.uniform(1e-3, 1, M)
+    poles = rng.uniform(-3, 3, 40) + 1j*rng.uniform(-2, 2, 40)
+    res = rng.normal(size=40) + 1j*rng.normal(size=40)
+    F = 1e7*(np.sum(res[None, :]/(Z[:, None] - poles[None, :]), axis=1) + np.exp(1j*Z))
+    mask = np.zeros(M, dtype=bool)
+    mask[rng.choice(M, m, replace=False)] = True
+    lib = hs.lib()
+    Zc, Fc, mc = np.ascontiguousarray(Z), np.ascontiguousarray(F), np.ascontiguousarray(mask, dtype=np.int32)
+    out = {}
+    for general in (0, 1):
+        w = np.zeros(m, dtype=np.complex128)
+        resid = C.c_double(0.0)
+        got_m = lib.hs_aaa_fit_warp(M, Zc.ctypes.data_as(C.c_void_p), Fc.ctypes.data_as(C.c_void_p),
+                                    mc.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p),
+                                    C.byref(resid), general)
+        assert got_m == m
+        out[general] = (w, resid.value)
+    assert np.array_equal(out[0][0].view(np.float64), out[1][0].view(np.float64))     # bit for bit
+    assert out[0][1] == out[1][1]
+    w = out[0][0]
+    A = _loewner(Z, F, mask)
+    sv = np.linalg.svd(A, compute_uv=False)
+    assert abs(np.linalg.norm(w) - 1.0) < 1e-12
+    fit = np.linalg.norm(A @ w)
+    if M - m < m:
+        assert fit <= 1e-12*sv[0]
+        return
+    wref = np.linalg.svd(A)[2][-1].conj()
+    assert fit <= sv[-1]*(1 + 1e-8) + 1e-15*sv[0]
+    gap = (sv[-2] - sv[-1])/sv[0]
+    assert abs(abs(np.vdot(wref, w)) - 1.0) < 1e-10 + 1e-14/max(gap, 1e-16)
+
+
+@pytest.mark.timeout(600)
+def test_mode_search_on_32_emulated_lanes(hostsim_backend):
+    """Whole PSIMode searches (psi_mode.cuh: mode_run = sampling, K1, AAA analysis, Ehrlich-Aberth zeros,
+    cleanup, zoom domains, secant polish) run by 32 emulated lanes -- the multi-lane code paths of kernels
+    K1/K3/K4 (lane-strided loops, butterfly reductions, ballots, shuffle broadcasts) executed on the CPU.
+    Against the one-lane run of the same code: same number of roots and of D evaluations, roots equal to
+    rounding; against the reference's goldens (test_psi_mode.py:53-67, :136-150): 1e-8."""
+    import time
+    from psitools_public_b200 import PowerBump, SizeDensity, TanhSinhNoDeepCopy, psi_mode_mpi
+    ts = TanhSinhNoDeepCopy()
+    pb = PowerBump(amin=1e-8, aP=0.1, aL=2.0/3.0*0.1, aR=0.156, bumpfac=2.0)
+    sd = SizeDensity(pb.sigma0, [1e-8, 0.156])
+    sd.poles = [pb.get_discontinuity()]
+    base = {'real_range': [-2, 2], 'imag_range': [1e-8, 1], 'tanhsinh_integrator': ts}
+    items = [
+        {'__init__': dict(base, stokes_range=[1e-8, 1e-2], dust_to_gas_ratio=3.0),
+         'calculate': {'wave_number_x': 10, 'wave_number_z': 1000}, 'random_seed': 0},
+        {'__init__': dict(base, stokes_range=[1e-8, 1.0], dust_to_gas_ratio=3.0),
+         'calculate': {'wave_number_x': 0.1, 'wave_number_z': 10}, 'random_seed': 0},
+        {'__init__': dict(base, stokes_range=[1e-8, 0.156], dust_to_gas_ratio=10.0, size_density=sd, n_sample=15),
+         'calculate': {'wave_number_x': 200, 'wave_number_z': 1000,
+                       'guess_roots': [0.3 + 0.05j]}, 'random_seed': 0}]
+    out = {}
+    try:
+        for lanes in (1, 32):
+            hs.lib().hs_set_mode_lanes(lanes)
+            ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False)
+            res = ms.run_all(items)
+            assert ms.last_stats["engine"] == "device"
+            out[lanes] = ([np.sort_complex(np.asarray(res[i])) for i in range(len(items))], ms.last_stats["evals"])
+    finally:
+        hs.lib().hs_set_mode_lanes(1)
+    assert out[1][1] == out[32][1]                                       # same number of D evaluations
+    for a, b in zip(out[1][0], out[32][0]):
+        assert len(a) == len(b)
+        assert np.all(np.abs(a - b) <= 1e-11*np.abs(a))
+    gold = [-1.0062579942546936 + 1.3209787635623396e-05j, -1.004879704650626 + 0.0008946325671658642j]
+    for r, g in zip(out[32][0], gold):
+        assert len(r) == 1 and abs(r[0] - g) <= 1e-8*abs(g)
+    assert len(out[32][0][2]) >= 1
+
+
 def test_exit_predictor_against_literal_rule(ts):
     """The level loop's convergence predictor (csrc/psi_quad.cuh: stop once the last two increments show the
     quadratic collapse of the tanh-sinh rule and the extrapolated next one is 1e4 below the tolerance)
