@@ -196,7 +196,7 @@ class ClockSampler:
             os.close(fd)
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -288,14 +288,14 @@ def run_b200(args):
 
     fp64_peak = ctx.measure_fp64_peak(5) if rank == 0 else None
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # before the warm-up: nvidia-smi needs tens of ms to come up
     for _ in range(args.warmup):
         step_resident()
     barrier()
     nodes_dev.zero_()
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
@@ -310,11 +310,21 @@ def run_b200(args):
         kev[i][1].record(stream)
     ev[1].record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count - launches0
     ms_total = ev[0].elapsed_time(ev[1])
     ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     node_evals = int(nodes_dev.item())
+    clocks = None
+    if rank == 0:
+        # K steps of ~6 ms are over before nvidia-smi (50 ms period) has sampled twice: keep the GPU under the
+        # SAME load (the same step, untimed) a little longer so that the clocks line has samples under this load
+        t_hold = time.perf_counter()
+        while time.perf_counter() - t_hold < 0.35:
+            step_resident()
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
+        clocks["window"] = ("warm-up + timed steps + the same step repeated untimed for 0.35 s "
+                            "(nvidia-smi -lms 50)")
     D_resident = D_dev.cpu().numpy().view(np.complex128)
 
     # the same steps under the reference's LITERAL exit rule (tanhsinh.py:120-126), for the record: the
