@@ -100,9 +100,37 @@ struct psi_ctx {
 static std::string g_err;
 int psi_internal_fail(int code, const std::string& msg) { g_err = msg; return code; }
 
+// >1: hs_disp_eval runs every point on 32 emulated lanes (the warp form of K1) instead of one lane
+static int g_eval_lanes = 1;
+
 static void eval_points(psi_ctx* c, long long n, const int* pidx, const int* dist, const double* kx,
                         const double* kz, const double* alpha, const double* w, double* D, double* M) {
     unsigned long long total = 0;
+    if (g_eval_lanes > 1) {
+        for (long long i = 0; i < n; ++i) {
+            const long long pi = pidx ? pidx[i] : i;
+            pthread_barrier_init(&WarpEmu::bar, nullptr, 32);
+            std::vector<std::thread> lanes;
+            for (int l = 0; l < 32; ++l)
+                lanes.emplace_back([&, l]() {
+                    WarpEmu::tl_lane = l;
+                    unsigned long long nodes = 0;
+                    cx m[7];
+                    const cx v = disp_eval_any<WarpEmu>(c->view, c->dists[dist[pi]], cx(w[2 * i], w[2 * i + 1]),
+                                                        kx[pi], kz[pi], alpha[pi], m, nodes);
+                    WarpEmu::sync();
+                    if (l == 0) {
+                        D[2 * i] = v.re; D[2 * i + 1] = v.im;
+                        if (M) for (int k = 0; k < 7; ++k) { M[14 * i + 2 * k] = m[k].re; M[14 * i + 2 * k + 1] = m[k].im; }
+                        total += nodes;
+                    }
+                });
+            for (auto& t : lanes) t.join();
+            pthread_barrier_destroy(&WarpEmu::bar);
+        }
+        c->nodes += total;
+        return;
+    }
 #pragma omp parallel for schedule(dynamic, 8) reduction(+ : total)
     for (long long i = 0; i < n; ++i) {
         const long long pi = pidx ? pidx[i] : i;
@@ -256,6 +284,7 @@ int hs_aaa_fit(int M, const double* Z, const double* F, const int* mask, double*
 }
 
 void hs_set_mode_lanes(int lanes) { g_mode_lanes = lanes; }
+void hs_set_eval_lanes(int lanes) { g_eval_lanes = lanes; }
 
 // The same fit run by 32 emulated lanes (WarpEmu); general_solves != 0 forces the memory form of the inverse
 // iteration's triangular solves, which must give bit-identical weights to the register form.

@@ -23,7 +23,17 @@ def test_background(ts):
         assert abs(b["vgy"] - g["vgy"]) <= 2e-14*abs(g["vgy"]), name
 
 
-def test_disp_eval(ts):
+@pytest.fixture(params=[1, 32])
+def eval_lanes(request):
+    """K1's arithmetic on one lane and on 32 emulated lanes (WarpEmu: the lane-strided level loop, the node
+    pairs per lane and the butterfly reductions of the warp kernel, run by host threads)."""
+    hs.lib().hs_set_eval_lanes(request.param)
+    yield request.param
+    hs.lib().hs_set_eval_lanes(1)
+
+
+@pytest.mark.timeout(900)
+def test_disp_eval(ts, eval_lanes):
     bg = load("background.json")
     for case in load("disp.json")["cases"]:
         spec = bg[case["dist"]]["spec"]
