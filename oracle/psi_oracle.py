@@ -646,19 +646,20 @@ class Mode:
         self.n_function_call += self.n_sample
 
     def _polish(self, starts, max_iter, initial_iterations=5):
-        """psi_mode.py:411-491 applied to the whole array of starts (the xtol uses ALL of them)."""
+        """psi_mode.py:340-352 + 411-491: find_dispersion_roots calls find_root with ONE scalar at a time, so
+        the xtol of :438-444 / :460-464 looks only at the current start (or its restart point)."""
         w0 = np.ravel(np.asarray(starts, dtype=complex)).copy()
         ret = 0*w0
         for i in range(len(w0)):
             eps = 1.0e-6
-            xtol = np.min(np.hstack([[1.48e-8], np.abs(w0.imag*1e-5)]))
+            xtol = np.min(np.hstack([[1.48e-8], np.abs(w0[i:i + 1].imag*1e-5)]))
             z = secant(self.disp, w0[i], offset_start(w0[i], eps), maxiter=initial_iterations,
                        xtol=xtol)
             self.n_function_call += z.function_calls
             if (not z.converged and np.abs(z.root - w0[i])/np.abs(w0[i]) < 1
                     and max_iter > initial_iterations):
                 w0[i] = z.root
-                xtol = np.min(np.hstack([[1.48e-8], np.abs(w0.imag*1e-5)]))
+                xtol = np.min(np.hstack([[1.48e-8], np.abs(w0[i:i + 1].imag*1e-5)]))
                 z = secant(self.disp, w0[i], offset_start(w0[i], eps), maxiter=max_iter,
                            xtol=xtol)
                 self.n_function_call += z.function_calls

@@ -85,27 +85,27 @@ PSI_NOINLINE SecantOut secant_run(EVAL& f, cx x0, cx x1, int maxiter, double xto
 
 // Polish `n` start values one after the other (psi_mode.py:340-352 + 411-491): five iterations first;
 // if that has not converged but stayed within |start| of the start, continue from there for up to
-// max_iter.  The step tolerance min(1.48e-8, 1e-5*min|Im start|) looks at ALL current start values
-// (restart points of earlier ones included).  w0[] is updated in place with the restart points;
-// out[i] receives the root, or the sentinel -1j when the iteration failed or left the domain.
-// Returns the number of dispersion evaluations (PSIMode.n_function_call increment); status 1 = the
-// reference would raise ValueError (a start value on the real axis makes the tolerance zero).
+// max_iter.  The step tolerance is min(1.48e-8, 1e-5*|Im start_i|) of THIS start value alone
+// (find_dispersion_roots hands find_root one scalar at a time, psi_mode.py:340-352, so the w0 array of
+// :438-444 has a single element) and of its restart point after a restart (:455-464).  w0[] is updated in
+// place with the restart points; out[i] receives the root, or the sentinel -1j when the iteration failed or
+// left the domain.  Returns the number of dispersion evaluations (PSIMode.n_function_call increment);
+// status 1 = the reference would raise ValueError (this start value lies on the real axis, which makes
+// its tolerance zero).
 template <class EVAL>
 PSI_NOINLINE int polish_run(EVAL& f, const RectDom& dom, cx* w0, int n, int max_iter, cx* out, int* max_conv_iter,
                       int* status) {
     int calls = 0;
     *status = 0;
     for (int i = 0; i < n; ++i) {
-        double xtol = 1.48e-8;
-        for (int k = 0; k < n; ++k) xtol = fmin(xtol, fabs(w0[k].im * 1e-5));
-        if (!(xtol > 0.0)) { *status = 1; return calls; }
         const cx start = w0[i];
+        double xtol = fmin(1.48e-8, fabs(start.im * 1e-5));
+        if (!(xtol > 0.0)) { *status = 1; return calls; }
         SecantOut r = secant_run(f, start, second_point(start, 1.0e-6), 5, xtol);
         calls += r.calls;
         if (!r.converged && abs_c(r.root - start) / abs_c(start) < 1.0 && max_iter > 5) {
             w0[i] = r.root;
-            xtol = 1.48e-8;
-            for (int k = 0; k < n; ++k) xtol = fmin(xtol, fabs(w0[k].im * 1e-5));
+            xtol = fmin(1.48e-8, fabs(r.root.im * 1e-5));
             if (!(xtol > 0.0)) { *status = 1; return calls; }
             r = secant_run(f, w0[i], second_point(w0[i], 1.0e-6), max_iter, xtol);
             calls += r.calls;

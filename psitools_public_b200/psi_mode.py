@@ -159,25 +159,27 @@ def mode_machine(cfg, guess_roots=(), count_roots=False, rng=None, trace=None, l
 
 
 def polish_machine(cfg, starts, max_iter, trace, say=lambda *a: None, initial_iterations=5,
-                   select_inside_domain=True):
+                   select_inside_domain=True, per_start=True, keep_all=False):
     """Secant polish of every start value on the exact dispersion relation, one after the other
     (reference psi_mode.py:340-352, 411-491): five iterations first; if that has not converged but
     stayed within |start| of the start, continue from there for up to ``max_iter``.  Failed or
-    outside-domain results are dropped.  The step tolerance min(1.48e-8, 1e-5*min|Im start|) looks
-    at ALL current start values, including restart points of earlier ones."""
+    outside-domain results are dropped.  ``per_start=True`` (find_dispersion_roots, which hands find_root
+    one scalar at a time): the step tolerance min(1.48e-8, 1e-5*|Im start|) is that of the current start
+    value alone, and of its restart point after a restart; ``per_start=False`` (the public find_root called
+    with an array, :438-444): the minimum runs over the whole current start array."""
     w0 = np.atleast_1d(np.asarray(starts, dtype=complex)).ravel().copy()
     out = np.zeros(len(w0), dtype=complex)
     eps = 1.0e-6
     for i in range(len(w0)):
         say('Starting iteration at z = {}'.format(w0[i]))
-        xtol = np.min(np.hstack([[1.48e-8], np.abs(w0.imag*1e-5)]))
+        xtol = np.min(np.hstack([[1.48e-8], np.abs((w0[i:i + 1] if per_start else w0).imag*1e-5)]))
         res = yield from cr.secant_machine(w0[i], cr.second_point(w0[i], eps), initial_iterations, xtol)
         trace.n_function_call += res.function_calls
         if (not res.converged and np.abs(res.root - w0[i])/np.abs(w0[i]) < 1
                 and max_iter > initial_iterations):
             say("Starting further iteration")
             w0[i] = res.root
-            xtol = np.min(np.hstack([[1.48e-8], np.abs(w0.imag*1e-5)]))
+            xtol = np.min(np.hstack([[1.48e-8], np.abs((w0[i:i + 1] if per_start else w0).imag*1e-5)]))
             res = yield from cr.secant_machine(w0[i], cr.second_point(w0[i], eps), max_iter, xtol)
             trace.n_function_call += res.function_calls
         elif not res.converged:
@@ -188,6 +190,8 @@ def polish_machine(cfg, starts, max_iter, trace, say=lambda *a: None, initial_it
             out[i] = res.root
         else:
             out[i] = -1j                      # sentinel, outside every search rectangle
+    if keep_all:
+        return out
     return out[np.asarray(cfg.domain.is_in(out)).nonzero()]
 
 

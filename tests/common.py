@@ -21,6 +21,11 @@ def load(name):
         return json.load(fh)
 
 
+def DISTS_BY_NAME(name):
+    """Distribution spec of a fixture name (the dict make_golden.py's DISTS holds, via background.json)."""
+    return load("background.json")[name]["spec"]
+
+
 def oracle_dist(spec):
     from oracle import psi_oracle as po
     if spec["kind"] == "powerlaw":
@@ -81,6 +86,25 @@ def det_extended(M7, w, kx, kz, alpha, c, vgx):
     a20 = kx*kz*g + e20
     a22 = kz*kz*g + d + e22
     return complex(a11*minor - a01*(a10*a22 - a12*a20))
+
+
+def det_terms_scale(M7, w, kx, kz, alpha, c, vgx):
+    """Sum of the magnitudes of the terms of det(P + M) in the cancellation-free expansion used by det_extended:
+    the natural scale against which an error of D is measured (at a root the terms cancel and |D| itself is no
+    yardstick)."""
+    nu = alpha*c**2
+    r = w - kx*vgx
+    d = kx*vgx - w - 1j*nu*(kx**2 + kz**2)
+    g = c**2/r
+    m = [complex(x) for x in M7]
+    e00, e02 = m[0] - 1j*kx**2*nu/3, m[2] - 1j*kx*kz*nu/3
+    e20, e22 = -1j*kx*kz*nu/3, m[6] - 1j*kz**2*nu/3
+    minor = abs((d + e00)*(d + e22)) + abs(e02*e20) + abs(g)*(kx*kx*abs(d + e22) + kz*kz*abs(d + e00)
+                                                             + kx*kz*abs(e02 + e20))
+    a01, a10, a11, a12 = 2j + m[1], -0.5j + m[3], d + m[4], m[5]
+    a20 = kx*kz*g + e20
+    a22 = kz*kz*g + d + e22
+    return float(abs(a11)*minor + abs(a01)*(abs(a10*a22) + abs(a12*a20)))
 
 
 def lu_noise_floor(w, kx, kz, c, vgx):

@@ -408,7 +408,26 @@ def sec_modegrid16():
     dump("modegrid16.json", dict(axis=list(map(float, ax)), stokes_range=[1e-8, 1.0], seed=2, cases=res))
 
 
-SECTIONS = dict(modegrid16=sec_modegrid16, nodes=sec_nodes, background=sec_background, disp=sec_disp, contour=sec_contour,
+def sec_multistart():
+    """PSIMode searches whose rational approximation has two or three zeros of VERY different Im inside the
+    domain (MRN mu=3, tau in [1e-8, 0.1], seed 2): find_dispersion_roots polishes them one scalar at a time
+    (psi_mode.py:340-352), so each secant run uses the tolerance of its own start, min(1.48e-8, 1e-5*|Im|) --
+    n_function_call pins that (an implementation that takes the minimum over all starts iterates longer)."""
+    import multiprocessing as mp
+    ks = [(0.1, 16.68100537200059), (0.1, 1000.0), (5.994842503189409, 129.15496650148827),
+          (5.994842503189409, 1000.0), (0.774263682681127, 5.994842503189409), (0.774263682681127, 2.1544346900318834)]
+    items = [{'__init__': {'stokes_range': [1e-8, 0.1], 'dust_to_gas_ratio': 3.0, 'size_distribution_power': 3.5,
+                           'real_range': [-2.0, 2.0], 'imag_range': [1e-8, 1.0], 'n_sample': 20,
+                           'max_zoom_domains': 1, 'tol': 1.0e-13, 'clean_tol': 1e-4},
+              'calculate': {'wave_number_x': kx, 'wave_number_z': kz}, 'random_seed': 2} for kx, kz in ks]
+    with mp.get_context("fork").Pool(PROCS) as pool:
+        res = pool.map(_grid_item, items, chunksize=1)
+    for r in res:
+        print(r['kx'], r['kz'], r['roots'], r['n_function_call'])
+    dump("multistart.json", dict(stokes_range=[1e-8, 0.1], seed=2, cases=res))
+
+
+SECTIONS = dict(multistart=sec_multistart, modegrid16=sec_modegrid16, nodes=sec_nodes, background=sec_background, disp=sec_disp, contour=sec_contour,
                 mode=sec_mode, modegrid=sec_modegrid, refine=sec_refine)
 
 if __name__ == "__main__":

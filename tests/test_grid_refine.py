@@ -109,6 +109,104 @@ def test_refiner_against_reference(backend, engine, tmp_path):
                                                            for r in row] for row in final['runs']]))
 
 
+class _Replay:
+    """Scheduler stand-in that answers every run with the roots the UNMODIFIED reference returned for it
+    (refine.json["batches"], in the reference's sweep order) and checks that the product asked for exactly the
+    reference's work list: same pixels in the same order with bit-identical guess lists."""
+
+    def __init__(self, batches):
+        self.batches, self.sweep = batches, 0
+
+    def _next(self, kx, kz, guesses):
+        ref = self.batches[self.sweep]
+        self.sweep += 1
+        assert len(kx) == len(ref), (self.sweep, len(kx), len(ref))
+        for i, r in enumerate(ref):
+            assert kx[i] == r["kx"] and kz[i] == r["kz"], (self.sweep, i)
+            assert np.array_equal(np.asarray(guesses[i], dtype=complex), carr(r["guess"])), (self.sweep, i)
+        return [carr(r["roots"]) for r in ref]
+
+    def run_all(self, arglist):
+        c = [a['calculate'] for a in arglist]
+        assert all(a['random_seed'] == 2 for a in arglist)
+        roots = self._next([x['wave_number_x'] for x in c], [x['wave_number_z'] for x in c],
+                           [x['guess_roots'] for x in c])
+        return dict(enumerate(roots))
+
+    def run_arrays(self, init, kx, kz, seeds, guesses=None, alpha=0.0):
+        n = len(kx)
+        assert np.all(np.broadcast_to(seeds, (n,)) == 2)
+        flat, off = (np.zeros(0, complex), np.zeros(n + 1, int)) if guesses is None else guesses
+        roots = self._next(list(kx), list(kz), [flat[off[i]:off[i + 1]] for i in range(n)])
+        mat = np.zeros((n, max([1] + [len(r) for r in roots])), dtype=complex)
+        for i, r in enumerate(roots):
+            mat[i, :len(r)] = r
+        return mat, np.array([len(r) for r in roots], dtype=np.int64)
+
+
+@pytest.mark.parametrize("path", ["dict", "array"])
+def test_refiner_bookkeeping_replay_is_exact(backend, path):
+    """Bookkeeping separated from numerics (reference psi_grid_refine.py:218-334): the reference's own per-run
+    roots are fed through the product's sweep logic -- candidate pixels, neighbour gathering order, prune_eps,
+    nguess, run ids incl. the re-use of the largest id, merge -- on the dict path, the array path (numpy cell
+    queue on the CPU backend, device cell queue of csrc/psi_refine.cu on the GPU).  Every sweep must ask for the
+    reference's work list bit for bit and the final grid must equal refine.json["final"] EXACTLY."""
+    from psitools_public_b200 import psi_mode_mpi
+    from psitools_public_b200.psi_grid_refine import RootStore
+    gold = load("refine.json")
+    gr, _ = make_refiner("device")
+    replay = _Replay(gold["batches"])
+    if path == "dict":
+        gr.ms = replay                                   # any foreign scheduler takes the dict path
+    else:
+        gr.ms = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False)
+        gr.ms.run_arrays = replay.run_arrays             # stock scheduler, only the solves are replayed
+        assert gr._array_path()
+    gr.run_basegrid()
+    gr.fill_in_grid()
+    assert replay.sweep == len(gold["batches"])          # same number of sweeps, all of them consumed
+    if path == "array":
+        assert isinstance(gr.grids[-1]['results'], RootStore)
+        assert ('_dev' in gr.__dict__) == (backend == "gpu")     # on the GPU the cell queue came from the device
+    final, gfin = gr.grids[-1], gold["final"]
+    assert np.array_equal(final['Kx'], np.array(gfin['Kx'])) and np.array_equal(final['Kz'], np.array(gfin['Kz']))
+    assert np.array_equal(final['runs'], np.array(gfin['runs']))
+    assert np.array_equal(final['nguess'], np.array(gfin['nguess']))
+    assert sorted(final['results']) == sorted(int(k) for k in gfin['results'])
+    for k, v in gfin['results'].items():
+        assert np.array_equal(np.asarray(final['results'][int(k)]), carr(v)), k
+    # per-pixel view: all 49 pixels show the reference's root lists
+    ref_results = {int(k): carr(v) for k, v in gfin["results"].items()}
+    for (iz, ix), r in np.ndenumerate(np.array(gfin['runs'])):
+        from psitools_public_b200.psi_grid_refine import get_if
+        assert np.array_equal(np.array(get_if(final['results'], final['runs'][iz, ix]), dtype=complex),
+                              np.array(get_if(ref_results, r), dtype=complex)), (iz, ix)
+
+
+def test_refine_fixture_divergence_is_a_knife_edge(hostsim_backend):
+    """Attribution of the 2 of 49 pixels on which the product's campaign differs from refine.json.
+    The first run that departs from the reference's log is run 2 of the third batch, K = (11.22, 8.61) with two
+    guesses: the reference reports the marginal root 0.17918+6.7e-5j, the product with the SAME guesses none.  The
+    outcome of that run flips when the guess roots are changed in the 14th digit -- far below the 1e-8 at which
+    polished roots are defined and below the 2.5e-10 error of the reference's own LU determinant on this run's
+    samples (tests/truth_mp.py) -- so no implementation that evaluates D independently can be pinned to it."""
+    from psitools_public_b200 import PSIMode
+    gold = load("refine.json")
+    b = gold["batches"][2][2]
+    gr, _ = make_refiner("python")
+    init = dict(gr.baseargs['__init__'], max_zoom_domains=0)
+    g0 = carr(b["guess"])
+    rng = np.random.RandomState(0)
+    found = []
+    for trial in range(10):
+        g = [z*(1 + 1e-14*rng.standard_normal()) for z in g0] if trial else list(g0)
+        np.random.seed(2)
+        r = PSIMode(**init).calculate(wave_number_x=b["kx"], wave_number_z=b["kz"], guess_roots=g)
+        assert all(abs(z - carr(b["roots"])[0]) < 1e-8 for z in r)        # when found, it is the reference's root
+        found.append(len(r))
+    assert 0 < sum(n > 0 for n in found) < len(found), found               # both outcomes occur
+
+
 def test_spreadgrid_and_prune():
     from psitools_public_b200.psi_grid_refine import prune_eps, spreadgrid
     kz, kx = np.meshgrid(np.logspace(0, 1, 3), np.logspace(0, 2, 4), indexing='ij')

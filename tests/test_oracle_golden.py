@@ -104,3 +104,21 @@ def test_mode_matches_reference(tab):
         pin = cplx(case["pin"])                       # golden pasted in test_psi_mode.py, rtol 1e-7
         np.testing.assert_allclose(roots[0].real, pin.real, rtol=1e-7)
         np.testing.assert_allclose(roots[0].imag, pin.imag, rtol=1e-7)
+
+
+def test_multistart_polish_matches_reference(tab):
+    """Searches whose approximant has two or three zeros of very different Im inside the domain
+    (multistart.json): root sets AND n_function_call equal the reference's.  The call count pins the secant
+    tolerance rule -- find_dispersion_roots polishes one scalar at a time (psi_mode.py:340-352), so each start
+    uses min(1.48e-8, 1e-5*|Im|) of ITSELF; taking the minimum over all starts iterates longer (the reference
+    needs 30 / 124 / 101 evaluations on cases 2 / 4 / 5)."""
+    g = load("multistart.json")
+    disp = po.Dispersion(po.DustDist.power_law(3.0, g["stokes_range"]), tab)
+    for case in g["cases"]:
+        np.random.seed(g["seed"])
+        md = po.Mode(disp, [-2.0, 2.0], [1e-8, 1.0], 20, 1)
+        roots = md.calculate(case["kx"], case["kz"])
+        ref = carr(case["roots"])
+        assert len(roots) == len(ref), case
+        assert all(abs(a - b) <= 1e-9*abs(b) for a, b in zip(roots, ref))
+        assert md.n_function_call == case["n_function_call"], (case["kx"], case["kz"], md.n_function_call)
