@@ -1,0 +1,159 @@
+"""K1's thread-per-point fast path (disp_eval_thread_kernel + the loose exit predictor, csrc/psi_b200.cu and
+psi_quad.cuh) -- the kernel BASELINE config 2's throughput rests on -- held to hard GPU tests on every work
+class (4 size-density node generators x inviscid/viscous):
+
+  * against the literal exit rule of tanhsinh.py:120-126 on 65,536 random points per class and tau_max,
+    a quarter of them on the resonant band |Im w| in [1e-8, 1e-5] with a resonance pole inside the Stokes
+    range, at rtol 1e-10 (rtol 1e-10, atol 1e-10*median|D|);
+  * against the oracle (bit-identical restatement of the reference) on a 4,096-point random sample of the
+    config-2 grid, no M requested, so that the thread kernel is what runs;
+  * K3 (secant polish) and K2 (contour count), which switch to the loose predictor internally, against
+    their own runs under the literal rule.
+Batches carry no M and at least 4,096 points: the launch counter shows two launches per class (thread
+kernel + left-over warp kernel) under the default rule and one under the literal rule."""
+import numpy as np
+import pytest
+
+from common import det_extended, product_kwargs, resonant_floor
+
+pytestmark = pytest.mark.gpu
+
+BUMP = dict(kind="powerbump", mu=10.0, amin=1e-8, aP=0.1, aL=2.0/3.0*0.1, aR=0.156, bumpfac=2.0)
+BUMP_WIDE = dict(kind="powerbump", mu=3.0, amin=1e-8, aP=0.6, aL=0.4, aR=1.0, bumpfac=2.0)
+TAIL = dict(kind="powerbumptail", mu=10.0, amin=1e-8, aP=0.1, aL=2.0/3.0*0.1, aR=0.156, bumpfac=2.0, aBT=1e-6)
+TAIL_WIDE = dict(kind="powerbumptail", mu=3.0, amin=1e-8, aP=0.6, aL=0.4, aR=1.0, bumpfac=2.0, aBT=1e-5)
+# (node kind, distribution spec): tau_max in {1e-2, 1} for the power laws, {0.156, 1} for the bump families
+DISTS = [(0, dict(kind="powerlaw", mu=3.0, stokes_range=[1e-8, 1e-2])),
+         (0, dict(kind="powerlaw", mu=3.0, stokes_range=[1e-8, 1.0])),
+         (1, dict(kind="powerlaw", mu=0.5, stokes_range=[1e-6, 1e-2], power=3.2, c=10.0)),
+         (1, dict(kind="powerlaw", mu=2.0, stokes_range=[1e-8, 1.0], power=3.8)),
+         (2, BUMP), (2, BUMP_WIDE), (3, TAIL), (3, TAIL_WIDE)]
+
+
+def _points(pd, kx, n, seed):
+    """n random omega: 3/4 in the box [-2,2] x [-1,1] (both half planes), 1/4 on the resonant band: |Im w| log-uniform
+    in [1e-8, 1e-5] with Re w = kx*ux(tau) for a tau inside the Stokes range (a resonance pole in every integral)."""
+    rng = np.random.RandomState(seed)
+    bg = pd.ctx.background(pd.dist_id)
+    nb = n//4
+    w = rng.uniform(-2, 2, n) + 1j*rng.uniform(-1, 1, n)
+    tau = np.exp(rng.uniform(np.log(pd.taumin*10), np.log(pd.taumax*0.9), nb))
+    ux = 2*bg["denom"]*(bg["j1"] - tau*(1 + bg["j0"]))/(1 + tau*tau)
+    w[:nb] = kx*ux + 1j*np.exp(rng.uniform(np.log(1e-8), np.log(1e-5), nb))*rng.choice([-1.0, 1.0], nb)
+    return w
+
+
+@pytest.mark.parametrize("visc", [False, True], ids=["inviscid", "viscous"])
+@pytest.mark.parametrize("which", range(len(DISTS)))
+def test_fast_path_vs_literal_rule(built, which, visc):
+    from psitools_public_b200 import PSIDispersion, TanhSinh
+    kind, spec = DISTS[which]
+    pd = PSIDispersion(tanhsinh_integrator=TanhSinh(), **product_kwargs(spec))
+    ctx = pd.ctx
+    alpha = 1e-6 if visc else 0.0
+    assert ctx.point_class(pd.dist_id, alpha) == 2*kind + int(visc)
+    kx, kz = 30.0, 120.0
+    n = 65536
+    w = _points(pd, kx, n, 100 + which)
+    assert ctx.exit_rule == "predicted"
+    l0 = ctx.launch_count
+    fast = pd.calculate(w, kx, kz, alpha)
+    assert ctx.launch_count - l0 == 2                 # thread kernel + warp kernel for what it left over
+    try:
+        ctx.exit_rule = "reference"
+        l0 = ctx.launch_count
+        lit = pd.calculate(w, kx, kz, alpha)
+        assert ctx.launch_count - l0 == 1
+    finally:
+        ctx.exit_rule = "predicted"
+    assert np.all(np.isfinite(fast)) and np.all(np.isfinite(lit))
+    scale = np.median(np.abs(lit))
+    err = np.abs(fast - lit)/(np.abs(lit) + scale)
+    band = err[:n//4]
+    print("class %d: max rel diff %.2e (band %.2e)" % (2*kind + int(visc), err.max(), band.max()))
+    assert err.max() <= 1e-10, (which, visc, w[np.argmax(err)], err.max())
+
+
+def _oracle_chunk(args):
+    from oracle import psi_oracle as po
+    w, = args
+    od = po.Dispersion(po.DustDist.power_law(3.0, [1e-8, 0.1]), po.NodeTable())
+    D, M = od.calculate(w, 50.0, 100.0, return_M=True)
+    return D, M, od.vgx
+
+
+def test_config2_4096_points_vs_oracle(built):
+    """a random 4,096-point subset of the 1024^2 config-2 grid against the oracle, the whole
+    grid evaluated in one default-rule batch (fast path).  D against the exact determinant of the oracle's own
+    M entries at rtol 1e-10 (+ the reference's reproducibility floor 3e-17/|Im w| on resonant near-axis rows),
+    atol 1e-10*median|D|; and against the oracle's LU determinant itself with its stated noise floor."""
+    import multiprocessing as mp
+    import os
+    from common import lu_noise_floor
+    from psitools_public_b200 import PSIDispersion, TanhSinh
+    pd = PSIDispersion(3.0, [1e-8, 0.1], tanhsinh_integrator=TanhSinh())
+    re = np.linspace(-7.5, 7.5, 1024)
+    im = np.linspace(-12.5, 2.5, 1024)
+    w = (re[None, :] + 1j*im[:, None]).ravel()
+    l0 = pd.ctx.launch_count
+    full = pd.calculate(w, 50.0, 100.0)
+    assert pd.ctx.launch_count - l0 == 2
+    rng = np.random.RandomState(11)
+    pick = rng.choice(w.size, 4096 - 256, replace=False)
+    # the rows nearest the real axis are rare in a uniform sample: add 256 points of the two rows |Im w| < 0.01
+    near = np.flatnonzero(np.abs(w.imag) < 0.01)
+    pick = np.concatenate([pick, rng.choice(near, 256, replace=False)])
+    procs = min(16, os.cpu_count() or 1)
+    chunks = np.array_split(pick, 4*procs)
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_oracle_chunk, [(w[c],) for c in chunks], chunksize=1)
+    ref = np.concatenate([r[0] for r in res])
+    Mref = np.concatenate([r[1] for r in res])
+    vgx = res[0][2]
+    scale = np.median(np.abs(ref))
+    worst = 0.0
+    for k, i in enumerate(pick):
+        rt = max(1e-10, resonant_floor(w[i]))
+        ex = det_extended(Mref[k], w[i], 50.0, 100.0, 0.0, 20.0, vgx)
+        worst = max(worst, abs(full[i] - ex)/(abs(ex) + scale))
+        assert abs(full[i] - ex) <= rt*(abs(ex) + scale), (w[i], abs(full[i] - ex)/abs(ex))
+        assert abs(full[i] - ref[k]) <= rt*(abs(ref[k]) + scale) + lu_noise_floor(w[i], 50.0, 100.0, 20.0, vgx), w[i]
+    print("config 2, 4096 points: max |D - det_exact(M_oracle)|/(|D| + median) = %.2e" % worst)
+
+
+def test_polish_and_contour_loose_predictor_vs_literal(built):
+    """K3 and K2 run their inline D evaluations under the loose predictor (psi_b200.cu: polish_kernel,
+    contour_kernel).  Against the same kernels under the literal rule: polished roots agree to 1e-9 relative
+    with the same convergence pattern, winding numbers are equal."""
+    from psitools_public_b200 import PSIDispersion, TanhSinh
+    ts = TanhSinh()
+    rng = np.random.RandomState(3)
+    for kind, spec in DISTS[1::2]:
+        pd = PSIDispersion(tanhsinh_integrator=ts, **product_kwargs(spec))
+        ctx = pd.ctx
+        n = 256
+        kx = 10**rng.uniform(-1, 2, n)
+        kz = 10**rng.uniform(-1, 3, n)
+        starts = [[complex(rng.uniform(-1.5, 0.5), 10**rng.uniform(-5, -0.5))] for _ in range(n)]
+        dom = [[-2, 2, 1e-8, 1]]*n
+        out = {}
+        for rule in ("predicted", "reference"):
+            try:
+                ctx.exit_rule = rule
+                out[rule] = ctx.polish_batch([pd.dist_id]*n, kx, kz, [0.0]*n, dom, starts, [40]*n)
+                z = [-2.0 + 2e-7j, 2.0 + 2e-7j, 2.0 + 2.0j, -2.0 + 2.0j]
+                out[rule + "c"] = ctx.contour_batch([pd.dist_id]*16, kx[:16], kz[:16], [0.0]*16, [z]*16, [0.1]*16,
+                                                    [0.1]*16, [100]*16)
+            finally:
+                ctx.exit_rule = "predicted"
+        a, b = out["predicted"], out["reference"]
+        conv_a = np.array([r[0] != -1j for r in a[0]])
+        conv_b = np.array([r[0] != -1j for r in b[0]])
+        both = conv_a & conv_b
+        # a chain that needs all 40 iterations can converge under one rule and stop one step short under the other
+        assert np.count_nonzero(conv_a != conv_b) <= 2 and both.sum() > 20
+        ra = np.array([r[0] for r in a[0]])[both]
+        rb = np.array([r[0] for r in b[0]])[both]
+        assert np.max(np.abs(ra - rb)/np.abs(rb)) < 1e-8, np.max(np.abs(ra - rb)/np.abs(rb))
+        assert np.array_equal(out["predictedc"][0], out["referencec"][0])
+        assert np.array_equal(out["predictedc"][1], out["referencec"][1])
