@@ -20,7 +20,7 @@ namespace psi {
 
 #if defined(PSI_AAA_STATS)
 // test-harness counters: fits, inverse iterations, -, Aberth calls, Aberth iterations
-static long long g_aaa_stats[8];
+static long long g_aaa_stats[16];
 #define PSI_STAT(i, n) (g_aaa_stats[i] += (n))
 // test-harness switch: run the general (memory) form of the triangular solves also for small systems
 static bool g_aaa_general_solves = false;
@@ -185,6 +185,8 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
     const int lane = W::lane();
     const int steps = r < m ? r : m;
     PSI_STAT(0, 1);
+    PSI_STAT(5, (long long)r * m * m);
+    PSI_STAT(8 + (m <= 10 ? 0 : m <= 20 ? 1 : m <= 32 ? 2 : 3), 1);
     for (int k = 0; k < steps; ++k) {
         cx* ak = A + (size_t)k * r;
         const int i0 = lane >= k ? lane : lane + ((k - lane + W::width - 1) / W::width) * W::width;   // first own row >= k
@@ -286,6 +288,7 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
         cx bl = own ? b[lane] : cx(0.0, 0.0);
         for (; it < 80; ++it) {
             PSI_STAT(1, 1);
+            PSI_STAT(6, (long long)m * m);
             cx yl(0.0, 0.0);
 #pragma unroll 1
             for (int j = 0; j < m; ++j) {                      // R^H y = b
@@ -333,6 +336,7 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
     }
     for (; it < 80; ++it) {
         PSI_STAT(1, 1);
+        PSI_STAT(6, (long long)m * m);
         // R^H y = b  (forward; L_ij = conj(R_ji), row j of R is strided in memory)
         for (int j = 0; j < m; ++j) {
             const cx rj = rinv[j];
@@ -417,6 +421,7 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
         W::sync();
         st.slot = k;
         st.v_m = 0;                                  // V belongs to some other mask now
+        PSI_STAT(2, 1);
         return s.memo_res[k];
     }
     for (int j = 0; j < m; ++j) {
@@ -531,6 +536,7 @@ PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with
     for (int q = 0; q < 8; ++q) { prev_step[q] = INFINITY; frozen[q] = false; }
     for (; it < 60; ++it) {
         PSI_STAT(4, 1);
+        PSI_STAT(7, (long long)nr * (m + nr));
         bool moving = false;
         int slot = 0;
 #pragma unroll 1

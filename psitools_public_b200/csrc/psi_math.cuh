@@ -346,7 +346,9 @@ struct JNode {
 // with the size-density poles and sorted (psi_dispersion.py:408-446).  The reference takes the
 // eigenvalues of the companion matrix; the cancellation-free closed form below agrees with it to an
 // ulp or two.  Returns the number of poles written to out[] (ascending).
-PSI_HD int resonance_poles(const DistParams& d, double wre, double kx, double* out) {
+// res_tau (may be null) receives the stopping times of the resonance poles that were added, *n_res their number.
+PSI_HD int resonance_poles(const DistParams& d, double wre, double kx, double* out, double* res_tau = nullptr,
+                           int* n_res = nullptr) {
     int n = 0;
     for (int i = 0; i < d.n_calc_poles; ++i) out[n++] = d.calc_poles[i];
     const double c2 = wre / kx;
@@ -364,8 +366,14 @@ PSI_HD int resonance_poles(const DistParams& d, double wre, double kx, double* o
             if (qq != 0.0) r[nr++] = c0 / qq; else r[nr++] = 0.0;
         }
     }
+    int nres = 0;
     for (int i = 0; i < nr; ++i)
-        if (r[i] > d.taumin && r[i] < d.taumax && n < 2 * kMaxPoles) out[n++] = r[i] / d.taumax;
+        if (r[i] > d.taumin && r[i] < d.taumax && n < 2 * kMaxPoles) {
+            out[n++] = r[i] / d.taumax;
+            if (res_tau) res_tau[nres] = r[i];
+            ++nres;
+        }
+    if (n_res) *n_res = nres;
     for (int i = 1; i < n; ++i) {                       // insertion sort, n <= 6
         double v = out[i]; int j = i - 1;
         while (j >= 0 && out[j] > v) { out[j + 1] = out[j]; --j; }

@@ -96,7 +96,8 @@ def det_terms_scale(M7, w, kx, kz, alpha, c, vgx):
     r = w - kx*vgx
     d = kx*vgx - w - 1j*nu*(kx**2 + kz**2)
     g = c**2/r
-    m = [complex(x) for x in M7]
+    M7 = np.asarray(M7, dtype=complex)          # (7,) for one point or (n, 7) with w of length n
+    m = [M7[..., k] for k in range(7)]
     e00, e02 = m[0] - 1j*kx**2*nu/3, m[2] - 1j*kx*kz*nu/3
     e20, e22 = -1j*kx*kz*nu/3, m[6] - 1j*kz**2*nu/3
     minor = abs((d + e00)*(d + e22)) + abs(e02*e20) + abs(g)*(kx*kx*abs(d + e22) + kz*kz*abs(d + e00)
@@ -104,7 +105,8 @@ def det_terms_scale(M7, w, kx, kz, alpha, c, vgx):
     a01, a10, a11, a12 = 2j + m[1], -0.5j + m[3], d + m[4], m[5]
     a20 = kx*kz*g + e20
     a22 = kz*kz*g + d + e22
-    return float(abs(a11)*minor + abs(a01)*(abs(a10*a22) + abs(a12*a20)))
+    out = abs(a11)*minor + abs(a01)*(abs(a10*a22) + abs(a12*a20))
+    return float(out) if np.ndim(out) == 0 else out
 
 
 def lu_noise_floor(w, kx, kz, c, vgx):

@@ -333,7 +333,7 @@ void hs_refine_count(int nz, int nx, const int* runs, const int* nguess, int wid
         nk[p] = refine_pixel(g, p / nx, p % nx, near.data(), reinterpret_cast<cx*>(kept) + (size_t)p * kRefineMaxNear);
 }
 
-void hs_aaa_stats(long long* out) { for (int i = 0; i < 8; ++i) { out[i] = g_aaa_stats[i]; g_aaa_stats[i] = 0; } }
+void hs_aaa_stats(long long* out) { for (int i = 0; i < 16; ++i) { out[i] = g_aaa_stats[i]; g_aaa_stats[i] = 0; } }
 
 int psi_polish_batch_host(psi_ctx* c, int n_items, const int* dist, const double* kx, const double* kz,
                           const double* alpha, const double* domain, const int* w0_off, const double* w0,
