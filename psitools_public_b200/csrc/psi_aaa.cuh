@@ -30,6 +30,19 @@ static bool g_aaa_general_solves = false;
 #define PSI_GENERAL_SOLVES false
 #endif
 
+// Phase profiling of the analysis stage (build with -DPSI_PROF: tools/prof_analysis.py): cycles per phase,
+// summed over warps with clock64() on lane 0.
+#if defined(PSI_PROF) && defined(__CUDACC__)
+static __device__ unsigned long long g_psi_prof[32];
+#endif
+#if defined(PSI_PROF) && defined(__CUDA_ARCH__)
+#define PROF_T0(v) const long long v = clock64()
+#define PROF_ADD(id, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_psi_prof[id], (unsigned long long)(clock64() - (v))); } while (0)
+#else
+#define PROF_T0(v)
+#define PROF_ADD(id, v)
+#endif
+
 // Out-of-line copies of the small helpers.  The analysis kernel is instruction-fetch bound (ncu: 83 % of
 // its stall samples are "no instruction" with 315 KB of SASS and 24 warps per SM in different phases), so
 // every helper exists once instead of at each use, and the strided loops are not unrolled.
@@ -63,8 +76,6 @@ struct AAAScratch {
     cx* tmp;      // [ncol]  second root buffer
     // greedy-phase result, replayed by PSIMode's clean_tol-halving loop
     int* g_mask;  // [cap]
-    cx* g_w;      // [ncol]
-    double* g_R;  // [cap]
     // work lists of the mode machine (psi_mode.cuh)
     cx* w0;       // [ncol]  start values of the polish
     cx* pol;      // [ncol]  polished values
@@ -82,35 +93,38 @@ struct AAAScratch {
     int cap, ncol;
 };
 
+// Scratch is split in two: the ITEM part (everything that must survive between the phase kernels of the
+// analysis stage: index lists, weights, residuals, zeros, the memo) and the WORK part (Loewner matrix, triangular
+// factor, vectors of the inverse iteration: only alive inside one fit).  The GPU pipeline keeps one item part
+// per search and one work part per group of the fit kernel; the single-warp form (mode_run, CPU harness) carves
+// both from one area.
+PSI_HD size_t aaa_item_bytes(int cap) {
+    const size_t ncol = (size_t)cap / 2 + 2;
+    return sizeof(cx) * ((3 + 3 * kMemoSlots) * ncol) +
+           sizeof(double) * ((1 + kMemoSlots) * (size_t)cap + kMemoSlots) +
+           sizeof(int) * ((3 + kMemoSlots) * (size_t)cap + ncol + 3 * kMemoSlots) + 64;
+}
+PSI_HD size_t aaa_work_bytes(int cap) {
+    const size_t ncol = (size_t)cap / 2 + 2;
+    return sizeof(cx) * ((size_t)cap * ncol + ncol * ncol + 4 * ncol) + 64;
+}
 PSI_HD size_t aaa_scratch_bytes(int cap) {
     const size_t ncol = (size_t)cap / 2 + 2;
-    return sizeof(cx) * (2 * (size_t)cap + (size_t)cap * ncol + ncol * ncol + (10 + 3 * kMemoSlots) * ncol) +
-           sizeof(double) * ((2 + kMemoSlots) * (size_t)cap + kMemoSlots) +
-           sizeof(int) * ((3 + kMemoSlots) * (size_t)cap + ncol + 3 * kMemoSlots) + 256;
+    return ((aaa_item_bytes(cap) + 255) & ~(size_t)255) + aaa_work_bytes(cap) + sizeof(cx) * (2 * (size_t)cap + 2 * ncol) + 256;
 }
 
-PSI_HD AAAScratch aaa_carve(void* base, int cap) {
-    AAAScratch s;
+PSI_HD void aaa_carve_item(void* base, int cap, AAAScratch& s) {
     const size_t ncol = (size_t)cap / 2 + 2;
     s.cap = cap; s.ncol = (int)ncol;
     cx* c = reinterpret_cast<cx*>(base);
-    s.Z = c; c += cap;
-    s.F = c; c += cap;
-    s.A = c; c += (size_t)cap * ncol;
-    s.V = c; c += ncol * ncol;
-    s.V2 = c; c += 4 * ncol;
     s.w = c; c += ncol;
     s.roots = c; c += ncol;
     s.tmp = c; c += ncol;
-    s.g_w = c; c += ncol;
-    s.w0 = c; c += ncol;
-    s.pol = c; c += ncol;
     s.memo_w = c; c += (size_t)kMemoSlots * ncol;
     s.memo_pole = c; c += (size_t)kMemoSlots * ncol;
     s.memo_zero = c; c += (size_t)kMemoSlots * ncol;
     double* d = reinterpret_cast<double*>(c);
     s.R = d; d += cap;
-    s.g_R = d; d += cap;
     s.memo_R = d; d += (size_t)kMemoSlots * cap;
     s.memo_res = d; d += kMemoSlots;
     int* i = reinterpret_cast<int*>(d);
@@ -122,6 +136,28 @@ PSI_HD AAAScratch aaa_carve(void* base, int cap) {
     s.memo_np = i; i += kMemoSlots;
     s.memo_nz = i; i += kMemoSlots;
     s.on = i;
+}
+PSI_HD void aaa_carve_work(void* base, int cap, AAAScratch& s) {
+    const size_t ncol = (size_t)cap / 2 + 2;
+    cx* c = reinterpret_cast<cx*>(base);
+    s.A = c; c += (size_t)cap * ncol;
+    s.V = c; c += ncol * ncol;
+    s.V2 = c;
+}
+
+// one area for everything, incl. sample buffers and polish lists (single-warp form of the search)
+PSI_HD AAAScratch aaa_carve(void* base, int cap) {
+    AAAScratch s;
+    const size_t ncol = (size_t)cap / 2 + 2;
+    unsigned char* b = reinterpret_cast<unsigned char*>(base);
+    aaa_carve_item(b, cap, s);
+    b += (aaa_item_bytes(cap) + 255) & ~(size_t)255;
+    aaa_carve_work(b, cap, s);
+    cx* c = s.V2 + 4 * ncol;
+    s.Z = c; c += cap;
+    s.F = c; c += cap;
+    s.w0 = c; c += ncol;
+    s.pol = c;
     return s;
 }
 
@@ -187,6 +223,7 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
     PSI_STAT(0, 1);
     PSI_STAT(5, (long long)r * m * m);
     PSI_STAT(8 + (m <= 10 ? 0 : m <= 20 ? 1 : m <= 32 ? 2 : 3), 1);
+    PROF_T0(t_qr);
     for (int k = 0; k < steps; ++k) {
         cx* ak = A + (size_t)k * r;
         const int i0 = lane >= k ? lane : lane + ((k - lane + W::width - 1) / W::width) * W::width;   // first own row >= k
@@ -238,6 +275,8 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
         }
         W::sync();
     }
+    PROF_ADD(3, t_qr);
+    PROF_T0(t_ii);
     // R: strict upper triangle from A (rows < r), diagonal already in place (zero where no step ran)
 #pragma unroll 1
     for (int e = lane; e < m * m; e += W::width) {
@@ -332,6 +371,7 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
             prev = d2;
         }
         W::sync();
+        PROF_ADD(4, t_ii);
         return it;
     }
     for (; it < 80; ++it) {
@@ -397,16 +437,22 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
         if (d2 <= 1.0e-24 || (d2 <= 1.0e-12 && d2 > 0.25 * prev)) { ++it; break; }
         prev = d2;
     }
+    PROF_ADD(4, t_ii);
     return it;
 }
 
-// Loewner fit for the current mask: weights and residuals (complex_roots.py:56-90).  Returns the
-// largest residual divided by max|F|.
+// Loewner fit for the current mask: weights and residuals (complex_roots.py:56-90), in two halves so that the
+// pipeline can run the cheap half (index lists + memo lookup) in its control kernel and the expensive half
+// (Loewner matrix, QR, inverse iteration, residuals) in the fit kernel.
+// aaa_fit_lookup: rebuilds the index lists; true = the mask was fitted before, weights/residuals restored and
+// *res = largest residual / max|F|.
 template <class W>
-PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample = -1) {
+PSI_NOINLINE bool aaa_fit_lookup(const AAAScratch& s, AAAState& st, double* res) {
+    PROF_T0(t_ix);
     aaa_index<W>(s, st);
+    PROF_ADD(0, t_ix);
     const int lane = W::lane(), r = st.r, m = st.m;
-    // memo lookup
+    PROF_T0(t_ml);
     for (int k = 0; k < kMemoSlots; ++k) {
         if (s.memo_m[k] != m) continue;
         bool same = true;
@@ -422,8 +468,20 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
         st.slot = k;
         st.v_m = 0;                                  // V belongs to some other mask now
         PSI_STAT(2, 1);
-        return s.memo_res[k];
+        PROF_ADD(1, t_ml);
+        *res = s.memo_res[k];
+        return true;
     }
+    PROF_ADD(1, t_ml);
+    return false;
+}
+
+// aaa_fit_compute: the fit itself (index lists of the current mask must be in place: aaa_fit_lookup).  Returns
+// the largest residual divided by max|F| and files the fit in the memo.
+template <class W>
+PSI_NOINLINE double aaa_fit_compute(const AAAScratch& s, AAAState& st, int added_sample) {
+    const int lane = W::lane(), r = st.r, m = st.m;
+    PROF_T0(t_bd);
     for (int j = 0; j < m; ++j) {
         const cx zj = s.Z[s.on[j]], fj = s.F[s.on[j]];
 #pragma unroll 1
@@ -433,6 +491,7 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
         }
     }
     W::sync();
+    PROF_ADD(2, t_bd);
     if (r == 0) {
 #pragma unroll 1
         for (int j = lane; j < m; j += W::width) s.w[j] = cx(j == m - 1 ? 1.0 : 0.0, 0.0);
@@ -459,6 +518,7 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
         st.v_m = m;
     }
     W::sync();
+    PROF_T0(t_rs);
     double rmax = 0.0;
 #pragma unroll 1
     for (int i = lane; i < r; i += W::width) {
@@ -475,6 +535,8 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
     }
     W::sync();
     const double resid = a_max<W>(rmax) / st.fmax;
+    PROF_ADD(5, t_rs);
+    PROF_T0(t_mi);
     {   // memo insert
         const int k = st.memo_next;
         st.memo_next = (k + 1) % kMemoSlots;
@@ -488,7 +550,15 @@ PSI_NOINLINE double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample 
         W::sync();
         st.slot = k;
     }
+    PROF_ADD(6, t_mi);
     return resid;
+}
+
+template <class W>
+PSI_HD double aaa_fit(const AAAScratch& s, AAAState& st, int added_sample = -1) {
+    double res;
+    if (aaa_fit_lookup<W>(s, st, &res)) return res;
+    return aaa_fit_compute<W>(s, st, added_sample);
 }
 
 // barycentric evaluation r(z) = sum w_j f_j/(z-z_j) / sum w_j/(z-z_j)   (complex_roots.py:331-368)
@@ -510,6 +580,7 @@ template <class W>
 PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with_f, cx* out) {
     const int lane = W::lane(), m = st.m, nr = m - 1;
     if (nr <= 0) return 0;
+    PROF_T0(t_ab);
     // scale and centre of the support points
     double cre = 0.0, cim = 0.0;
     for (int j = 0; j < m; ++j) { cre += s.Z[s.on[j]].re; cim += s.Z[s.on[j]].im; }
@@ -594,6 +665,7 @@ PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with
         W::sync();
         if (!W::any(moving)) break;
     }
+    PROF_ADD(with_f ? 8 : 7, t_ab);
     return it;
 }
 
@@ -624,18 +696,26 @@ PSI_HD void sort_complex(const cx* in, cx* out, int n) {
 // (50 iterations, tol 1.48e-8; a start is kept when the iteration degenerates or leaves the finite
 // numbers), sorted, entries closer than 1e-12 (numpy's lexicographic ">" on the difference) merged
 // (complex_roots.py:178-240).  Result in s.roots[0..n); returns n.
+// aaa_zeros_load: the zeros of a support mask seen before (true; *n = their number), or false.
 template <class W>
-PSI_NOINLINE int aaa_zeros(const AAAScratch& s, const AAAState& st) {
+PSI_HD bool aaa_zeros_load(const AAAScratch& s, const AAAState& st, int* n_out) {
+    const int lane = W::lane(), nr = st.m - 1;
+    if (nr <= 0) { *n_out = 0; return true; }
+    if (s.memo_nz[st.slot] < 0) return false;
+    const int n = s.memo_nz[st.slot];
+#pragma unroll 1
+    for (int k = lane; k < n; k += W::width) s.roots[k] = s.memo_zero[(size_t)st.slot * s.ncol + k];
+    W::sync();
+    *n_out = n;
+    return true;
+}
+
+template <class W>
+PSI_NOINLINE int aaa_zeros_compute(const AAAScratch& s, const AAAState& st) {
     const int lane = W::lane(), nr = st.m - 1;
     if (nr <= 0) return 0;
-    if (s.memo_nz[st.slot] >= 0) {                       // same support mask seen before: replay
-        const int n = s.memo_nz[st.slot];
-#pragma unroll 1
-        for (int k = lane; k < n; k += W::width) s.roots[k] = s.memo_zero[(size_t)st.slot * s.ncol + k];
-        W::sync();
-        return n;
-    }
     aberth_roots<W>(s, st, true, s.roots);
+    PROF_T0(t_zs);
 #pragma unroll 1
     for (int k = lane; k < nr; k += W::width) {
         const cx z0 = s.roots[k];
@@ -669,6 +749,8 @@ PSI_NOINLINE int aaa_zeros(const AAAScratch& s, const AAAState& st) {
         if (ok && !flagged) s.roots[k] = root;
     }
     W::sync();
+    PROF_ADD(9, t_zs);
+    PROF_T0(t_so);
     sort_complex<W>(s.roots, s.tmp, nr);
     // unique_within_tol (every lane computes the same compaction)
     int n = 0;
@@ -690,47 +772,66 @@ PSI_NOINLINE int aaa_zeros(const AAAScratch& s, const AAAState& st) {
     for (int k = lane; k < n; k += W::width) s.memo_zero[(size_t)st.slot * s.ncol + k] = s.roots[k];
     if (lane == 0) s.memo_nz[st.slot] = n;
     W::sync();
+    PROF_ADD(10, t_so);
     return n;
+}
+
+template <class W>
+PSI_HD int aaa_zeros(const AAAScratch& s, const AAAState& st) {
+    int n;
+    if (aaa_zeros_load<W>(s, st, &n)) return n;
+    return aaa_zeros_compute<W>(s, st);
 }
 
 // One cleanup pass (complex_roots.py:286-329): every pole inside the domain whose residue, measured by
 // a 4-point contour integral of side 1e-5, is below clean_tol*max|F| costs the nearest support point.
-// Returns the number of support points removed (the fit is redone either way, as in the reference).
+// aaa_poles_compute: poles of the current fit and, per pole inside the domain, (residue ratio, sample to drop),
+// filed under the fit's memo slot (the decisions do not depend on clean_tol).
 template <class W>
-PSI_NOINLINE int aaa_cleanup(const AAAScratch& s, AAAState& st) {
+PSI_NOINLINE void aaa_poles_compute(const AAAScratch& s, AAAState& st) {
     const int lane = W::lane(), np_ = st.m - 1;
     const int slot = st.slot;
-    cx* dec = s.memo_pole + (size_t)slot * s.ncol;       // (residue ratio, sample index) per pole in the domain
-    if (s.memo_np[slot] < 0) {
-        aberth_roots<W>(s, st, false, s.roots);
-        const double side = 1.0e-5;
-        const double c45 = 0.7071067811865476;
-        const cx ring[4] = {cx(side * c45, -side * c45), cx(side * c45, side * c45), cx(-side * c45, side * c45),
-                            cx(-side * c45, -side * c45)};
+    cx* dec = s.memo_pole + (size_t)slot * s.ncol;
+    aberth_roots<W>(s, st, false, s.roots);
+    PROF_T0(t_cr);
+    const double side = 1.0e-5;
+    const double c45 = 0.7071067811865476;
+    const cx ring[4] = {cx(side * c45, -side * c45), cx(side * c45, side * c45), cx(-side * c45, side * c45),
+                        cx(-side * c45, -side * c45)};
 #pragma unroll 1
-        for (int k = lane; k < np_; k += W::width) {
-            const cx pole = s.roots[k];
-            cx d(INFINITY, -1.0);
-            if (finite_c(pole) && st.dom.is_in(pole)) {
-                cx zc[4], fc[4];
-                for (int q = 0; q < 4; ++q) { zc[q] = pole + ring[q]; fc[q] = aaa_eval(s, st, zc[q]); }
-                cx integral(0.0, 0.0);
-                for (int q = 0; q < 4; ++q) {
-                    const cx dz = zc[(q + 1) & 3] - zc[q], fs = fc[(q + 1) & 3] + fc[q];
-                    integral = integral + (0.5 * dz) * fs;
-                }
-                int nearest = 0; double bd = INFINITY;
-                for (int j = 0; j < st.m; ++j) {
-                    const double dd = a_abs(pole - s.Z[s.on[j]]);
-                    if (dd < bd) { bd = dd; nearest = j; }
-                }
-                d = cx(a_abs(integral) / st.fmax, (double)s.on[nearest]);
+    for (int k = lane; k < np_; k += W::width) {
+        const cx pole = s.roots[k];
+        cx d(INFINITY, -1.0);
+        if (finite_c(pole) && st.dom.is_in(pole)) {
+            cx zc[4], fc[4];
+            for (int q = 0; q < 4; ++q) { zc[q] = pole + ring[q]; fc[q] = aaa_eval(s, st, zc[q]); }
+            cx integral(0.0, 0.0);
+            for (int q = 0; q < 4; ++q) {
+                const cx dz = zc[(q + 1) & 3] - zc[q], fs = fc[(q + 1) & 3] + fc[q];
+                integral = integral + (0.5 * dz) * fs;
             }
-            dec[k] = d;
+            int nearest = 0; double bd = INFINITY;
+            for (int j = 0; j < st.m; ++j) {
+                const double dd = a_abs(pole - s.Z[s.on[j]]);
+                if (dd < bd) { bd = dd; nearest = j; }
+            }
+            d = cx(a_abs(integral) / st.fmax, (double)s.on[nearest]);
         }
-        if (lane == 0) s.memo_np[slot] = np_ > 0 ? np_ : 0;
-        W::sync();
+        dec[k] = d;
     }
+    if (lane == 0) s.memo_np[slot] = np_ > 0 ? np_ : 0;
+    W::sync();
+    PROF_ADD(11, t_cr);
+}
+
+PSI_HD bool aaa_poles_ready(const AAAScratch& s, const AAAState& st) { return s.memo_np[st.slot] >= 0; }
+
+// aaa_cleanup_apply: drop the support points the stored decisions condemn at the current clean_tol; returns
+// their number (the fit is redone either way, as in the reference).
+template <class W>
+PSI_HD int aaa_cleanup_apply(const AAAScratch& s, AAAState& st) {
+    const int lane = W::lane(), slot = st.slot;
+    const cx* dec = s.memo_pole + (size_t)slot * s.ncol;
     const int nd = s.memo_np[slot];
     int removed = 0;
     for (int k = 0; k < nd; ++k) if (dec[k].im >= 0.0 && dec[k].re < st.clean_tol) ++removed;
@@ -738,6 +839,13 @@ PSI_NOINLINE int aaa_cleanup(const AAAScratch& s, AAAState& st) {
     if (lane == 0)
         for (int k = 0; k < nd; ++k) if (dec[k].im >= 0.0 && dec[k].re < st.clean_tol) s.mask[(int)dec[k].im] = 0;
     W::sync();
+    return removed;
+}
+
+template <class W>
+PSI_NOINLINE int aaa_cleanup(const AAAScratch& s, AAAState& st) {
+    if (!aaa_poles_ready(s, st)) aaa_poles_compute<W>(s, st);
+    const int removed = aaa_cleanup_apply<W>(s, st);
     aaa_fit<W>(s, st);
     return removed;
 }

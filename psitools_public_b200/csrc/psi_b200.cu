@@ -77,6 +77,61 @@ struct WarpCuda {
     }
 };
 
+// Sub-warp policy: G lanes (8, 16 or 32) cooperate on one item, 32/G items share a warp -- and with it one
+// instruction stream.  The analysis stage of K4 (psi_aaa.cuh) works on matrices of 18 x 10 (20 samples) to about
+// 90 x 32 entries: a whole warp per search leaves most lanes idle and is bound by instruction fetch and by the
+// latency of its dependent load/shuffle chains, so several searches per warp multiply the useful work per issued
+// instruction.  All collectives name only the lanes of their own group (groups of one warp may diverge).
+template <int G>
+struct GroupCuda {
+    static constexpr int width = G;
+    static __device__ __forceinline__ int lane() { return threadIdx.x & (G - 1); }
+    static __device__ __forceinline__ unsigned shift() { return threadIdx.x & 31 & ~(G - 1); }
+    static __device__ __forceinline__ unsigned mask() {
+        return G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << shift());
+    }
+    static __device__ __forceinline__ double sum(double v) {
+        const unsigned mk = mask();
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mk, v, o);
+        return v;
+    }
+    static __device__ __forceinline__ double max(double v) {
+        const unsigned mk = mask();
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mk, v, o));
+        return v;
+    }
+    static __device__ __noinline__ void sum4c(double (&re)[4], double (&im)[4]) {
+        const unsigned mk = mask();
+#pragma unroll 1
+        for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                re[c] += __shfl_xor_sync(mk, re[c], o);
+                im[c] += __shfl_xor_sync(mk, im[c], o);
+            }
+        }
+    }
+    static __device__ __forceinline__ void sync() { __syncwarp(mask()); }
+    static __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(mask(), v, src, G); }
+    static __device__ __forceinline__ unsigned ballot(bool p) {
+        const unsigned b = __ballot_sync(mask(), p) >> shift();
+        return G == 32 ? b : (b & ((1u << (G & 31)) - 1u));
+    }
+    static __device__ __forceinline__ int popc(unsigned v) { return __popc(v); }
+    static __device__ __forceinline__ bool any(bool p) { return ballot(p) != 0u; }
+    static __device__ __forceinline__ void argmax(double& v, int& idx) {
+        const unsigned mk = mask();
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(mk, v, o);
+            const int oi = __shfl_xor_sync(mk, idx, o);
+            if (oi >= 0 && (idx < 0 || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
+        }
+    }
+};
+
 // Thread policy: one thread = one evaluation, no cooperation (fast path of K1, below).
 struct ThreadCuda {
     static constexpr int width = 1;
@@ -255,6 +310,15 @@ __device__ __forceinline__ bool next_item(unsigned long long* queue, long long n
     v = __shfl_sync(0xffffffffu, v, 0);
     idx = (long long)v;
     return v < (unsigned long long)n;
+}
+
+template <class W>
+__device__ __forceinline__ bool next_item_group(unsigned long long* queue, long long n, long long& idx) {
+    double v = 0.0;
+    if (W::lane() == 0) v = (double)atomicAdd(queue, 1ull);          // item counts stay far below 2^53
+    v = W::bcast(v, 0);
+    idx = (long long)v;
+    return idx < n;
 }
 
 // K1.  One specialisation per work class (NK, VISC); a launch handles the points of ITS class and
@@ -480,6 +544,8 @@ contour_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict
 // once per zoom level.  Homogeneous stages keep the SMs' instruction caches and FP64 pipes busy; the
 // single-warp form of the same search (mode_run in psi_mode.cuh) is what the CPU harness exercises.
 
+struct AnItem { AAAState st; AnDriver d; };     // analysis state of one search between the phase kernels
+
 struct ModeDev {            // device pointers of the per-item state (n items, cap samples, P start values)
     cx *Z, *F, *w0, *pol, *zoom, *roots;
     double* box_dx;
@@ -494,7 +560,7 @@ struct ModeDev {            // device pointers of the per-item state (n items, c
 __global__ void mode_sample_kernel(ModeDev m, int n_items, const double* __restrict__ domain,
                                    const int* __restrict__ iparams, const double* __restrict__ uni,
                                    const int* __restrict__ uni_off, const int* __restrict__ guess_off,
-                                   const double2* __restrict__ guesses) {
+                                   const double2* __restrict__ guesses, AnItem* an) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     const int ph = m.phase[i];
@@ -536,47 +602,106 @@ __global__ void mode_sample_kernel(ModeDev m, int n_items, const double* __restr
     m.calls[i] += n_new;
     m.M[i] = M; m.upos[i] = upos;
     m.phase[i] = kPhaseAnalyze;
+    an[i].d.pc = kPcStart;
     const unsigned long long pos = atomicAdd(m.counters, (unsigned long long)n_new);
     for (int k = 0; k < n_new; ++k) m.elem[pos + k] = (long long)i * m.cap + first + k;
 }
 
-// warp per item: AAA analysis of the current samples (mode_analyze) -> polish start values + zoom plan
-__global__ void __launch_bounds__(256, 3)
-mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, const int* __restrict__ iparams,
-                    const double* __restrict__ dparams, const int* __restrict__ guess_off,
-                    unsigned char* scratch, size_t scratch_per_warp, unsigned long long* queue,
-                    unsigned long long* n_polish) {
-    const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    AAAScratch sc = aaa_carve(scratch + (size_t)warp_global * scratch_per_warp, m.cap);
-    long long idx;
-    while (next_item(queue, n_items, idx)) {
+// ---- analysis stage of K4: four kernels over the searches of a zoom level (state machine: psi_mode.cuh, mode_ctl).
+// G lanes per search, 32/G searches per warp.  Per-search state between the kernels: AnItem + the item part of the
+// AAA scratch (index lists, weights, residuals, zeros, memo) in `item_scratch`; the work part (Loewner matrix,
+// triangular factor) belongs to the groups of the fit kernel.
+struct AnArgs {
+    AnItem* items;
+    unsigned char* item_scratch;
+    size_t item_stride;
+    long long* lists;                   // [3][n_items]: searches waiting for a fit / poles / zeros
+    unsigned long long* counters;       // [0..2] list lengths, [3] searches still running, [4..6] queue heads
+};
+
+template <class W>
+__device__ __forceinline__ AAAScratch an_scratch(const ModeDev& m, const AnArgs& a, long long idx) {
+    AAAScratch sc;
+    aaa_carve_item(a.item_scratch + (size_t)idx * a.item_stride, m.cap, sc);
+    sc.A = nullptr; sc.V = nullptr; sc.V2 = nullptr;
+    sc.Z = m.Z + (size_t)idx * m.cap;                 // the item's own sample buffers, analysed in place
+    sc.F = m.F + (size_t)idx * m.cap;
+    sc.w0 = m.w0 + (size_t)idx * m.P;
+    sc.pol = nullptr;
+    return sc;
+}
+
+// control kernel: every search that is being analysed advances through its cheap transitions until it needs an
+// expensive operation (queued on the matching list) or has its plan (polish start values, zoom boxes)
+template <int G>
+__global__ void __launch_bounds__(256)
+an_ctl_kernel(ModeDev m, AnArgs a, int n_items, const double* __restrict__ domain, const int* __restrict__ iparams,
+              const double* __restrict__ dparams, const int* __restrict__ guess_off, unsigned long long* n_polish) {
+    typedef GroupCuda<G> W;
+    const int lane = W::lane();
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long n_groups = (long long)gridDim.x * blockDim.x / G;
+    for (long long idx = group; idx < n_items; idx += n_groups) {
         if (m.phase[idx] != kPhaseAnalyze) continue;
+        AnItem* it = a.items + idx;
+        AnDriver d = it->d;
+        if (d.pc == kPcDone) continue;
         ModeCfg cfg;
         cfg.dom = RectDom{domain[4 * idx], domain[4 * idx + 1], domain[4 * idx + 2], domain[4 * idx + 3]};
         cfg.n_sample = iparams[3 * idx]; cfg.max_zoom = iparams[3 * idx + 1]; cfg.max_secant = iparams[3 * idx + 2];
         cfg.tol = dparams[2 * idx]; cfg.clean_tol = dparams[2 * idx + 1];
-        sc.Z = m.Z + (size_t)idx * m.cap;                 // analyse the item's own sample buffers in place
-        sc.F = m.F + (size_t)idx * m.cap;
-        sc.w0 = m.w0 + (size_t)idx * m.P;
+        const AAAScratch sc = an_scratch<W>(m, a, idx);
         AAAState st;
-        st.M = m.M[idx]; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol;
-        st.dom = cfg.dom; st.memo_next = 0; st.slot = 0; st.v_m = 0;
+        if (d.pc == kPcStart) {
+            st.M = m.M[idx]; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol;
+            st.dom = cfg.dom; st.memo_next = 0; st.slot = 0; st.v_m = 0;
+            d.req = kReqNone; d.k = 1; d.added = -1; d.removed = 0; d.nz = 0; d.res = 0.0;
+        } else {
+            st = it->st;
+        }
         ModePlan plan;
-        const bool ok = mode_analyze<WarpCuda>(cfg, m.level[idx], guess_off[idx + 1] - guess_off[idx], sc, st, plan);
-        __syncwarp();
+        const int req = mode_ctl<W>(cfg, m.level[idx], guess_off[idx + 1] - guess_off[idx], sc, st, d, plan);
+        W::sync();
         if (lane == 0) {
-            if (!ok) {
+            it->st = st; it->d = d;
+            if (req == kReqFailed) {
                 m.status[idx] = kModeBadSamples; m.phase[idx] = kPhaseDone; m.n_out[idx] = 0;
-            } else {
+            } else if (d.pc == kPcDone) {
                 m.n0[idx] = plan.n0; m.max_iter[idx] = plan.max_iter; m.n_zoom[idx] = plan.n_zoom;
                 m.box_dx[idx] = plan.box_dx;
                 for (int q = 0; q < plan.n_zoom; ++q) m.zoom[4 * (size_t)idx + q] = plan.zoom[q];
                 m.pcalls[idx] = 0; m.pconv[idx] = 0; m.pstat[idx] = 0;
                 m.phase[idx] = plan.n0 > 0 ? kPhasePolish : kPhaseDecide;
                 if (plan.n0 > 0) atomicAdd(n_polish, 1ull);
+            } else {
+                const unsigned long long pos = atomicAdd(a.counters + (req - 1), 1ull);
+                a.lists[(size_t)(req - 1) * n_items + pos] = idx;
+                atomicAdd(a.counters + 3, 1ull);
             }
         }
+    }
+}
+
+// one expensive operation (REQ) for every search on its list
+template <int G, int REQ>
+__global__ void __launch_bounds__(256, 3)
+an_heavy_kernel(ModeDev m, AnArgs a, int n_items, unsigned char* work, size_t work_stride) {
+    typedef GroupCuda<G> W;
+    const int lane = W::lane();
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long n_list = (long long)a.counters[REQ - 1];
+    const long long* list = a.lists + (size_t)(REQ - 1) * n_items;
+    long long k;
+    while (next_item_group<W>(a.counters + 3 + REQ, n_list, k)) {
+        const long long idx = list[k];
+        AnItem* it = a.items + idx;
+        AAAScratch sc = an_scratch<W>(m, a, idx);
+        if (REQ == kReqFit) aaa_carve_work(work + (size_t)group * work_stride, m.cap, sc);
+        AAAState st = it->st;
+        AnDriver d = it->d;
+        mode_heavy<W>(REQ, sc, st, d);
+        W::sync();
+        if (lane == 0) { it->st = st; it->d = d; }
     }
 }
 
@@ -1019,19 +1144,23 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     }
     const size_t ni = (size_t)n_items, ng = (size_t)guess_off[n_items];
     const int P = cap / 2 + 2;
-    // AAA scratch: one area per warp of the analysis kernel
-    static const int an_threads = getenv("PSI_AN_THREADS") ? atoi(getenv("PSI_AN_THREADS")) : 256;
-    static const int an_ctas = getenv("PSI_AN_CTAS") ? atoi(getenv("PSI_AN_CTAS")) : 4;
-    const int awarps = an_threads / 32;
-    const int agrid = std::min(c->sm_count * an_ctas, (n_items + awarps - 1) / awarps);
-    const size_t per_warp = (aaa_scratch_bytes(cap) + 255) & ~(size_t)255;
-    const size_t need = per_warp * (size_t)c->sm_count * an_ctas * awarps;
+    // analysis stage: G lanes per search, first level / zoom levels (PSI_AN_GROUP0 / PSI_AN_GROUP1: 8, 16, 32);
+    // searches with many guess domains -- more than 128 samples -- keep a whole warp (their matrices fill it).
+    // The fit kernel owns one work area (Loewner matrix, triangular factor) per group.
+    static const int an_ctas = getenv("PSI_AN_CTAS") ? atoi(getenv("PSI_AN_CTAS")) : 3;
+    static const int env_g0 = getenv("PSI_AN_GROUP0") ? atoi(getenv("PSI_AN_GROUP0")) : 8;
+    static const int env_g1 = getenv("PSI_AN_GROUP1") ? atoi(getenv("PSI_AN_GROUP1")) : 16;
+    const int an_g0 = cap > 128 ? 32 : env_g0, an_g1 = cap > 128 ? 32 : env_g1;
+    const int an_threads = 256;
+    const size_t work_stride = (aaa_work_bytes(cap) + 255) & ~(size_t)255;
+    const size_t need = work_stride * (size_t)c->sm_count * an_ctas * (an_threads / std::min(an_g0, an_g1));
     if (need > c->mode_scratch_bytes) {
         if (c->d_mode_scratch) CK(cudaFree(c->d_mode_scratch));
         c->d_mode_scratch = nullptr; c->mode_scratch_bytes = 0;
         CK(cudaMalloc(&c->d_mode_scratch, need));
         c->mode_scratch_bytes = need;
     }
+    const size_t item_stride = (aaa_item_bytes(cap) + 255) & ~(size_t)255;
     // inputs + per-item state in one staging allocation
     const size_t nreq = ni * (size_t)max_req;
     StageItem it[] = {
@@ -1041,9 +1170,10 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         {nullptr, 16 * ni * cap}, {nullptr, 16 * ni * cap},                                        // 11 Z, 12 F
         {nullptr, 16 * ni * P}, {nullptr, 16 * ni * P}, {nullptr, 64 * ni},                        // 13 w0, 14 pol, 15 zoom
         {nullptr, 16 * ni * max_roots}, {nullptr, 8 * ni},                                         // 16 roots, 17 box_dx
-        {nullptr, 4 * ni * 13}, {nullptr, 8 * nreq}};                                              // 18 ints, 19 elem
-    char* d[20];
-    int rc = stage_upload(c, it, 20, 0, d, nullptr);
+        {nullptr, 4 * ni * 13}, {nullptr, 8 * nreq},                                               // 18 ints, 19 elem
+        {nullptr, sizeof(AnItem) * ni}, {nullptr, item_stride * ni}, {nullptr, 24 * ni}, {nullptr, 64}};   // 20-23 analysis
+    char* d[24];
+    int rc = stage_upload(c, it, 24, 0, d, nullptr);
     if (rc != PSI_OK) return rc;
     cudaStream_t st = c->stream;
     ModeDev m;
@@ -1056,6 +1186,9 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     m.elem = (long long*)d[19];
     m.counters = c->d_counter + 6;
     m.cap = cap; m.P = P; m.max_roots = max_roots;
+    AnArgs an;
+    an.items = (AnItem*)d[20]; an.item_scratch = (unsigned char*)d[21]; an.item_stride = item_stride;
+    an.lists = (long long*)d[22]; an.counters = (unsigned long long*)d[23];
     CK(cudaMemsetAsync(ints, 0, 4 * ni * 13, st));                         // phase 0 = kPhaseSample everywhere
     CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
     NodeTableView t = table_view(c);
@@ -1079,7 +1212,7 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         CK(cudaEventRecord(ev[0], st));
         mode_sample_kernel<<<tgrid, 256, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
                                                   (const double*)d[7], (const int*)d[8], (const int*)d[9],
-                                                  (const double2*)d[10]);
+                                                  (const double2*)d[10], an.items);
         CK(cudaGetLastError());
         unsigned long long cnt[2] = {0, 0};
         CK(cudaEventRecord(ev[1], st));
@@ -1095,10 +1228,48 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(c->d_counter + 8, 0, sizeof(unsigned long long), st));
         CK(cudaEventRecord(ev[2], st));
-        mode_analyze_kernel<<<agrid, an_threads, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
-                                                   (const double*)d[6], (const int*)d[9],
-                                                   (unsigned char*)c->d_mode_scratch, per_warp, c->d_counter,
-                                                   c->d_counter + 8);
+        {
+            // rounds of [control kernel | fits | poles | zeros] until every search of this level has its plan
+            const int g = round == 0 ? an_g0 : an_g1;
+            const int per_cta = an_threads / g;
+            const int cgrid = std::min(c->sm_count * 6, (n_items + (an_threads / 8) - 1) / (an_threads / 8));
+            for (int an_round = 0;; ++an_round) {
+                CK(cudaMemsetAsync(an.counters, 0, 8 * sizeof(unsigned long long), st));
+                an_ctl_kernel<8><<<cgrid, an_threads, 0, st>>>(m, an, n_items, (const double*)d[4], (const int*)d[5],
+                                                               (const double*)d[6], (const int*)d[9], c->d_counter + 8);
+                CK(cudaGetLastError());
+                unsigned long long ac[4] = {0, 0, 0, 0};
+                CK(cudaMemcpyAsync(ac, an.counters, sizeof(ac), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                launches += 1;
+                if (ac[3] == 0) break;
+                auto grid_for = [&](unsigned long long n) {
+                    return (int)std::min<unsigned long long>((unsigned long long)c->sm_count * an_ctas,
+                                                             (n + per_cta - 1) / per_cta);
+                };
+                if (ac[0]) {
+                    auto kern = g == 8 ? an_heavy_kernel<8, kReqFit> : g == 16 ? an_heavy_kernel<16, kReqFit>
+                                                                               : an_heavy_kernel<32, kReqFit>;
+                    kern<<<grid_for(ac[0]), an_threads, 0, st>>>(m, an, n_items, (unsigned char*)c->d_mode_scratch,
+                                                                work_stride);
+                    ++launches;
+                }
+                if (ac[1]) {
+                    auto kern = g == 8 ? an_heavy_kernel<8, kReqPoles> : g == 16 ? an_heavy_kernel<16, kReqPoles>
+                                                                                 : an_heavy_kernel<32, kReqPoles>;
+                    kern<<<grid_for(ac[1]), an_threads, 0, st>>>(m, an, n_items, nullptr, 0);
+                    ++launches;
+                }
+                if (ac[2]) {
+                    auto kern = g == 8 ? an_heavy_kernel<8, kReqZeros> : g == 16 ? an_heavy_kernel<16, kReqZeros>
+                                                                                 : an_heavy_kernel<32, kReqZeros>;
+                    kern<<<grid_for(ac[2]), an_threads, 0, st>>>(m, an, n_items, nullptr, 0);
+                    ++launches;
+                }
+                CK(cudaGetLastError());
+                if (an_round > 100000) return fail(PSI_ERR_CUDA, "analysis stage does not terminate");
+            }
+        }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ev[3], st));
         // few root searches to polish: one BLOCK per search instead of one warp (the slowest serial secant
@@ -1209,6 +1380,17 @@ int psi_contour_batch_host(psi_ctx* c, int n_items, const int* dist, const doubl
     if (stats) { stats[0] = 1; stats[1] = (long long)cnt[1]; }
     return PSI_OK;
 }
+
+#if defined(PSI_PROF)
+// profiling build only (tools/prof_analysis.py): read and clear the per-phase cycle counters of the analysis stage
+int psi_prof_read(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, g_psi_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+    unsigned long long zero[32] = {0};
+    cudaMemcpyToSymbol(g_psi_prof, zero, sizeof(zero));
+    return 0;
+}
+#endif
 
 int psi_measure_fp64_peak(psi_ctx* c, int reps, double* tflops) {
     if (!c || !tflops || reps < 1) return fail(PSI_ERR_ARG, "psi_measure_fp64_peak: bad argument");

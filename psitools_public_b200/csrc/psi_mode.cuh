@@ -62,75 +62,209 @@ struct ModePlan {
 
 // AAA + zero selection of one zoom level (psi_mode.py:147-310): rational approximation of the current
 // samples, clean_tol halving until enough support points and one growing zero, zoom candidates, start
-// values of the polish.  Returns false when the samples are not finite (ValueError in the reference).
+// values of the polish -- written as a RESUMABLE state machine.  mode_ctl() advances a search through all its
+// cheap transitions (index lists, memo lookups, greedy promotion, cleanup decisions, clean_tol halving, the zoom
+// plan) and stops when it needs one of three expensive operations:
+//     kReqFit   a Loewner fit of the current mask            (aaa_fit_compute:   Loewner matrix, QR, inverse iteration)
+//     kReqPoles poles + residue decisions of the current fit (aaa_poles_compute: Ehrlich-Aberth + 4-point contours)
+//     kReqZeros zeros of the current fit                     (aaa_zeros_compute: Ehrlich-Aberth + secant on r(z))
+// The GPU pipeline runs each of the four pieces as its own kernel over all searches that need it (psi_b200.cu:
+// an_ctl_kernel, an_fit_kernel, an_poles_kernel, an_zeros_kernel), so that the warps of an SM execute ONE
+// compact piece of code at a time -- the monolithic form spent 3/4 of its stall cycles waiting for instruction
+// fetch, every warp in a different phase of 185 KB of machine code.  mode_analyze() below drives the same state
+// machine in a loop (single-warp form of the search, CPU harness): one statement of the logic for both.
+enum AnRequest { kReqNone = 0, kReqFit = 1, kReqPoles = 2, kReqZeros = 3, kReqFailed = 4 };
+enum AnPc { kPcStart = 0, kPcGreedyNext, kPcGreedyFit, kPcGreedyEnd, kPcClean, kPcCleanApply, kPcCleanFit,
+            kPcZeros, kPcZerosDone, kPcHalve, kPcReplayFit, kPcPlan, kPcDone };
+
+struct AnDriver {
+    int pc;          // where mode_ctl resumes
+    int req;         // expensive operation it is waiting for
+    int k;           // greedy step (number of promotions so far + 1)
+    int added;       // sample promoted before the pending fit (-1: none; lets the inverse iteration start warm)
+    int removed;     // support points dropped by the last cleanup pass
+    int nz;          // zeros of the current fit (in s.roots)
+    double res;      // largest residual / max|F| of the last fit
+};
+
+// the three expensive operations
+template <class W>
+PSI_HD void mode_heavy(int req, const AAAScratch& s, AAAState& st, AnDriver& d) {
+    if (req == kReqFit) d.res = aaa_fit_compute<W>(s, st, d.added);
+    else if (req == kReqPoles) aaa_poles_compute<W>(s, st);
+    else if (req == kReqZeros) aaa_zeros_compute<W>(s, st);
+}
+
+// Runs until the search needs an expensive operation (returned, also in d.req) or is finished (d.pc == kPcDone:
+// kReqNone = plan filled in, kReqFailed = non-finite samples, the reference's ValueError).
+template <class W>
+PSI_HD int mode_ctl(const ModeCfg& cfg, int level, int n_guess, const AAAScratch& s, AAAState& st, AnDriver& d,
+                    ModePlan& plan) {
+    const int lane = W::lane(), M = st.M;
+    d.req = kReqNone;
+    for (;;) {
+        switch (d.pc) {
+        case kPcStart: {                                   // RationalApproximation.calculate (complex_roots.py:126-176)
+            st.clean_tol = cfg.clean_tol;
+            aaa_memo_clear<W>(s, st);
+            double fm = 0.0; bool fin = true;
+#pragma unroll 1
+            for (int i = lane; i < M; i += W::width) {
+                fm = fmax(fm, a_abs(s.F[i]));
+                if (!finite_c(s.F[i]) || !finite_c(s.Z[i])) fin = false;
+            }
+            st.fmax = a_max<W>(fm);
+            if (W::any(!fin)) { d.pc = kPcDone; d.req = kReqFailed; return d.req; }
+#pragma unroll 1
+            for (int i = lane; i < M; i += W::width) s.mask[i] = (i < 2) ? 1 : 0;
+            W::sync();
+            st.v_m = 0;
+            d.k = 1; d.added = -1;
+            d.pc = kPcGreedyNext;                          // the two-point fit never ends the greedy loop
+            if (!aaa_fit_lookup<W>(s, st, &d.res)) { d.req = kReqFit; return d.req; }
+            continue;
+        }
+        case kPcGreedyNext: {
+            if (d.k >= M / 2) { d.pc = kPcGreedyEnd; continue; }
+            // promote the worst-fitted sample (first maximum, like numpy.argmax)
+            int best = -1; double bv = -1.0;
+            for (int i = lane; i < st.r; i += W::width)
+                if (s.R[i] > bv) { bv = s.R[i]; best = i; }
+            W::argmax(bv, best);
+            const int added = s.off[best];
+            W::sync();
+            if (lane == 0) s.mask[added] = 1;
+            W::sync();
+            d.added = added; d.k += 1;
+            d.pc = kPcGreedyFit;
+            if (!aaa_fit_lookup<W>(s, st, &d.res)) { d.req = kReqFit; return d.req; }
+            continue;
+        }
+        case kPcGreedyFit:
+            d.pc = d.res < st.tol ? kPcGreedyEnd : kPcGreedyNext;
+            continue;
+        case kPcGreedyEnd:
+#pragma unroll 1
+            for (int i = lane; i < M; i += W::width) s.g_mask[i] = s.mask[i];
+            W::sync();
+            d.pc = kPcClean;
+            continue;
+        case kPcClean:                                     // cleanup passes until nothing is removed (:286-329)
+            d.pc = kPcCleanApply;
+            if (!aaa_poles_ready(s, st)) { d.req = kReqPoles; return d.req; }
+            continue;
+        case kPcCleanApply:
+            d.removed = aaa_cleanup_apply<W>(s, st);
+            d.added = -1;
+            d.pc = kPcCleanFit;
+            if (!aaa_fit_lookup<W>(s, st, &d.res)) { d.req = kReqFit; return d.req; }
+            continue;
+        case kPcCleanFit:
+            d.pc = d.removed != 0 ? kPcClean : kPcZeros;
+            continue;
+        case kPcZeros:
+            d.pc = kPcHalve;
+            if (!aaa_zeros_load<W>(s, st, &d.nz)) { d.pc = kPcZerosDone; d.req = kReqZeros; return d.req; }
+            continue;
+        case kPcZerosDone:
+            d.nz = st.m - 1 <= 0 ? 0 : s.memo_nz[st.slot];
+            d.pc = kPcHalve;
+            continue;
+        case kPcHalve: {
+            // halve clean_tol until enough support points and one growing zero inside the domain (:174-217)
+            const int need = 4 * (1 + level + n_guess);
+            bool growing = false;
+            for (int k = 0; k < d.nz; ++k) {
+                const cx z = s.roots[k];
+                if (cfg.dom.is_in(z) && z.im > 0.0) growing = true;
+            }
+            if (st.m >= need && growing) { d.pc = kPcPlan; continue; }
+            st.clean_tol = 0.5 * st.clean_tol;
+            if (st.clean_tol < st.tol) { d.pc = kPcPlan; continue; }
+            // calculate() again on the same samples: the greedy phase does not depend on clean_tol -> replay it
+            W::sync();
+#pragma unroll 1
+            for (int i = lane; i < M; i += W::width) s.mask[i] = s.g_mask[i];
+            W::sync();
+            d.added = -1;
+            d.pc = kPcReplayFit;
+            if (!aaa_fit_lookup<W>(s, st, &d.res)) { d.req = kReqFit; return d.req; }
+            continue;
+        }
+        case kPcReplayFit:
+            d.pc = kPcClean;
+            continue;
+        case kPcPlan: {
+            const int nz = d.nz;
+            // zoom candidates: below the top of the box, inside in Re; by decreasing Im, at least box_dx
+            // apart in Re, at most four (:236-261)
+            plan.box_dx = pow(10.0, -1.0 - 0.5 * level);
+            plan.n_zoom = 0;
+            {
+                int nc = 0;
+                for (int k = 0; k < nz; ++k) {
+                    const cx z = s.roots[k];
+                    if (z.im < cfg.dom.ymax && z.re < cfg.dom.xmax && z.re > cfg.dom.xmin) ++nc;
+                }
+                W::sync();
+                for (int k = lane; k < nz; k += W::width) {       // rank by Im (ascending) into tmp
+                    const cx z = s.roots[k];
+                    if (!(z.im < cfg.dom.ymax && z.re < cfg.dom.xmax && z.re > cfg.dom.xmin)) continue;
+                    int rank = 0;
+                    for (int l = 0; l < nz; ++l) {
+                        const cx y = s.roots[l];
+                        if (!(y.im < cfg.dom.ymax && y.re < cfg.dom.xmax && y.re > cfg.dom.xmin)) continue;
+                        if (y.im < z.im || (y.im == z.im && l < k)) ++rank;
+                    }
+                    s.tmp[rank] = z;
+                }
+                W::sync();
+                for (int i = nc - 1; i >= 0 && plan.n_zoom < 4; --i) {
+                    const cx z = s.tmp[i];
+                    bool ok = true;
+                    for (int q = 0; q < plan.n_zoom; ++q) if (fabs(z.re - plan.zoom[q].re) < plan.box_dx) ok = false;
+                    if (ok) plan.zoom[plan.n_zoom++] = z;
+                }
+            }
+            // start values of the polish: zeros inside the domain, else the least damped candidate
+            int n0 = 0;
+            W::sync();
+            if (lane == 0) {
+                int c = 0;
+                for (int k = 0; k < nz; ++k) if (cfg.dom.is_in(s.roots[k])) s.w0[c++] = s.roots[k];
+            }
+            for (int k = 0; k < nz; ++k) if (cfg.dom.is_in(s.roots[k])) ++n0;
+            plan.max_iter = cfg.max_secant;
+            if (level < cfg.max_zoom) plan.max_iter = cfg.n_sample;
+            if (n0 == 0 && plan.n_zoom > 0) {
+                if (lane == 0) s.w0[0] = plan.zoom[0];
+                n0 = 1;
+                plan.max_iter = 5;
+            }
+            W::sync();
+            plan.n0 = n0;
+            d.pc = kPcDone;
+            return kReqNone;
+        }
+        default:
+            return kReqNone;
+        }
+    }
+}
+
+// One zoom level in one go (single-warp form).  Returns false when the samples are not finite (ValueError in
+// the reference).
 template <class W>
 PSI_HD bool mode_analyze(const ModeCfg& cfg, int level, int n_guess, const AAAScratch& s, AAAState& st,
                          ModePlan& plan) {
-    st.clean_tol = cfg.clean_tol;
-    if (!aaa_calculate<W>(s, st, false)) return false;
-    int nz = aaa_zeros<W>(s, st);
-    // halve clean_tol until enough support points and one growing zero inside the domain (:174-217)
-    const int need = 4 * (1 + level + n_guess);
+    AnDriver d;
+    d.pc = kPcStart; d.req = kReqNone; d.k = 1; d.added = -1; d.removed = 0; d.nz = 0; d.res = 0.0;
     for (;;) {
-        bool growing = false;
-        for (int k = 0; k < nz; ++k) {
-            const cx z = s.roots[k];
-            if (cfg.dom.is_in(z) && z.im > 0.0) growing = true;
-        }
-        if (st.m >= need && growing) break;
-        st.clean_tol = 0.5 * st.clean_tol;
-        if (st.clean_tol < st.tol) break;
-        aaa_calculate<W>(s, st, true);
-        nz = aaa_zeros<W>(s, st);
+        const int req = mode_ctl<W>(cfg, level, n_guess, s, st, d, plan);
+        if (req == kReqFailed) return false;
+        if (d.pc == kPcDone) return true;
+        mode_heavy<W>(req, s, st, d);
     }
-    // zoom candidates: below the top of the box, inside in Re; by decreasing Im, at least box_dx
-    // apart in Re, at most four (:236-261)
-    plan.box_dx = pow(10.0, -1.0 - 0.5 * level);
-    plan.n_zoom = 0;
-    {
-        int nc = 0;
-        for (int k = 0; k < nz; ++k) {
-            const cx z = s.roots[k];
-            if (z.im < cfg.dom.ymax && z.re < cfg.dom.xmax && z.re > cfg.dom.xmin) ++nc;
-        }
-        W::sync();
-        for (int k = W::lane(); k < nz; k += W::width) {       // rank by Im (ascending) into tmp
-            const cx z = s.roots[k];
-            if (!(z.im < cfg.dom.ymax && z.re < cfg.dom.xmax && z.re > cfg.dom.xmin)) continue;
-            int rank = 0;
-            for (int l = 0; l < nz; ++l) {
-                const cx y = s.roots[l];
-                if (!(y.im < cfg.dom.ymax && y.re < cfg.dom.xmax && y.re > cfg.dom.xmin)) continue;
-                if (y.im < z.im || (y.im == z.im && l < k)) ++rank;
-            }
-            s.tmp[rank] = z;
-        }
-        W::sync();
-        for (int i = nc - 1; i >= 0 && plan.n_zoom < 4; --i) {
-            const cx z = s.tmp[i];
-            bool ok = true;
-            for (int q = 0; q < plan.n_zoom; ++q) if (fabs(z.re - plan.zoom[q].re) < plan.box_dx) ok = false;
-            if (ok) plan.zoom[plan.n_zoom++] = z;
-        }
-    }
-    // start values of the polish: zeros inside the domain, else the least damped candidate
-    int n0 = 0;
-    W::sync();
-    if (W::lane() == 0) {
-        int c = 0;
-        for (int k = 0; k < nz; ++k) if (cfg.dom.is_in(s.roots[k])) s.w0[c++] = s.roots[k];
-    }
-    for (int k = 0; k < nz; ++k) if (cfg.dom.is_in(s.roots[k])) ++n0;
-    plan.max_iter = cfg.max_secant;
-    if (level < cfg.max_zoom) plan.max_iter = cfg.n_sample;
-    if (n0 == 0 && plan.n_zoom > 0) {
-        if (W::lane() == 0) s.w0[0] = plan.zoom[0];
-        n0 = 1;
-        plan.max_iter = 5;
-    }
-    W::sync();
-    plan.n0 = n0;
-    return true;
 }
 
 // Returns a ModeStatus; out_roots[0..min(*n_roots, max_roots)) receive the roots inside the domain,
