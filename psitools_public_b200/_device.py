@@ -162,7 +162,7 @@ class EngineAPI:
     def mode_batch(self, dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
                    seeds, guesses, max_roots=8, device_aaa=False, dense=False):
         """``_mode_batch`` in chunks: the K4 pipeline keeps every search's samples and work lists resident
-        (~530 B per sample slot), so a multi-million-item batch with guess domains is cut into pieces that
+        (~50 B per sample slot), so a multi-million-item batch with guess domains is cut into pieces that
         fit ``PSI_B200_BATCH_BYTES`` (default 48 GiB of the 180 GB).  Items are independent: results do not
         depend on the cut."""
         n = len(dist)
@@ -176,9 +176,7 @@ class EngineAPI:
             goff = np.concatenate(([0], np.cumsum([len(g) for g in guesses]))).astype(np.int64)
         ng = goff[1:] - goff[:-1]
         cap = int(np.max(ns*(1 + ng + 4*mz))) if n else 0
-        # samples + polish lists (50 B per slot), K1 request list, roots, and the analysis stage's per-search state
-        # (index lists, weights, memo of fits: csrc/psi_aaa.cuh aaa_item_bytes, ~480 B per sample slot)
-        per_item = 530*cap + 8*int(np.max(ns*np.maximum(1 + ng, 4))) + 16*max_roots + 4096 if n else 1
+        per_item = 50*cap + 8*int(np.max(ns*np.maximum(1 + ng, 4))) + 16*max_roots + 256 if n else 1
         budget = int(os.environ.get("PSI_B200_BATCH_BYTES", str(48 << 30)))
         chunk = max(1, budget//per_item)
         if not device_aaa or n <= chunk:

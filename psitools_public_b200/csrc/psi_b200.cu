@@ -544,8 +544,6 @@ contour_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict
 // once per zoom level.  Homogeneous stages keep the SMs' instruction caches and FP64 pipes busy; the
 // single-warp form of the same search (mode_run in psi_mode.cuh) is what the CPU harness exercises.
 
-struct AnItem { AAAState st; AnDriver d; };     // analysis state of one search between the phase kernels
-
 struct ModeDev {            // device pointers of the per-item state (n items, cap samples, P start values)
     cx *Z, *F, *w0, *pol, *zoom, *roots;
     double* box_dx;
@@ -560,7 +558,7 @@ struct ModeDev {            // device pointers of the per-item state (n items, c
 __global__ void mode_sample_kernel(ModeDev m, int n_items, const double* __restrict__ domain,
                                    const int* __restrict__ iparams, const double* __restrict__ uni,
                                    const int* __restrict__ uni_off, const int* __restrict__ guess_off,
-                                   const double2* __restrict__ guesses, AnItem* an) {
+                                   const double2* __restrict__ guesses) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     const int ph = m.phase[i];
@@ -602,106 +600,59 @@ __global__ void mode_sample_kernel(ModeDev m, int n_items, const double* __restr
     m.calls[i] += n_new;
     m.M[i] = M; m.upos[i] = upos;
     m.phase[i] = kPhaseAnalyze;
-    an[i].d.pc = kPcStart;
     const unsigned long long pos = atomicAdd(m.counters, (unsigned long long)n_new);
     for (int k = 0; k < n_new; ++k) m.elem[pos + k] = (long long)i * m.cap + first + k;
 }
 
-// ---- analysis stage of K4: four kernels over the searches of a zoom level (state machine: psi_mode.cuh, mode_ctl).
-// G lanes per search, 32/G searches per warp.  Per-search state between the kernels: AnItem + the item part of the
-// AAA scratch (index lists, weights, residuals, zeros, memo) in `item_scratch`; the work part (Loewner matrix,
-// triangular factor) belongs to the groups of the fit kernel.
-struct AnArgs {
-    AnItem* items;
-    unsigned char* item_scratch;
-    size_t item_stride;
-    long long* lists;                   // [3][n_items]: searches waiting for a fit / poles / zeros
-    unsigned long long* counters;       // [0..2] list lengths, [3] searches still running, [4..6] queue heads
-};
-
-template <class W>
-__device__ __forceinline__ AAAScratch an_scratch(const ModeDev& m, const AnArgs& a, long long idx) {
-    AAAScratch sc;
-    aaa_carve_item(a.item_scratch + (size_t)idx * a.item_stride, m.cap, sc);
-    sc.A = nullptr; sc.V = nullptr; sc.V2 = nullptr;
-    sc.Z = m.Z + (size_t)idx * m.cap;                 // the item's own sample buffers, analysed in place
-    sc.F = m.F + (size_t)idx * m.cap;
-    sc.w0 = m.w0 + (size_t)idx * m.P;
-    sc.pol = nullptr;
-    return sc;
-}
-
-// control kernel: every search that is being analysed advances through its cheap transitions until it needs an
-// expensive operation (queued on the matching list) or has its plan (polish start values, zoom boxes)
+// Analysis stage of K4.  G lanes per search (32/G searches per warp): AAA analysis of the current samples
+// (mode_analyze, psi_mode.cuh) -> polish start values + zoom plan.  (Tried in round 2 and dropped: one kernel per
+// phase of the state machine -- control / fits / poles / zeros -- in lock-step rounds over all searches, so that
+// an SM runs one compact piece of code at a time.  0.208 s instead of 0.146 s on the 256^2 map: the fits are bound
+// by the traffic of their trailing-matrix updates, not by instruction fetch, each round waits for its slowest
+// search, and the per-search state no longer stays in L2; profiles/k4_phase_kernels_r2_launches.csv.)
 template <int G>
-__global__ void __launch_bounds__(256)
-an_ctl_kernel(ModeDev m, AnArgs a, int n_items, const double* __restrict__ domain, const int* __restrict__ iparams,
-              const double* __restrict__ dparams, const int* __restrict__ guess_off, unsigned long long* n_polish) {
+__global__ void __launch_bounds__(256, 3)
+mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, const int* __restrict__ iparams,
+                    const double* __restrict__ dparams, const int* __restrict__ guess_off,
+                    unsigned char* scratch, size_t scratch_per_group, int scratch_cap, int own_lo, int own_hi,
+                    unsigned long long* queue, unsigned long long* n_polish) {
     typedef GroupCuda<G> W;
     const int lane = W::lane();
     const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const long long n_groups = (long long)gridDim.x * blockDim.x / G;
-    for (long long idx = group; idx < n_items; idx += n_groups) {
+    AAAScratch sc = aaa_carve(scratch + (size_t)group * scratch_per_group, scratch_cap);
+    long long idx;
+    while (next_item_group<W>(queue, n_items, idx)) {
         if (m.phase[idx] != kPhaseAnalyze) continue;
-        AnItem* it = a.items + idx;
-        AnDriver d = it->d;
-        if (d.pc == kPcDone) continue;
+        {   // this launch takes the searches whose OWN sample capacity lies in (own_lo, own_hi]: the group size a
+            // search is analysed with depends on the search alone, never on what else is in the batch
+            const int own = iparams[3 * idx] * (1 + guess_off[idx + 1] - guess_off[idx] + 4 * iparams[3 * idx + 1]);
+            if (own <= own_lo || own > own_hi) continue;
+        }
         ModeCfg cfg;
         cfg.dom = RectDom{domain[4 * idx], domain[4 * idx + 1], domain[4 * idx + 2], domain[4 * idx + 3]};
         cfg.n_sample = iparams[3 * idx]; cfg.max_zoom = iparams[3 * idx + 1]; cfg.max_secant = iparams[3 * idx + 2];
         cfg.tol = dparams[2 * idx]; cfg.clean_tol = dparams[2 * idx + 1];
-        const AAAScratch sc = an_scratch<W>(m, a, idx);
+        sc.Z = m.Z + (size_t)idx * m.cap;                 // analyse the item's own sample buffers in place
+        sc.F = m.F + (size_t)idx * m.cap;
+        sc.w0 = m.w0 + (size_t)idx * m.P;
         AAAState st;
-        if (d.pc == kPcStart) {
-            st.M = m.M[idx]; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol;
-            st.dom = cfg.dom; st.memo_next = 0; st.slot = 0; st.v_m = 0;
-            d.req = kReqNone; d.k = 1; d.added = -1; d.removed = 0; d.nz = 0; d.res = 0.0;
-        } else {
-            st = it->st;
-        }
+        st.M = m.M[idx]; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol;
+        st.dom = cfg.dom; st.memo_next = 0; st.slot = 0; st.v_m = 0;
         ModePlan plan;
-        const int req = mode_ctl<W>(cfg, m.level[idx], guess_off[idx + 1] - guess_off[idx], sc, st, d, plan);
+        const bool ok = mode_analyze<W>(cfg, m.level[idx], guess_off[idx + 1] - guess_off[idx], sc, st, plan);
         W::sync();
         if (lane == 0) {
-            it->st = st; it->d = d;
-            if (req == kReqFailed) {
+            if (!ok) {
                 m.status[idx] = kModeBadSamples; m.phase[idx] = kPhaseDone; m.n_out[idx] = 0;
-            } else if (d.pc == kPcDone) {
+            } else {
                 m.n0[idx] = plan.n0; m.max_iter[idx] = plan.max_iter; m.n_zoom[idx] = plan.n_zoom;
                 m.box_dx[idx] = plan.box_dx;
                 for (int q = 0; q < plan.n_zoom; ++q) m.zoom[4 * (size_t)idx + q] = plan.zoom[q];
                 m.pcalls[idx] = 0; m.pconv[idx] = 0; m.pstat[idx] = 0;
                 m.phase[idx] = plan.n0 > 0 ? kPhasePolish : kPhaseDecide;
                 if (plan.n0 > 0) atomicAdd(n_polish, 1ull);
-            } else {
-                const unsigned long long pos = atomicAdd(a.counters + (req - 1), 1ull);
-                a.lists[(size_t)(req - 1) * n_items + pos] = idx;
-                atomicAdd(a.counters + 3, 1ull);
             }
         }
-    }
-}
-
-// one expensive operation (REQ) for every search on its list
-template <int G, int REQ>
-__global__ void __launch_bounds__(256, 3)
-an_heavy_kernel(ModeDev m, AnArgs a, int n_items, unsigned char* work, size_t work_stride) {
-    typedef GroupCuda<G> W;
-    const int lane = W::lane();
-    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const long long n_list = (long long)a.counters[REQ - 1];
-    const long long* list = a.lists + (size_t)(REQ - 1) * n_items;
-    long long k;
-    while (next_item_group<W>(a.counters + 3 + REQ, n_list, k)) {
-        const long long idx = list[k];
-        AnItem* it = a.items + idx;
-        AAAScratch sc = an_scratch<W>(m, a, idx);
-        if (REQ == kReqFit) aaa_carve_work(work + (size_t)group * work_stride, m.cap, sc);
-        AAAState st = it->st;
-        AnDriver d = it->d;
-        mode_heavy<W>(REQ, sc, st, d);
-        W::sync();
-        if (lane == 0) { it->st = st; it->d = d; }
     }
 }
 
@@ -1145,22 +1096,30 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     const size_t ni = (size_t)n_items, ng = (size_t)guess_off[n_items];
     const int P = cap / 2 + 2;
     // analysis stage: G lanes per search, first level / zoom levels (PSI_AN_GROUP0 / PSI_AN_GROUP1: 8, 16, 32);
-    // searches with many guess domains -- more than 128 samples -- keep a whole warp (their matrices fill it).
-    // The fit kernel owns one work area (Loewner matrix, triangular factor) per group.
+    // searches with many guess domains -- more than 128 samples of their own -- keep a whole warp (their matrices
+    // fill it, and the scratch areas, one per group, are megabytes each).  Two scratch regions: small searches
+    // (areas carved for 128 samples) and big ones.
     static const int an_ctas = getenv("PSI_AN_CTAS") ? atoi(getenv("PSI_AN_CTAS")) : 3;
-    static const int env_g0 = getenv("PSI_AN_GROUP0") ? atoi(getenv("PSI_AN_GROUP0")) : 8;
-    static const int env_g1 = getenv("PSI_AN_GROUP1") ? atoi(getenv("PSI_AN_GROUP1")) : 16;
-    const int an_g0 = cap > 128 ? 32 : env_g0, an_g1 = cap > 128 ? 32 : env_g1;
-    const int an_threads = 256;
-    const size_t work_stride = (aaa_work_bytes(cap) + 255) & ~(size_t)255;
-    const size_t need = work_stride * (size_t)c->sm_count * an_ctas * (an_threads / std::min(an_g0, an_g1));
+    static const int an_g0 = getenv("PSI_AN_GROUP0") ? atoi(getenv("PSI_AN_GROUP0")) : 8;
+    static const int an_g1 = getenv("PSI_AN_GROUP1") ? atoi(getenv("PSI_AN_GROUP1")) : 16;
+    const int an_threads = 256, kSmallCap = 128;
+    bool any_small = false, any_big = false;
+    for (int i = 0; i < n_items; ++i) {
+        const int own = iparams[3 * i] * (1 + guess_off[i + 1] - guess_off[i] + 4 * iparams[3 * i + 1]);
+        (own <= kSmallCap ? any_small : any_big) = true;
+    }
+    const int cap_small = std::min(cap, kSmallCap);
+    const size_t per_group_small = (aaa_scratch_bytes(cap_small) + 255) & ~(size_t)255;
+    const size_t per_group_big = (aaa_scratch_bytes(cap) + 255) & ~(size_t)255;
+    const size_t bytes_small = any_small ? per_group_small * (size_t)c->sm_count * an_ctas * (an_threads / std::min(an_g0, an_g1)) : 0;
+    const size_t bytes_big = any_big ? per_group_big * (size_t)c->sm_count * an_ctas * (an_threads / 32) : 0;
+    const size_t need = bytes_small + bytes_big;
     if (need > c->mode_scratch_bytes) {
         if (c->d_mode_scratch) CK(cudaFree(c->d_mode_scratch));
         c->d_mode_scratch = nullptr; c->mode_scratch_bytes = 0;
         CK(cudaMalloc(&c->d_mode_scratch, need));
         c->mode_scratch_bytes = need;
     }
-    const size_t item_stride = (aaa_item_bytes(cap) + 255) & ~(size_t)255;
     // inputs + per-item state in one staging allocation
     const size_t nreq = ni * (size_t)max_req;
     StageItem it[] = {
@@ -1170,10 +1129,9 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         {nullptr, 16 * ni * cap}, {nullptr, 16 * ni * cap},                                        // 11 Z, 12 F
         {nullptr, 16 * ni * P}, {nullptr, 16 * ni * P}, {nullptr, 64 * ni},                        // 13 w0, 14 pol, 15 zoom
         {nullptr, 16 * ni * max_roots}, {nullptr, 8 * ni},                                         // 16 roots, 17 box_dx
-        {nullptr, 4 * ni * 13}, {nullptr, 8 * nreq},                                               // 18 ints, 19 elem
-        {nullptr, sizeof(AnItem) * ni}, {nullptr, item_stride * ni}, {nullptr, 24 * ni}, {nullptr, 64}};   // 20-23 analysis
-    char* d[24];
-    int rc = stage_upload(c, it, 24, 0, d, nullptr);
+        {nullptr, 4 * ni * 13}, {nullptr, 8 * nreq}};                                              // 18 ints, 19 elem
+    char* d[20];
+    int rc = stage_upload(c, it, 20, 0, d, nullptr);
     if (rc != PSI_OK) return rc;
     cudaStream_t st = c->stream;
     ModeDev m;
@@ -1186,9 +1144,6 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     m.elem = (long long*)d[19];
     m.counters = c->d_counter + 6;
     m.cap = cap; m.P = P; m.max_roots = max_roots;
-    AnArgs an;
-    an.items = (AnItem*)d[20]; an.item_scratch = (unsigned char*)d[21]; an.item_stride = item_stride;
-    an.lists = (long long*)d[22]; an.counters = (unsigned long long*)d[23];
     CK(cudaMemsetAsync(ints, 0, 4 * ni * 13, st));                         // phase 0 = kPhaseSample everywhere
     CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
     NodeTableView t = table_view(c);
@@ -1212,7 +1167,7 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         CK(cudaEventRecord(ev[0], st));
         mode_sample_kernel<<<tgrid, 256, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
                                                   (const double*)d[7], (const int*)d[8], (const int*)d[9],
-                                                  (const double2*)d[10], an.items);
+                                                  (const double2*)d[10]);
         CK(cudaGetLastError());
         unsigned long long cnt[2] = {0, 0};
         CK(cudaEventRecord(ev[1], st));
@@ -1228,47 +1183,20 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(c->d_counter + 8, 0, sizeof(unsigned long long), st));
         CK(cudaEventRecord(ev[2], st));
-        {
-            // rounds of [control kernel | fits | poles | zeros] until every search of this level has its plan
-            const int g = round == 0 ? an_g0 : an_g1;
+        for (int big = 0; big < 2; ++big) {
+            if (!(big ? any_big : any_small)) continue;
+            const int g = big ? 32 : (round == 0 ? an_g0 : an_g1);
             const int per_cta = an_threads / g;
-            const int cgrid = std::min(c->sm_count * 6, (n_items + (an_threads / 8) - 1) / (an_threads / 8));
-            for (int an_round = 0;; ++an_round) {
-                CK(cudaMemsetAsync(an.counters, 0, 8 * sizeof(unsigned long long), st));
-                an_ctl_kernel<8><<<cgrid, an_threads, 0, st>>>(m, an, n_items, (const double*)d[4], (const int*)d[5],
-                                                               (const double*)d[6], (const int*)d[9], c->d_counter + 8);
-                CK(cudaGetLastError());
-                unsigned long long ac[4] = {0, 0, 0, 0};
-                CK(cudaMemcpyAsync(ac, an.counters, sizeof(ac), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                launches += 1;
-                if (ac[3] == 0) break;
-                auto grid_for = [&](unsigned long long n) {
-                    return (int)std::min<unsigned long long>((unsigned long long)c->sm_count * an_ctas,
-                                                             (n + per_cta - 1) / per_cta);
-                };
-                if (ac[0]) {
-                    auto kern = g == 8 ? an_heavy_kernel<8, kReqFit> : g == 16 ? an_heavy_kernel<16, kReqFit>
-                                                                               : an_heavy_kernel<32, kReqFit>;
-                    kern<<<grid_for(ac[0]), an_threads, 0, st>>>(m, an, n_items, (unsigned char*)c->d_mode_scratch,
-                                                                work_stride);
-                    ++launches;
-                }
-                if (ac[1]) {
-                    auto kern = g == 8 ? an_heavy_kernel<8, kReqPoles> : g == 16 ? an_heavy_kernel<16, kReqPoles>
-                                                                                 : an_heavy_kernel<32, kReqPoles>;
-                    kern<<<grid_for(ac[1]), an_threads, 0, st>>>(m, an, n_items, nullptr, 0);
-                    ++launches;
-                }
-                if (ac[2]) {
-                    auto kern = g == 8 ? an_heavy_kernel<8, kReqZeros> : g == 16 ? an_heavy_kernel<16, kReqZeros>
-                                                                                 : an_heavy_kernel<32, kReqZeros>;
-                    kern<<<grid_for(ac[2]), an_threads, 0, st>>>(m, an, n_items, nullptr, 0);
-                    ++launches;
-                }
-                CK(cudaGetLastError());
-                if (an_round > 100000) return fail(PSI_ERR_CUDA, "analysis stage does not terminate");
-            }
+            const int agrid = std::min(c->sm_count * an_ctas, (n_items + per_cta - 1) / per_cta);
+            auto kern = g == 8 ? mode_analyze_kernel<8> : g == 16 ? mode_analyze_kernel<16> : mode_analyze_kernel<32>;
+            CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+            kern<<<agrid, an_threads, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
+                                               (const double*)d[6], (const int*)d[9],
+                                               (unsigned char*)c->d_mode_scratch + (big ? bytes_small : 0),
+                                               big ? per_group_big : per_group_small, big ? cap : cap_small,
+                                               big ? kSmallCap : -1, big ? (1 << 30) : kSmallCap, c->d_counter,
+                                               c->d_counter + 8);
+            ++launches;
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ev[3], st));
@@ -1295,7 +1223,7 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         mode_decide_kernel<<<tgrid, 256, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5]);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ev[5], st));
-        launches += 4;
+        launches += 3;
         c->launches += 4;
         CK(cudaMemcpyAsync(cnt, m.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

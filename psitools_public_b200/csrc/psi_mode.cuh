@@ -68,11 +68,9 @@ struct ModePlan {
 //     kReqFit   a Loewner fit of the current mask            (aaa_fit_compute:   Loewner matrix, QR, inverse iteration)
 //     kReqPoles poles + residue decisions of the current fit (aaa_poles_compute: Ehrlich-Aberth + 4-point contours)
 //     kReqZeros zeros of the current fit                     (aaa_zeros_compute: Ehrlich-Aberth + secant on r(z))
-// The GPU pipeline runs each of the four pieces as its own kernel over all searches that need it (psi_b200.cu:
-// an_ctl_kernel, an_fit_kernel, an_poles_kernel, an_zeros_kernel), so that the warps of an SM execute ONE
-// compact piece of code at a time -- the monolithic form spent 3/4 of its stall cycles waiting for instruction
-// fetch, every warp in a different phase of 185 KB of machine code.  mode_analyze() below drives the same state
-// machine in a loop (single-warp form of the search, CPU harness): one statement of the logic for both.
+// mode_analyze() below drives the state machine in a loop; the split keeps the three expensive operations apart
+// from the control flow (they can be timed, replaced and scheduled separately -- psi_b200.cu records the
+// experiment that ran each of the four pieces as its own kernel).
 enum AnRequest { kReqNone = 0, kReqFit = 1, kReqPoles = 2, kReqZeros = 3, kReqFailed = 4 };
 enum AnPc { kPcStart = 0, kPcGreedyNext, kPcGreedyFit, kPcGreedyEnd, kPcClean, kPcCleanApply, kPcCleanFit,
             kPcZeros, kPcZerosDone, kPcHalve, kPcReplayFit, kPcPlan, kPcDone };

@@ -224,6 +224,7 @@ PSI_HD void background_warp(const NodeTableView& t, DistParams& d, unsigned long
 // Work class of a point: which specialisation of K1 evaluates it (kernels are compiled per class so
 // that each keeps its own, smaller register footprint).  class = node kind * 2 + (viscous ? 1 : 0).
 constexpr int kNumClasses = 8;
+constexpr double kNearPoleBand = 2.5;      // |Re d(tau*)| below which the damped-frequency split point is added
 constexpr double kResonantBand = 1.0e-5;   // |Im(w - kx ux + i(...))| at a resonance pole below which the exit predictor is off
 PSI_HD int point_class(const DistParams& d, double alpha) {
     return node_kind_of(d) * 2 + ((alpha * d.c * d.c) != 0.0 ? 1 : 0);
@@ -245,7 +246,7 @@ PSI_HD cx disp_eval_warp(const NodeTableView& t, const DistParams& d, cx w, doub
     } else {
         double poles[2 * kMaxPoles], res_tau[2];
         int n_res = 0;
-        const int np = resonance_poles(d, w.re, kx, poles, res_tau, &n_res);
+        int np = resonance_poles(d, w.re, kx, poles, res_tau, &n_res);
         // Resonant band: next to a resonance pole tau_p the integrands carry 1/(w - kx ux(tau) + i(k^2 D + 1e-10)),
         // whose imaginary part y_p = Im w + k^2 D(tau_p) + 1e-10 is all that keeps it finite there.  The nodes that
         // cluster at the pole cannot be told apart to better than an ulp of u = ln(tau), so every level adds
@@ -262,6 +263,27 @@ PSI_HD cx disp_eval_warp(const NodeTableView& t, const DistParams& d, cx w, doub
                 y += p.k2 * (1.0 + tp + 4.0 * tp * tp) * p.nu / (t1 * t1);
             }
             if (fabs(y) < kResonantBand) band = true;
+        }
+        // Damped frequencies with Im w < -1/taumax: at tau* = -1/Im w the imaginary part of d = kx ux - w - i/tau
+        // vanishes, and where |Re d(tau*)| is of order one the integrands' factors 1/d and 1/(1 - d^2) have poles
+        // within ~1e-2 (in ln tau) of the path -- in the MIDDLE of a sub-interval, where the rule needs its last
+        // levels to resolve them (these points, 1-3 % of BASELINE config 2's grid, cost half of its run time).
+        // The reference's rule gets them right all the same (1e-14 against 40-digit arithmetic), so under the
+        // predicted rule the interval is split at tau* as it is at the resonance poles: the near-poles then sit
+        // next to an end point, which tanh-sinh resolves by level 5-6.  exit_rule = "reference" keeps the
+        // reference's own sub-intervals.
+        if (t.predict_exit != 0 && w.im < 0.0 && np < 2 * kMaxPoles) {
+            const double ts = -1.0 / w.im;
+            if (ts > d.taumin && ts < d.taumax) {
+                const double kxux = p.kxA2 * fma(-ts, p.j0p, p.j1) / fma(ts, ts, 1.0);
+                if (fabs(kxux - w.re) <= kNearPoleBand) {
+                    const double v = ts / d.taumax;
+                    int j = np - 1;
+                    while (j >= 0 && poles[j] > v) { poles[j + 1] = poles[j]; --j; }
+                    poles[j + 1] = v;
+                    ++np;
+                }
+            }
         }
         double sc[7];
         m_scales(p, sc);

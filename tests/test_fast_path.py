@@ -133,14 +133,77 @@ def test_config2_4096_points_vs_oracle(built):
     Mref = np.concatenate([r[1] for r in res])
     vgx = res[0][2]
     scale = np.median(np.abs(ref))
-    worst = 0.0
+    worst, off = 0.0, []
     for k, i in enumerate(pick):
         rt = max(1e-10, resonant_floor(w[i]))
         ex = det_extended(Mref[k], w[i], 50.0, 100.0, 0.0, 20.0, vgx)
-        worst = max(worst, abs(full[i] - ex)/(abs(ex) + scale))
-        assert abs(full[i] - ex) <= rt*(abs(ex) + scale), (w[i], abs(full[i] - ex)/abs(ex))
-        assert abs(full[i] - ref[k]) <= rt*(abs(ref[k]) + scale) + lu_noise_floor(w[i], 50.0, 100.0, 20.0, vgx), w[i]
-    print("config 2, 4096 points: max |D - det_exact(M_oracle)|/(|D| + median) = %.2e" % worst)
+        ok = abs(full[i] - ex) <= rt*(abs(ex) + scale) and \
+            abs(full[i] - ref[k]) <= rt*(abs(ref[k]) + scale) + lu_noise_floor(w[i], 50.0, 100.0, 20.0, vgx)
+        if ok:
+            worst = max(worst, abs(full[i] - ex)/(abs(ex) + scale))
+        else:
+            off.append((i, ref[k]))
+    print("config 2, 4096 points: max |D - det_exact(M_oracle)|/(|D| + median) = %.2e; %d points off the oracle"
+          % (worst, len(off)))
+    # Points off the oracle are admissible only next to the branch cuts of D in the damped corner of the grid
+    # (Im w < -1/taumax, see test_near_cut_points below), where the REFERENCE's quadrature has not converged;
+    # each of them is adjudicated by 40-digit arithmetic in favour of the product.
+    assert len(off) <= 8, len(off)
+    for i, r in off:
+        assert w[i].imag < -1.0/0.1, w[i]
+        _adjudicate(pd, w[i], full[i], r, 50.0, 100.0)
+
+
+def _adjudicate(pd, w, got, reference_value, kx, kz):
+    """40-digit value of D (tests/truth_mp.py, split at tau* = -1/Im w as a quadrature aid): the product must be
+    within 1e-8 of it and closer to it than the reference's value."""
+    import mpmath as mp
+    import truth_mp
+    t = truth_mp.TruthDispersion(pd.mu, [pd.taumin, pd.taumax], c=pd.c, j01=(pd.j0, pd.j1), rhod=pd.desc.rhod)
+    if w.imag < 0:
+        t.sd_poles = [mp.mpf(-1.0/w.imag)]
+    exact = t.calculate(w, kx, kz)
+    assert t.max_err < 1e-25
+    e_prod, e_ref = abs(got - exact)/abs(exact), abs(reference_value - exact)/abs(exact)
+    assert e_prod < 1e-8 and e_prod < e_ref, (w, e_prod, e_ref)
+    return e_prod, e_ref
+
+
+def test_near_cut_points(built):
+    """The damped corner of BASELINE config 2's grid (Im w < -1/taumax = -10, Re w in [-3.2, 0.2]).  There D has
+    branch cuts -- the curves w = kx ux(tau) - i/tau (+0, +-1), on which a pole of 1/d or 1/(1 - d^2) crosses the
+    real tau axis -- and next to them the reference's quadrature, which has no split point at tau* = -1/Im w, is
+    not converged after its 12 levels: O(1) errors against 40-digit arithmetic on ~0.05 % of the grid.  Under the
+    default rule the product splits at tau* (csrc/psi_quad.cuh) and is accurate there; exit_rule = 'reference'
+    reproduces the reference's values.  Checked: (1) away from the cuts default and literal rule agree to 1e-10;
+    (2) the points where they do not are few (< 3 % of this corner) and each sampled one is adjudicated by exact
+    arithmetic: product within 1e-8, reference further off; (3) literal rule == oracle at those points (the
+    product CAN reproduce the reference's numbers)."""
+    from oracle import psi_oracle as po
+    from psitools_public_b200 import PSIDispersion, TanhSinh
+    pd = PSIDispersion(3.0, [1e-8, 0.1], tanhsinh_integrator=TanhSinh())
+    re = np.linspace(-7.5, 7.5, 1024)
+    im = np.linspace(-12.5, 2.5, 1024)
+    re, im = re[(re > -3.2) & (re < 0.2)], im[im < -9.9][::2]
+    w = (re[None, :] + 1j*im[:, None]).ravel()
+    fast = pd.calculate(w, 50.0, 100.0)
+    try:
+        pd.ctx.exit_rule = "reference"
+        lit = pd.calculate(w, 50.0, 100.0)
+    finally:
+        pd.ctx.exit_rule = "predicted"
+    err = np.abs(fast - lit)/(np.abs(lit) + np.median(np.abs(lit)))
+    off = np.flatnonzero(err > 1e-10)
+    print("damped corner: %d of %d points differ by more than 1e-10 (max %.2e)" % (len(off), len(w), err.max()))
+    assert 0 < len(off) < 0.03*len(w)
+    order = off[np.argsort(-err[off])]
+    picks = list(order[:3]) + list(order[len(order)//2:len(order)//2 + 2])
+    od = po.Dispersion(po.DustDist.power_law(3.0, [1e-8, 0.1]), po.NodeTable())
+    for i in picks:
+        e_prod, e_ref = _adjudicate(pd, w[i], fast[i], lit[i], 50.0, 100.0)
+        oref = od.calculate(w[i], 50.0, 100.0)
+        print("  w = %s: product %.1e, reference rule %.1e off the exact value" % (w[i], e_prod, e_ref))
+        assert abs(lit[i] - oref) <= 1e-9*abs(oref), (w[i], lit[i], oref)      # literal rule reproduces the reference
 
 
 def test_polish_and_contour_loose_predictor_vs_literal(built):
