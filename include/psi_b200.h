@@ -131,17 +131,46 @@ int psi_mode_batch_host(psi_ctx* ctx, int n_items, const int* dist, const double
                         double* roots, int* n_roots, int* n_calls, int* status, long long* stats);
 
 /* Kernel K4 -- the same batch (same arguments, same outputs) with every search running ENTIRELY on the
- * device: one warp per item does the sampling, the D evaluations, the AAA rational approximation
- * (one-sided Jacobi SVD + Ehrlich-Aberth instead of LAPACK), the zoom logic and the secant polish
- * (csrc/psi_mode.cuh); one launch per work class, no host round trip.  status: 0 ok, 1 non-finite
- * samples (ValueError in the reference), 2 sample capacity, 3 start value on the real axis
- * (ValueError), 4 more roots than max_roots.  stats (16 slots) = {launches, D evaluations,
- * node evaluations, -, -, -, -, -, then microseconds on the stream of the five stages sample, K1, AAA
- * analysis, K3 polish, decide}. */
+ * device, as a pipeline of homogeneous kernels over all searches, repeated once per zoom level:
+ * sampling (thread per search) -> K1 on the searches' own sample buffers -> AAA analysis (8/16/32 lanes per
+ * search: greedy Loewner fits by Householder QR + inverse iteration, Froissart cleanup and zeros by
+ * Ehrlich-Aberth, clean_tol halving, zoom plan; csrc/psi_aaa.cuh, psi_mode.cuh) -> K3 secant polish -> decision.
+ * Host traffic per level: two 16-byte read-backs (request count, "anyone zooming?").  Replaces
+ * PSIMode.calculate (psi_mode.py:106-333) + RationalApproximation (complex_roots.py:38-368) for whole maps.
+ * status: 0 ok, 1 non-finite samples (ValueError in the reference), 2 sample capacity, 3 start value on the
+ * real axis (ValueError), 4 more roots than max_roots.  stats (16 slots) = {launches, D evaluations, node
+ * evaluations, -, -, -, -, -, then microseconds on the stream of the five stages sample, K1, AAA analysis,
+ * K3 polish, decide}.  At most PSI_MODE_MAX_SAMPLES samples per search. */
+#define PSI_MODE_MAX_SAMPLES 512
 int psi_mode_batch_device(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
                           const double* alpha, const double* domain, const int* iparams, const double* dparams,
                           const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,
                           double* roots, int* n_roots, int* n_calls, int* status, long long* stats);
+
+/* The same batch with the results left ON THE DEVICE: *rec_dev receives a device pointer to rec_rows
+ * (>= n_items, the excess zeroed) packed records of 4 + 2*max_roots doubles
+ *     {n_roots, status, n_function_call, 0, Re root_0, Im root_0, ..., root_{max_roots-1}}
+ * valid until the next call on the context -- what one rank of a multi-GPU map hands to ncclAllGather
+ * (torch.distributed.all_gather_into_tensor on a tensor wrapping the pointer) without a detour through host
+ * memory; replaces the pickled point-to-point result traffic of psi_mode_mpi.py:57-160 and the per-sweep
+ * bcast of psi_grid_refine.py:325-326. */
+int psi_mode_batch_device_rec(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
+                              const double* alpha, const double* domain, const int* iparams, const double* dparams,
+                              const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,
+                              int rec_rows, double** rec_dev, long long* stats);
+
+/* ONE search (PSIMode.calculate, psi_mode.py:106-333) through the same pipeline, with the caller's own stream
+ * of U[0,1) numbers (numpy's global legacy stream: n_uni >= 2*n_sample*(1 + n_guess + 4*max_zoom)) and
+ * everything PSIMode exposes afterwards: roots, n_function_call, z_sample / f_sample (cap =
+ * n_sample*(1 + n_guess + 4*max_zoom) complex slots each, *n_samples used), ra.maskF (cap ints), the count
+ * of random numbers consumed (so that the caller can advance its generator exactly as the reference would)
+ * and max_convergence_iterations.  domain = {xmin, xmax, ymin, ymax}, iparams = {n_sample, max_zoom_domains,
+ * max_secant_iterations}, dparams = {tol, clean_tol}. */
+int psi_mode_search_detail(psi_ctx* ctx, int dist, double kx, double kz, double alpha, const double* domain,
+                           const int* iparams, const double* dparams, const double* uni, int n_uni,
+                           const double* guesses, int n_guess, int max_roots, double* roots, int* n_roots,
+                           int* n_calls, int* status, double* z_sample, double* f_sample, int* n_samples,
+                           int* mask, int* n_uni_used, int* max_conv);
 
 /* Kernel K2 -- n_items ClosedPath(f, z_list).count_roots(max_iter, tol, max_step)
  * (complex_roots.py:517-625) in ONE launch: one warp per contour runs every refinement pass and the

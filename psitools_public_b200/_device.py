@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PSI_B200_LIB", os.path.join(_HERE, "libpsi_b200.so"))   # override: experiments only
 
 PSI_MAX_POLES = 4
+MODE_MAX_SAMPLES = 512            # PSI_MODE_MAX_SAMPLES of include/psi_b200.h
 KIND_POWERLAW, KIND_POWERBUMP, KIND_POWERBUMPTAIL = 0, 1, 2
 
 
@@ -66,6 +67,9 @@ _SIGNATURES = {
     "psi_engine_set_threads": (None, [C.c_int]),
     "psi_mode_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*10 + [C.c_int] + [_vp]*5),
     "psi_mode_batch_device": (C.c_int, [_vp, C.c_int] + [_vp]*10 + [C.c_int] + [_vp]*5),
+    "psi_mode_batch_device_rec": (C.c_int, [_vp, C.c_int] + [_vp]*10 + [C.c_int, C.c_int, C.POINTER(_vp), _vp]),
+    "psi_mode_search_detail": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp, _vp,
+                                         C.c_int, _vp, C.c_int, C.c_int] + [_vp]*10),
     "psi_contour_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*13),
     "psi_polish_batch_host": (C.c_int, [_vp, C.c_int] + [_vp]*12),
     "psi_refine_open": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_longlong,
@@ -132,6 +136,34 @@ def openblas_paths():
     return out
 
 
+def _checked_seeds(seeds, n):
+    """uint32 seeds; out-of-range values raise ValueError like numpy.random.seed (they must not wrap silently:
+    the device stream would then differ from the reference's)."""
+    s = np.broadcast_to(np.asarray(seeds), (n,))
+    if s.size and (np.any(s < 0) or np.any(s > 0xffffffff)):
+        raise ValueError("Seed must be between 0 and 2**32 - 1")
+    return np.ascontiguousarray(s, dtype=np.uint32)
+
+
+class DeviceRecords:
+    """Packed result records of a K4 batch that are still in device memory (psi_mode_batch_device_rec): ``rows``
+    rows of ``width`` = 4 + 2*max_roots doubles {n_roots, status, n_function_call, 0, roots...}.  Exposes
+    ``__cuda_array_interface__`` so that torch (or cupy) can wrap the library's buffer without a copy; valid until
+    the next call on the same context."""
+
+    def __init__(self, ptr, rows, width, n_items, max_roots):
+        self.ptr, self.rows, self.width, self.n_items, self.max_roots = int(ptr), int(rows), int(width), int(n_items), int(max_roots)
+        self.__cuda_array_interface__ = {"shape": (self.rows, self.width), "typestr": "<f8",
+                                         "data": (self.ptr, False), "version": 2, "strides": None}
+
+    @staticmethod
+    def unpack(table, max_roots):
+        """(root matrix, root counts, status, n_function_call) of a host copy of record rows."""
+        table = np.asarray(table, dtype=np.float64).reshape(-1, 4 + 2*max_roots)
+        roots = np.ascontiguousarray(table[:, 4:]).view(np.complex128)
+        return roots, table[:, 0].astype(np.int64), table[:, 1].astype(np.int64), table[:, 2].astype(np.int64)
+
+
 class EngineAPI:
     """Python face of the native lock-step engine (csrc/psi_engine.cu); mixed into Context.  Needs
     ``self.lib`` (a CDLL exporting the psi_* engine entry points) and ``self.handle``."""
@@ -175,7 +207,11 @@ class EngineAPI:
         else:
             goff = np.concatenate(([0], np.cumsum([len(g) for g in guesses]))).astype(np.int64)
         ng = goff[1:] - goff[:-1]
-        cap = int(np.max(ns*(1 + ng + 4*mz))) if n else 0
+        own = ns*(1 + ng + 4*mz)                       # samples a search can reach
+        if device_aaa and n and int(own.max()) > MODE_MAX_SAMPLES:
+            return self._mode_batch_mixed(own > MODE_MAX_SAMPLES, dist, kx, kz, alpha, domain, n_sample, max_zoom,
+                                          max_secant, tol, clean_tol, seeds, guesses, goff, max_roots, dense)
+        cap = int(own.max()) if n else 0
         per_item = 50*cap + 8*int(np.max(ns*np.maximum(1 + ng, 4))) + 16*max_roots + 256 if n else 1
         budget = int(os.environ.get("PSI_B200_BATCH_BYTES", str(48 << 30)))
         chunk = max(1, budget//per_item)
@@ -214,6 +250,45 @@ class EngineAPI:
             return (roots, nr), nc, st
         return [roots[i, :nr[i]].copy() for i in range(n)], nc, st
 
+    def _mode_batch_mixed(self, big, dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
+                          seeds, guesses, goff, max_roots, dense):
+        """A batch in which SOME searches can exceed the device pipeline's 512 samples (a refinement pixel with many
+        neighbour roots as guesses): those go to the host-LAPACK engine, all others stay on the device."""
+        n = len(big)
+        per = lambda a, sel: np.broadcast_to(np.asarray(a), (n,) + np.shape(a)[1:])[sel]
+        domain = np.asarray(domain, dtype=float).reshape(n, 4)
+        if guesses is not None and not isinstance(guesses, tuple):
+            guesses = (np.array([complex(z) for g in guesses for z in g], dtype=np.complex128), goff)
+        out_r, out_n, out_c, stats = {}, np.zeros(n, np.int64), np.zeros(n, np.int64), None
+        for sel, dev in ((np.flatnonzero(~big), True), (np.flatnonzero(big), False)):
+            if not len(sel):
+                continue
+            g = None
+            if guesses is not None:
+                length = (goff[1:] - goff[:-1])[sel]
+                off = np.zeros(len(sel) + 1, dtype=np.int64)
+                np.cumsum(length, out=off[1:])
+                take = np.repeat(goff[:-1][sel] - off[:-1], length) + np.arange(off[-1])
+                g = (np.asarray(guesses[0])[take], off)
+            (r, nr), nc, st = self.mode_batch(per(dist, sel), per(kx, sel), per(kz, sel), per(alpha, sel), domain[sel],
+                                              per(n_sample, sel), per(max_zoom, sel), per(max_secant, sel),
+                                              per(tol, sel), per(clean_tol, sel), per(seeds, sel), g, max_roots,
+                                              device_aaa=dev, dense=True)
+            out_r[dev] = (sel, r)
+            out_n[sel], out_c[sel] = nr, nc
+            if stats is None:
+                stats = dict(st)
+            else:
+                stats["evals"] = stats.get("evals", 0) + st.get("evals", 0)
+        stats["host_engine_items"] = int(np.count_nonzero(big))
+        width = max(r.shape[1] for _, r in out_r.values())
+        roots = np.zeros((n, width), dtype=np.complex128)
+        for sel, r in out_r.values():
+            roots[sel, :r.shape[1]] = r
+        if dense:
+            return (roots, out_n), out_c, stats
+        return [roots[i, :out_n[i]].copy() for i in range(n)], out_c, stats
+
     def _mode_batch(self, dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
                     seeds, guesses, max_roots=8, device_aaa=False, dense=False):
         """Run len(dist) PSIMode.calculate searches.  Per-item arrays; ``guesses`` is a list of
@@ -231,7 +306,7 @@ class EngineAPI:
         ip = i32(np.stack([np.broadcast_to(n_sample, (n,)), np.broadcast_to(max_zoom, (n,)),
                            np.broadcast_to(max_secant, (n,))], axis=1))
         dp = f64(np.stack([np.broadcast_to(tol, (n,)), np.broadcast_to(clean_tol, (n,))], axis=1))
-        seeds = np.ascontiguousarray(np.broadcast_to(seeds, (n,)), dtype=np.uint32)
+        seeds = _checked_seeds(seeds, n)
         goff = np.zeros(n + 1, dtype=np.int32)
         if guesses is None:
             flat = []
@@ -276,6 +351,73 @@ class EngineAPI:
             return (roots, nr), nc, st_out
         out = [roots[i, :nr[i]].copy() for i in range(n)]
         return out, nc, st_out
+
+    def mode_batch_records(self, dist, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
+                           seeds, guesses, max_roots=8, rec_rows=0):
+        """K4 batch whose results stay on the device (``DeviceRecords``) -- for the all-gather of a multi-GPU map.
+        Same arguments as ``mode_batch``; ``rec_rows`` >= number of items pads the record table (all ranks of a
+        collective need tables of one size)."""
+        n = len(dist)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        dist, kx, kz, alpha = i32(dist), f64(kx), f64(kz), f64(alpha)
+        domain = f64(domain).reshape(n, 4)
+        ip = i32(np.stack([np.broadcast_to(n_sample, (n,)), np.broadcast_to(max_zoom, (n,)),
+                           np.broadcast_to(max_secant, (n,))], axis=1))
+        dp = f64(np.stack([np.broadcast_to(tol, (n,)), np.broadcast_to(clean_tol, (n,))], axis=1))
+        seeds = _checked_seeds(seeds, n)
+        goff = np.zeros(n + 1, dtype=np.int32)
+        flat = np.zeros(0, np.complex128)
+        if guesses is not None:
+            if isinstance(guesses, tuple):
+                flat = np.asarray(guesses[0], dtype=np.complex128)
+                goff[:] = np.asarray(guesses[1], dtype=np.int64)
+            else:
+                goff[1:] = np.cumsum([len(g) for g in guesses])
+                flat = np.array([complex(z) for g in guesses for z in g], dtype=np.complex128)
+        gz = np.ascontiguousarray(flat) if len(flat) else np.zeros(1, np.complex128)
+        rows = max(int(rec_rows), n, 1)
+        ptr = _vp()
+        stats = np.zeros(16, dtype=np.int64)
+        self._check(self.lib.psi_mode_batch_device_rec(self.handle, C.c_int(n), _ptr(dist), _ptr(kx), _ptr(kz),
+                                                       _ptr(alpha), _ptr(domain), _ptr(ip), _ptr(dp), _ptr(seeds),
+                                                       _ptr(goff), _ptr(gz), C.c_int(max_roots), C.c_int(rows),
+                                                       C.byref(ptr), _ptr(stats)), "psi_mode_batch_device_rec")
+        st = dict(passes=1, evals=int(stats[1]), launches=int(stats[0]), logic_s=0.0, eval_s=0.0, polish_evals=0,
+                  stage_s=dict(zip(("sample", "k1", "analyze", "k3", "decide"), (stats[8:13]*1e-6).tolist())))
+        return DeviceRecords(ptr.value, rows, 4 + 2*max_roots, n, max_roots), st
+
+    def mode_search_detail(self, dist_id, kx, kz, alpha, domain, n_sample, max_zoom, max_secant, tol, clean_tol,
+                           uniforms, guesses, max_roots=16):
+        """One PSIMode.calculate search through the K4 pipeline with the caller's own random stream; returns a dict
+        with roots, n_function_call, status, z_sample, f_sample, mask (support points of the final rational
+        approximation), n_uniforms_used and max_convergence_iterations."""
+        g = np.ascontiguousarray(np.asarray(list(guesses), dtype=np.complex128))
+        ng = len(g)
+        cap = int(n_sample)*(1 + ng + 4*int(max_zoom))
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        dom = np.ascontiguousarray(domain, dtype=np.float64)
+        ip = np.array([n_sample, max_zoom, max_secant], dtype=np.int32)
+        dp = np.array([tol, clean_tol], dtype=np.float64)
+        while True:
+            roots = np.zeros(max_roots, dtype=np.complex128)
+            ints = np.zeros(6, dtype=np.int32)      # n_roots, n_calls, status, n_samples, n_uni_used, max_conv
+            Z, F = np.zeros(cap, np.complex128), np.zeros(cap, np.complex128)
+            mask = np.zeros(cap, dtype=np.int32)
+            ip_ = lambda k: C.cast(ints.ctypes.data + 4*k, _vp)
+            self._check(self.lib.psi_mode_search_detail(
+                self.handle, C.c_int(int(dist_id)), C.c_double(kx), C.c_double(kz), C.c_double(alpha), _ptr(dom),
+                _ptr(ip), _ptr(dp), _ptr(u), C.c_int(len(u)), _ptr(g) if ng else None, C.c_int(ng),
+                C.c_int(max_roots), _ptr(roots), ip_(0), ip_(1), ip_(2), _ptr(Z), _ptr(F), ip_(3), _ptr(mask),
+                ip_(4), ip_(5)), "psi_mode_search_detail")
+            if ints[0] > max_roots:
+                max_roots = int(ints[0])
+                continue
+            break
+        m = int(ints[3])
+        return dict(roots=roots[:ints[0]].copy(), n_function_call=int(ints[1]), status=int(ints[2]),
+                    z_sample=Z[:m].copy(), f_sample=F[:m].copy(), mask=mask[:m].astype(bool),
+                    n_uniforms_used=int(ints[4]), max_convergence_iterations=int(ints[5]))
 
     def contour_batch(self, dist, kx, kz, alpha, z_lists, tol, max_step, max_iter):
         """Root counts of len(dist) closed contours with ONE launch of kernel K2.  Returns (counts,

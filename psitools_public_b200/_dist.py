@@ -133,6 +133,43 @@ def all_gather_ragged(cnt, flat):
     return cnts, flats
 
 
+def all_reduce_max(value):
+    """Maximum of a small non-negative integer over all ranks (error / fallback flags ahead of a collective)."""
+    td = _td()
+    if td is None or td.get_world_size() == 1:
+        return int(value)
+    import torch
+    t = torch.tensor([int(value)], dtype=torch.int64, device=_device_for_collectives())
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return int(t.item())
+
+
+def nccl_active():
+    """True when results can be exchanged device to device (torch.distributed with the NCCL backend, > 1 rank)."""
+    td = _td()
+    return td is not None and td.get_world_size() > 1 and td.get_backend() == "nccl"
+
+
+def all_gather_device_records(rec, to_host=True):
+    """ONE ncclAllGather of fixed-slot result records straight out of the library's device buffer (``rec``: a
+    _device.DeviceRecords with the same number of rows on every rank).  Returns (table, max_n_roots, max_status):
+    ``table`` is the host copy with rows in GLOBAL item order (rank q owns items q::world, so row j of rank q is
+    item q + j*world) or None when ``to_host`` is false; the two maxima are reduced on the device so that every
+    rank can act on them (truncated root lists, failed searches) without pulling the table."""
+    import torch
+    td = _td()
+    world = td.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mine = torch.as_tensor(rec, device=dev)                       # zero-copy view of the library's buffer
+    out = torch.empty((world, rec.rows, rec.width), dtype=torch.float64, device=dev)
+    td.all_gather_into_tensor(out.view(-1), mine.reshape(-1))
+    head = out[:, :, :2].amax(dim=(0, 1)).cpu()                   # [max n_roots, max status]
+    table = None
+    if to_host:
+        table = out.permute(1, 0, 2).reshape(world*rec.rows, rec.width).cpu().numpy()
+    return table, int(head[0]), int(head[1])
+
+
 def barrier():
     td = _td()
     if td is not None:

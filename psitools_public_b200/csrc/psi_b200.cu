@@ -548,6 +548,8 @@ struct ModeDev {            // device pointers of the per-item state (n items, c
     cx *Z, *F, *w0, *pol, *zoom, *roots;
     double* box_dx;
     int *M, *level, *upos, *phase, *n0, *max_iter, *n_zoom, *calls, *status, *n_out, *pcalls, *pconv, *pstat;
+    int *conv_max;                      // largest pconv over the levels of a search
+    int *mask_out;                      // [n * cap] support mask of the last analysis (null: not wanted)
     long long* elem;                    // request list for K1 (element indices into Z/F)
     unsigned long long* counters;       // [0] number of requests, [1] items still active
     int cap, P, max_roots;
@@ -604,6 +606,36 @@ __global__ void mode_sample_kernel(ModeDev m, int n_items, const double* __restr
     for (int k = 0; k < n_new; ++k) m.elem[pos + k] = (long long)i * m.cap + first + k;
 }
 
+// Size classes of the analysis stage: a search with M samples is analysed by 8 lanes (M <= 32: the first level of a
+// plain map, 18 x 10 Loewner matrices), 16 lanes (M <= kAnClass1; unused by default) or a whole warp -- a property of
+// the search at this zoom level alone, never of what else is in the batch (results do not depend on how a batch is
+// cut).  Measured (1 B200): 8 lanes for M = 20 take the first level of the 256^2 map from 65 to 27 ms; 16 lanes for
+// M = 40..100 gain 10 % on its second level but lose 35 % on the refinement sweeps of config 4, whose searches carry
+// guess domains and end with more support points than 16 lanes hold in registers (profiles/k4_groups_r2.txt).
+// Thread per search: the searches waiting for their analysis are appended to their class's list.
+constexpr int kAnClass0 = 32, kAnClass1 = 32;
+// (Appended warp by warp, the 32 searches of a warp in index order: neighbouring searches -- neighbouring pixels of a
+// map, which behave alike -- stay neighbours on the list and end up in the same analysis warp.)
+__global__ void mode_classify_kernel(ModeDev m, int n_items, int* lists, unsigned long long* counts, int class0,
+                                     int class1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int cls = -1;
+    if (i < n_items && m.phase[i] == kPhaseAnalyze) {
+        const int M = m.M[i];
+        cls = M <= class0 ? 0 : (M <= class1 ? 1 : 2);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const unsigned members = __ballot_sync(0xffffffffu, cls == c);
+        if (members == 0u) continue;
+        unsigned long long base = 0;
+        if (lane == __ffs(members) - 1) base = atomicAdd(counts + c, (unsigned long long)__popc(members));
+        base = __shfl_sync(0xffffffffu, base, __ffs(members) - 1);
+        if (cls == c) lists[(size_t)c * n_items + base + __popc(members & ((1u << lane) - 1u))] = i;
+    }
+}
+
 // Analysis stage of K4.  G lanes per search (32/G searches per warp): AAA analysis of the current samples
 // (mode_analyze, psi_mode.cuh) -> polish start values + zoom plan.  (Tried in round 2 and dropped: one kernel per
 // phase of the state machine -- control / fits / poles / zeros -- in lock-step rounds over all searches, so that
@@ -614,20 +646,17 @@ template <int G>
 __global__ void __launch_bounds__(256, 3)
 mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, const int* __restrict__ iparams,
                     const double* __restrict__ dparams, const int* __restrict__ guess_off,
-                    unsigned char* scratch, size_t scratch_per_group, int scratch_cap, int own_lo, int own_hi,
+                    unsigned char* scratch, size_t scratch_per_group, int scratch_cap,
+                    const int* __restrict__ list, const unsigned long long* __restrict__ n_list,
                     unsigned long long* queue, unsigned long long* n_polish) {
     typedef GroupCuda<G> W;
     const int lane = W::lane();
     const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
     AAAScratch sc = aaa_carve(scratch + (size_t)group * scratch_per_group, scratch_cap);
-    long long idx;
-    while (next_item_group<W>(queue, n_items, idx)) {
-        if (m.phase[idx] != kPhaseAnalyze) continue;
-        {   // this launch takes the searches whose OWN sample capacity lies in (own_lo, own_hi]: the group size a
-            // search is analysed with depends on the search alone, never on what else is in the batch
-            const int own = iparams[3 * idx] * (1 + guess_off[idx + 1] - guess_off[idx] + 4 * iparams[3 * idx + 1]);
-            if (own <= own_lo || own > own_hi) continue;
-        }
+    const long long n_work = (long long)*n_list;          // searches of this launch's size class (mode_classify_kernel)
+    long long k;
+    while (next_item_group<W>(queue, n_work, k)) {
+        const long long idx = list[k];
         ModeCfg cfg;
         cfg.dom = RectDom{domain[4 * idx], domain[4 * idx + 1], domain[4 * idx + 2], domain[4 * idx + 3]};
         cfg.n_sample = iparams[3 * idx]; cfg.max_zoom = iparams[3 * idx + 1]; cfg.max_secant = iparams[3 * idx + 2];
@@ -641,6 +670,8 @@ mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, c
         ModePlan plan;
         const bool ok = mode_analyze<W>(cfg, m.level[idx], guess_off[idx + 1] - guess_off[idx], sc, st, plan);
         W::sync();
+        if (m.mask_out != nullptr && ok)
+            for (int i = lane; i < st.M; i += W::width) m.mask_out[(size_t)idx * m.cap + i] = sc.mask[i];
         if (lane == 0) {
             if (!ok) {
                 m.status[idx] = kModeBadSamples; m.phase[idx] = kPhaseDone; m.n_out[idx] = 0;
@@ -666,6 +697,7 @@ __global__ void mode_decide_kernel(ModeDev m, int n_items, const double* __restr
     const RectDom dom{domain[4 * i], domain[4 * i + 1], domain[4 * i + 2], domain[4 * i + 3]};
     if (m.pstat[i] != 0) { m.status[i] = kModeZeroTol; m.phase[i] = kPhaseDone; m.n_out[i] = 0; return; }
     m.calls[i] += m.pcalls[i];
+    if (ph == kPhasePolish && m.pconv[i] > m.conv_max[i]) m.conv_max[i] = m.pconv[i];
     int n_out = 0;
     bool grow = false;
     const int n0 = ph == kPhasePolish ? m.n0[i] : 0;
@@ -683,6 +715,21 @@ __global__ void mode_decide_kernel(ModeDev m, int n_items, const double* __restr
     } else {
         m.phase[i] = kPhaseZoom;
         atomicAdd(m.counters + 1, 1ull);
+    }
+}
+
+// thread per row: packed result records {n_roots, status, n_function_call, 0, roots...} (rows >= n_items zeroed)
+__global__ void mode_pack_kernel(ModeDev m, int n_items, int rows, double* rec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const int width = 4 + 2 * m.max_roots;
+    double* r = rec + (size_t)i * width;
+    if (i >= n_items) { for (int k = 0; k < width; ++k) r[k] = 0.0; return; }
+    const int n = m.n_out[i];
+    r[0] = n; r[1] = m.status[i]; r[2] = m.calls[i]; r[3] = 0.0;
+    for (int k = 0; k < m.max_roots; ++k) {
+        const cx z = k < n ? m.roots[(size_t)i * m.max_roots + k] : cx(0.0, 0.0);
+        r[4 + 2 * k] = z.re; r[5 + 2 * k] = z.im;
     }
 }
 
@@ -1080,8 +1127,20 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
                              const double* alpha, const double* domain, const int* iparams,
                              const double* dparams, const double* uni, long long n_uni, const int* uni_off,
                              const int* guess_off, const double* guesses, int cap, int max_roots,
-                             double* roots, int* n_roots, int* n_calls, int* status, long long* stats) {
-    if (n_items == 0) return PSI_OK;
+                             double* roots, int* n_roots, int* n_calls, int* status, long long* stats,
+                             const PsiModeExtra* extra) {
+    if (n_items == 0) {
+        if (extra && extra->rec_dev) {                      // a rank without work still contributes (zero) records
+            CK(cudaSetDevice(c->device));
+            const size_t bytes = 8 * (size_t)std::max(extra->rec_rows, 1) * (4 + 2 * max_roots);
+            int rc0 = ensure_stage(c, bytes);
+            if (rc0 != PSI_OK) return rc0;
+            CK(cudaMemsetAsync(c->d_stage, 0, bytes, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            *extra->rec_dev = (double*)c->d_stage;
+        }
+        return PSI_OK;
+    }
     CK(cudaSetDevice(c->device));
     bool ok;
     const unsigned mask = class_mask_of(c, n_items, dist, alpha, &ok);
@@ -1095,25 +1154,21 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     }
     const size_t ni = (size_t)n_items, ng = (size_t)guess_off[n_items];
     const int P = cap / 2 + 2;
-    // analysis stage: G lanes per search, first level / zoom levels (PSI_AN_GROUP0 / PSI_AN_GROUP1: 8, 16, 32);
-    // searches with many guess domains -- more than 128 samples of their own -- keep a whole warp (their matrices
-    // fill it, and the scratch areas, one per group, are megabytes each).  Two scratch regions: small searches
-    // (areas carved for 128 samples) and big ones.
+    // analysis stage: 8 / 16 / 32 lanes per search by its sample count (mode_classify_kernel); one scratch region
+    // per class, areas carved for the largest search of the class
     static const int an_ctas = getenv("PSI_AN_CTAS") ? atoi(getenv("PSI_AN_CTAS")) : 3;
-    static const int an_g0 = getenv("PSI_AN_GROUP0") ? atoi(getenv("PSI_AN_GROUP0")) : 8;
-    static const int an_g1 = getenv("PSI_AN_GROUP1") ? atoi(getenv("PSI_AN_GROUP1")) : 16;
-    const int an_threads = 256, kSmallCap = 128;
-    bool any_small = false, any_big = false;
-    for (int i = 0; i < n_items; ++i) {
-        const int own = iparams[3 * i] * (1 + guess_off[i + 1] - guess_off[i] + 4 * iparams[3 * i + 1]);
-        (own <= kSmallCap ? any_small : any_big) = true;
+    static const int an_class0 = getenv("PSI_AN_CLASS0") ? atoi(getenv("PSI_AN_CLASS0")) : kAnClass0;
+    static const int an_class1 = getenv("PSI_AN_CLASS1") ? atoi(getenv("PSI_AN_CLASS1")) : kAnClass1;
+    const int an_threads = 256;
+    const int an_g[3] = {8, 16, 32};
+    const int an_cap[3] = {std::min(cap, an_class0), std::min(cap, an_class1), cap};
+    size_t an_per_group[3], an_off[3], need = 0;
+    for (int k = 0; k < 3; ++k) {
+        const bool used = k == 0 || cap > (k == 1 ? an_class0 : an_class1);
+        an_per_group[k] = (aaa_scratch_bytes(an_cap[k]) + 255) & ~(size_t)255;
+        an_off[k] = need;
+        if (used) need += an_per_group[k] * (size_t)c->sm_count * an_ctas * (an_threads / an_g[k]);
     }
-    const int cap_small = std::min(cap, kSmallCap);
-    const size_t per_group_small = (aaa_scratch_bytes(cap_small) + 255) & ~(size_t)255;
-    const size_t per_group_big = (aaa_scratch_bytes(cap) + 255) & ~(size_t)255;
-    const size_t bytes_small = any_small ? per_group_small * (size_t)c->sm_count * an_ctas * (an_threads / std::min(an_g0, an_g1)) : 0;
-    const size_t bytes_big = any_big ? per_group_big * (size_t)c->sm_count * an_ctas * (an_threads / 32) : 0;
-    const size_t need = bytes_small + bytes_big;
     if (need > c->mode_scratch_bytes) {
         if (c->d_mode_scratch) CK(cudaFree(c->d_mode_scratch));
         c->d_mode_scratch = nullptr; c->mode_scratch_bytes = 0;
@@ -1122,6 +1177,8 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     }
     // inputs + per-item state in one staging allocation
     const size_t nreq = ni * (size_t)max_req;
+    const bool want_mask = extra && extra->mask;
+    const int rec_rows = (extra && extra->rec_dev) ? std::max(extra->rec_rows, n_items) : 0;
     StageItem it[] = {
         {dist, 4 * ni}, {kx, 8 * ni}, {kz, 8 * ni}, {alpha, 8 * ni}, {domain, 32 * ni},            // 0-4
         {iparams, 12 * ni}, {dparams, 16 * ni}, {uni, 8 * (size_t)n_uni}, {uni_off, 4 * ni},       // 5-8
@@ -1129,9 +1186,12 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         {nullptr, 16 * ni * cap}, {nullptr, 16 * ni * cap},                                        // 11 Z, 12 F
         {nullptr, 16 * ni * P}, {nullptr, 16 * ni * P}, {nullptr, 64 * ni},                        // 13 w0, 14 pol, 15 zoom
         {nullptr, 16 * ni * max_roots}, {nullptr, 8 * ni},                                         // 16 roots, 17 box_dx
-        {nullptr, 4 * ni * 13}, {nullptr, 8 * nreq}};                                              // 18 ints, 19 elem
-    char* d[20];
-    int rc = stage_upload(c, it, 20, 0, d, nullptr);
+        {nullptr, 4 * ni * 14}, {nullptr, 8 * nreq},                                               // 18 ints, 19 elem
+        {nullptr, want_mask ? 4 * ni * cap : 0},                                                   // 20 final masks
+        {nullptr, rec_rows ? 8 * (size_t)rec_rows * (4 + 2 * max_roots) : 0},                      // 21 records
+        {nullptr, 12 * ni}, {nullptr, 64}};                                                        // 22-23 size classes
+    char* d[24];
+    int rc = stage_upload(c, it, 24, 0, d, nullptr);
     if (rc != PSI_OK) return rc;
     cudaStream_t st = c->stream;
     ModeDev m;
@@ -1141,10 +1201,13 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     m.M = ints; m.level = ints + ni; m.upos = ints + 2 * ni; m.phase = ints + 3 * ni; m.n0 = ints + 4 * ni;
     m.max_iter = ints + 5 * ni; m.n_zoom = ints + 6 * ni; m.calls = ints + 7 * ni; m.status = ints + 8 * ni;
     m.n_out = ints + 9 * ni; m.pcalls = ints + 10 * ni; m.pconv = ints + 11 * ni; m.pstat = ints + 12 * ni;
+    m.conv_max = ints + 13 * ni;
+    m.mask_out = want_mask ? (int*)d[20] : nullptr;
     m.elem = (long long*)d[19];
     m.counters = c->d_counter + 6;
     m.cap = cap; m.P = P; m.max_roots = max_roots;
-    CK(cudaMemsetAsync(ints, 0, 4 * ni * 13, st));                         // phase 0 = kPhaseSample everywhere
+    CK(cudaMemsetAsync(ints, 0, 4 * ni * 14, st));
+    if (want_mask) CK(cudaMemsetAsync(d[20], 0, 4 * ni * cap, st));                         // phase 0 = kPhaseSample everywhere
     CK(cudaMemsetAsync(c->d_counter + 4, 0, 2 * sizeof(unsigned long long), st));
     NodeTableView t = table_view(c);
     const int tgrid = (n_items + 255) / 256;
@@ -1183,20 +1246,23 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(c->d_counter + 8, 0, sizeof(unsigned long long), st));
         CK(cudaEventRecord(ev[2], st));
-        for (int big = 0; big < 2; ++big) {
-            if (!(big ? any_big : any_small)) continue;
-            const int g = big ? 32 : (round == 0 ? an_g0 : an_g1);
-            const int per_cta = an_threads / g;
-            const int agrid = std::min(c->sm_count * an_ctas, (n_items + per_cta - 1) / per_cta);
-            auto kern = g == 8 ? mode_analyze_kernel<8> : g == 16 ? mode_analyze_kernel<16> : mode_analyze_kernel<32>;
-            CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
-            kern<<<agrid, an_threads, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
-                                               (const double*)d[6], (const int*)d[9],
-                                               (unsigned char*)c->d_mode_scratch + (big ? bytes_small : 0),
-                                               big ? per_group_big : per_group_small, big ? cap : cap_small,
-                                               big ? kSmallCap : -1, big ? (1 << 30) : kSmallCap, c->d_counter,
-                                               c->d_counter + 8);
-            ++launches;
+        {
+            int* an_lists = (int*)d[22];
+            unsigned long long* an_counts = (unsigned long long*)d[23];        // [0..2] class sizes, [4..6] queue heads
+            CK(cudaMemsetAsync(an_counts, 0, 8 * sizeof(unsigned long long), st));
+            mode_classify_kernel<<<tgrid, 256, 0, st>>>(m, n_items, an_lists, an_counts, an_class0, an_class1);
+            for (int k = 0; k < 3; ++k) {
+                if (k > 0 && cap <= (k == 1 ? an_class0 : an_class1)) continue;       // no search can be that large
+                const int per_cta = an_threads / an_g[k];
+                const int agrid = std::min(c->sm_count * an_ctas, (n_items + per_cta - 1) / per_cta);
+                auto kern = k == 0 ? mode_analyze_kernel<8> : k == 1 ? mode_analyze_kernel<16> : mode_analyze_kernel<32>;
+                kern<<<agrid, an_threads, 0, st>>>(m, n_items, (const double*)d[4], (const int*)d[5],
+                                                   (const double*)d[6], (const int*)d[9],
+                                                   (unsigned char*)c->d_mode_scratch + an_off[k], an_per_group[k],
+                                                   an_cap[k], an_lists + (size_t)k * n_items, an_counts + k,
+                                                   an_counts + 4 + k, c->d_counter + 8);
+                ++launches;
+            }
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ev[3], st));
@@ -1231,10 +1297,24 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
         if (cnt[1] == 0) break;                                          // nobody wants to zoom
     }
     unsigned long long cnt2[2] = {0, 0};
-    CK(cudaMemcpyAsync(roots, m.roots, 16 * ni * max_roots, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(n_roots, m.n_out, 4 * ni, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(n_calls, m.calls, 4 * ni, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(status, m.status, 4 * ni, cudaMemcpyDeviceToHost, st));
+    if (rec_rows) {
+        mode_pack_kernel<<<(rec_rows + 255) / 256, 256, 0, st>>>(m, n_items, rec_rows, (double*)d[21]);
+        CK(cudaGetLastError());
+        *extra->rec_dev = (double*)d[21];
+        ++launches;
+    }
+    if (roots) CK(cudaMemcpyAsync(roots, m.roots, 16 * ni * max_roots, cudaMemcpyDeviceToHost, st));
+    if (n_roots) CK(cudaMemcpyAsync(n_roots, m.n_out, 4 * ni, cudaMemcpyDeviceToHost, st));
+    if (n_calls) CK(cudaMemcpyAsync(n_calls, m.calls, 4 * ni, cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status, m.status, 4 * ni, cudaMemcpyDeviceToHost, st));
+    if (extra) {
+        if (extra->Z) CK(cudaMemcpyAsync(extra->Z, m.Z, 16 * ni * cap, cudaMemcpyDeviceToHost, st));
+        if (extra->F) CK(cudaMemcpyAsync(extra->F, m.F, 16 * ni * cap, cudaMemcpyDeviceToHost, st));
+        if (extra->M) CK(cudaMemcpyAsync(extra->M, m.M, 4 * ni, cudaMemcpyDeviceToHost, st));
+        if (extra->mask) CK(cudaMemcpyAsync(extra->mask, m.mask_out, 4 * ni * cap, cudaMemcpyDeviceToHost, st));
+        if (extra->upos) CK(cudaMemcpyAsync(extra->upos, m.upos, 4 * ni, cudaMemcpyDeviceToHost, st));
+        if (extra->conv) CK(cudaMemcpyAsync(extra->conv, m.conv_max, 4 * ni, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaMemcpyAsync(cnt2, c->d_counter + 4, sizeof(cnt2), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     for (auto& e : ev) cudaEventDestroy(e);

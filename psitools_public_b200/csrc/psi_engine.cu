@@ -771,17 +771,11 @@ int psi_engine_bind_lapack(const char* numpy_openblas64, const char* scipy_openb
 /* host threads used by the engine's per-item logic (AAA etc.); n <= 0 restores the OpenMP default */
 void psi_engine_set_threads(int n) { g_threads = n; }
 
-/* K4 driver: the same batch as psi_mode_batch_host, but every search runs entirely on the device (one
- * warp per item, one launch per work class).  The host only generates the random streams. */
-int psi_mode_batch_device(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
-                          const double* alpha, const double* domain, const int* iparams, const double* dparams,
-                          const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,
-                          double* roots, int* n_roots, int* n_calls, int* status, long long* stats) {
-    if (!ctx || n_items < 0 || !dist || !kx || !kz || !alpha || !domain || !iparams || !dparams || !seeds ||
-        !guess_off || !roots || !n_roots || !n_calls || !status || max_roots < 1)
-        return psi_internal_fail(PSI_ERR_ARG, "psi_mode_batch_device: bad argument");
-    // one U[0,1) stream per distinct seed, long enough for the hungriest item using it: every domain
-    // (initial, one per guess, four per zoom level) consumes 2*n_sample numbers
+/* K4 drivers: the same batch as psi_mode_batch_host, but every search runs entirely on the device.  The host
+ * only generates the random streams: one U[0,1) stream per distinct seed, long enough for the hungriest item
+ * using it (every domain -- initial, one per guess, four per zoom level -- consumes 2*n_sample numbers). */
+static int mode_streams(int n_items, const int* iparams, const unsigned* seeds, const int* guess_off,
+                        std::vector<double>& uni, std::vector<int>& uoff, int* cap_out) {
     std::map<unsigned, long long> need;
     int cap = 0;
     for (int i = 0; i < n_items; ++i) {
@@ -792,7 +786,6 @@ int psi_mode_batch_device(psi_ctx* ctx, int n_items, const int* dist, const doub
         long long& n = need[seeds[i]];
         n = std::max(n, 2ll * ns * domains);
     }
-    std::vector<double> uni;
     std::map<unsigned, long long> start;
     for (auto& kv : need) {
         start[kv.first] = (long long)uni.size();
@@ -801,15 +794,80 @@ int psi_mode_batch_device(psi_ctx* ctx, int n_items, const int* dist, const doub
         for (long long k = 0; k < kv.second; ++k) uni.push_back(rng.sample());
     }
     if (uni.size() > 0x7fffffffull) return psi_internal_fail(PSI_ERR_CAPACITY, "random streams too long");
-    if (cap > 512)
+    if (cap > PSI_MODE_MAX_SAMPLES)
         return psi_internal_fail(PSI_ERR_CAPACITY, "more than 512 samples per search: use psi_mode_batch_host");
-    std::vector<int> uoff(n_items);
+    uoff.resize(n_items);
     for (int i = 0; i < n_items; ++i) uoff[i] = (int)start[seeds[i]];
+    *cap_out = cap;
+    return PSI_OK;
+}
+
+int psi_mode_batch_device(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
+                          const double* alpha, const double* domain, const int* iparams, const double* dparams,
+                          const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,
+                          double* roots, int* n_roots, int* n_calls, int* status, long long* stats) {
+    if (!ctx || n_items < 0 || !dist || !kx || !kz || !alpha || !domain || !iparams || !dparams || !seeds ||
+        !guess_off || !roots || !n_roots || !n_calls || !status || max_roots < 1)
+        return psi_internal_fail(PSI_ERR_ARG, "psi_mode_batch_device: bad argument");
+    std::vector<double> uni;
+    std::vector<int> uoff;
+    int cap = 0;
+    int rc = mode_streams(n_items, iparams, seeds, guess_off, uni, uoff, &cap);
+    if (rc != PSI_OK) return rc;
     const double dummy[2] = {0.0, 0.0};
     return psi_internal_mode_device(ctx, n_items, dist, kx, kz, alpha, domain, iparams, dparams, uni.data(),
                                     (long long)uni.size(), uoff.data(), guess_off,
                                     guesses ? guesses : dummy, cap, max_roots, roots, n_roots, n_calls, status,
                                     stats);
+}
+
+/* The same batch with the results left ON THE DEVICE as packed records (see PsiModeExtra): what a rank hands to
+ * the all-gather of a multi-GPU map without a detour through host memory. */
+int psi_mode_batch_device_rec(psi_ctx* ctx, int n_items, const int* dist, const double* kx, const double* kz,
+                              const double* alpha, const double* domain, const int* iparams, const double* dparams,
+                              const unsigned* seeds, const int* guess_off, const double* guesses, int max_roots,
+                              int rec_rows, double** rec_dev, long long* stats) {
+    if (!ctx || n_items < 0 || !rec_dev || max_roots < 1 || !guess_off ||
+        (n_items > 0 && (!dist || !kx || !kz || !alpha || !domain || !iparams || !dparams || !seeds)))
+        return psi_internal_fail(PSI_ERR_ARG, "psi_mode_batch_device_rec: bad argument");
+    std::vector<double> uni;
+    std::vector<int> uoff;
+    int cap = 0;
+    int rc = mode_streams(n_items, iparams, seeds, guess_off, uni, uoff, &cap);
+    if (rc != PSI_OK) return rc;
+    const double dummy[2] = {0.0, 0.0};
+    PsiModeExtra ex;
+    ex.rec_dev = rec_dev; ex.rec_rows = rec_rows;
+    return psi_internal_mode_device(ctx, n_items, dist, kx, kz, alpha, domain, iparams, dparams, uni.data(),
+                                    (long long)uni.size(), uoff.data(), guess_off, guesses ? guesses : dummy, cap,
+                                    max_roots, nullptr, nullptr, nullptr, nullptr, stats, &ex);
+}
+
+/* ONE search with the caller's own stream of U[0,1) numbers (n_uni >= 2*n_sample*(1 + n_guess + 4*max_zoom)) and
+ * everything PSIMode exposes after calculate(): roots, n_function_call, the sample points and values (cap =
+ * n_sample*(1 + n_guess + 4*max_zoom) slots each, *n_samples used), the support mask of the final rational
+ * approximation, the number of random numbers consumed and the largest iteration count of a converged polish. */
+int psi_mode_search_detail(psi_ctx* ctx, int dist, double kx, double kz, double alpha, const double* domain,
+                           const int* iparams, const double* dparams, const double* uni, int n_uni,
+                           const double* guesses, int n_guess, int max_roots, double* roots, int* n_roots,
+                           int* n_calls, int* status, double* z_sample, double* f_sample, int* n_samples,
+                           int* mask, int* n_uni_used, int* max_conv) {
+    if (!ctx || !domain || !iparams || !dparams || !uni || n_guess < 0 || max_roots < 1 || !roots || !n_roots ||
+        !n_calls || !status)
+        return psi_internal_fail(PSI_ERR_ARG, "psi_mode_search_detail: bad argument");
+    const int cap = iparams[0] * (1 + n_guess + 4 * iparams[1]);
+    if (iparams[0] < 2 || iparams[1] < 0 || n_uni < 2 * cap)
+        return psi_internal_fail(PSI_ERR_ARG, "psi_mode_search_detail: bad n_sample / max_zoom / stream length");
+    if (cap > PSI_MODE_MAX_SAMPLES)
+        return psi_internal_fail(PSI_ERR_CAPACITY, "more than 512 samples per search: use psi_mode_batch_host");
+    const int goff[2] = {0, n_guess}, uoff[1] = {0};
+    const double dummy[2] = {0.0, 0.0};
+    PsiModeExtra ex;
+    ex.Z = z_sample; ex.F = f_sample; ex.M = n_samples; ex.mask = mask; ex.upos = n_uni_used; ex.conv = max_conv;
+    long long stats[16];
+    return psi_internal_mode_device(ctx, 1, &dist, &kx, &kz, &alpha, domain, iparams, dparams, uni, n_uni, uoff,
+                                    goff, n_guess ? guesses : dummy, cap, max_roots, roots, n_roots, n_calls,
+                                    status, stats, &ex);
 }
 
 /* profiling aid: {svd calls, svd ns, eig calls, eig ns} accumulated since load */

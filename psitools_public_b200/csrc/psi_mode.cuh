@@ -268,14 +268,18 @@ PSI_HD bool mode_analyze(const ModeCfg& cfg, int level, int n_guess, const AAASc
 // Returns a ModeStatus; out_roots[0..min(*n_roots, max_roots)) receive the roots inside the domain,
 // *n_calls the reference's n_function_call.  (Single-warp form of the whole search; the GPU library runs
 // the same pieces as a pipeline of homogeneous kernels, see mode_pipeline in psi_b200.cu.)
+struct ModeDetail { int M, upos, conv; };    // samples used, random numbers consumed, max iterations of a converged polish
+
 template <class W, class EVAL>
 PSI_HD int mode_run(EVAL& f, const ModeCfg& cfg, const cx* guesses, int n_guess, const double* uni,
-                    const AAAScratch& s, cx* out_roots, int max_roots, int* n_roots, int* n_calls) {
+                    const AAAScratch& s, cx* out_roots, int max_roots, int* n_roots, int* n_calls,
+                    ModeDetail* detail = nullptr) {
     AAAState st;
     st.M = 0; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol; st.dom = cfg.dom;
     st.memo_next = 0; st.slot = 0; st.v_m = 0;
-    int upos = 0, calls = 0;
+    int upos = 0, calls = 0, conv_max = 0;
     *n_roots = 0; *n_calls = 0;
+    if (detail) { detail->M = 0; detail->upos = 0; detail->conv = 0; }
     const int n_domains_max = 1 + n_guess + 4 * cfg.max_zoom;
     if (cfg.n_sample * n_domains_max > s.cap) return kModeCapacity;
 
@@ -294,6 +298,8 @@ PSI_HD int mode_run(EVAL& f, const ModeCfg& cfg, const cx* guesses, int n_guess,
         int conv = 0, pst = 0;
         calls += polish_run(f, cfg.dom, s.w0, plan.n0, plan.max_iter, s.pol, &conv, &pst);
         W::sync();
+        if (conv > conv_max) conv_max = conv;
+        if (detail) { detail->M = st.M; detail->upos = upos; detail->conv = conv_max; }
         if (pst != 0) { *n_calls = calls; return kModeZeroTol; }
         n_out = 0;
         bool grow = false;
@@ -312,6 +318,7 @@ PSI_HD int mode_run(EVAL& f, const ModeCfg& cfg, const cx* guesses, int n_guess,
     }
     *n_roots = n_out;
     *n_calls = calls;
+    if (detail) { detail->M = st.M; detail->upos = upos; detail->conv = conv_max; }
     return n_out > max_roots ? kModeTruncated : kModeOk;
 }
 

@@ -125,11 +125,20 @@ class MpiScheduler:
     def _decode(self, rec):
         return np.asarray(rec, dtype=np.float64).view(np.complex128).copy()
 
-    def _run_native(self, arglist, mine):
+    def _run_native(self, arglist, mine, rec_rows=None, max_roots=8):
         """All of this rank's items through the batched engine (K4 pipeline or C++ lock-step engine);
-        None if an item needs the general (Python) path.  Returns (root matrix, root counts, stats)."""
-        if not mine:
+        None if an item needs the general (Python) path.  Returns (root matrix, root counts, stats) -- or, with
+        ``rec_rows`` (device engine, multi-GPU), (DeviceRecords, None, stats): the results stay on the device for
+        the all-gather."""
+        if not mine and rec_rows is None:
             return (np.zeros((0, 1), dtype=np.complex128), np.zeros(0, dtype=np.int64)), {}
+        if not mine:
+            sub0 = arglist[0]
+            ctx = self._cache.get(sub0['__init__']).psi_dispersion.ctx
+            z = np.zeros(0)
+            rec, st = ctx.mode_batch_records(z.astype(np.int32), z, z, z, np.zeros((0, 4)), z, z, z, z, z, z, None,
+                                             max_roots=max_roots, rec_rows=rec_rows)
+            return (rec, None), st
         # One C-speed pass per field (map + itemgetter) instead of Python loops over the items: on a 256^2 map
         # the arg-dict handling was 30-50 ms of a 0.3 s batch.
         sub = [arglist[i] for i in mine] if len(mine) != len(arglist) else arglist
@@ -176,21 +185,18 @@ class MpiScheduler:
             seeds = np.fromiter(map(_GET_SEED, sub), dtype=np.int64, count=n)
         except KeyError:
             seeds = np.fromiter((a.get('random_seed', 0) for a in sub), dtype=np.int64, count=n)
-        device = self.engine == "device"
-        if device:      # the device AAA holds at most 512 samples per search
-            most = int(np.max(n_sample*(1 + n_guess + 4*max_zoom)))
-            device = most <= 512
-            if not device:
-                import warnings
-                warnings.warn("a search of this batch can reach %d samples (> 512, the capacity of the "
-                              "device AAA): running the batch with engine='native'" % most)
-        (roots, nr), ncalls, st = ctx.mode_batch(
+        device = self.engine == "device"      # (searches beyond the pipeline's 512 samples: Context.mode_batch routes
+        batch_args = (                          # just those to the host engine)
             per_pm(lambda pm: pm.psi_dispersion.dist_id, int),
             np.fromiter(map(_GET_KX, calc), dtype=float, count=n),
             np.fromiter(map(_GET_KZ, calc), dtype=float, count=n), alpha,
             dom, n_sample, max_zoom, per_pm(lambda pm: pm.cfg.max_secant_iterations, int),
             per_pm(lambda pm: pm.cfg.tol), per_pm(lambda pm: pm.cfg.clean_tol), seeds,
-            guesses if n_guess.any() else None, device_aaa=device, dense=True)
+            guesses if n_guess.any() else None)
+        if rec_rows is not None:
+            rec, st = ctx.mode_batch_records(*batch_args, max_roots=max_roots, rec_rows=rec_rows)
+            return (rec, None), st
+        (roots, nr), ncalls, st = ctx.mode_batch(*batch_args, device_aaa=device, dense=True)
         st["function_calls"] = int(np.sum(ncalls))
         return (roots, nr), st
 
@@ -224,19 +230,39 @@ class MpiScheduler:
             gl = (flat[take], myoff)
         device = self.engine == "device"
         cfg = pm.cfg
-        most = cfg.n_sample*(1 + (int(np.max(gl[1][1:] - gl[1][:-1])) if gl is not None and len(mine) else 0)
-                             + 4*cfg.max_zoom_level)
-        if device and most > 512:
-            import warnings
-            warnings.warn("a search of this batch can reach %d samples (> 512, the capacity of the "
-                          "device AAA): running the batch with engine='native'" % most)
-            device = False
         dom = np.tile(np.array([pm.domain.xmin, pm.domain.xmax, pm.domain.ymin, pm.domain.ymax], dtype=float),
                       (len(mine), 1))
         t1 = time.time()
+        dist_ids = np.full(len(mine), pm.psi_dispersion.dist_id, dtype=np.int32)
+        n_guess_max = int(np.max(gl[1][1:] - gl[1][:-1])) if gl is not None and len(mine) else 0
+        cap = cfg.n_sample*(1 + n_guess_max + 4*cfg.max_zoom_level)
+        fits = cap <= 512 and 60*cap*max(len(mine), 1) <= int(os.environ.get("PSI_B200_BATCH_BYTES", str(48 << 30)))
+        if device and _dist.nccl_active() and _dist.all_reduce_max(0 if fits else 1) == 0:
+            # results stay on the device: one ncclAllGather of packed records out of the library's buffer
+            rows, max_roots = (n + step - 1)//step, 8
+            while True:
+                rec, st = ctx.mode_batch_records(dist_ids, kx, kz, al, dom, cfg.n_sample, cfg.max_zoom_level,
+                                                 cfg.max_secant_iterations, cfg.tol, cfg.clean_tol, seeds, gl,
+                                                 max_roots=max_roots, rec_rows=rows)
+                t2 = time.time()
+                table, top, worst = _dist.all_gather_device_records(rec, to_host=True)
+                if worst not in (0, 4):
+                    raise RuntimeError("device root search failed on some rank (status %d)" % worst)
+                if top <= max_roots:
+                    break
+                max_roots = top
+            from ._device import DeviceRecords
+            roots_all, cnt_all, _, calls = DeviceRecords.unpack(table[:n], max_roots)
+            width = max(1, int(cnt_all.max()) if n else 1)
+            self.last_stats = dict(items=len(mine), passes=1, function_calls=int(calls[lo::step].sum()),
+                                   evals=st.get("evals", 0), seconds=time.time() - t0, prep_seconds=t1 - t0,
+                                   batch_seconds=t2 - t1, launches=st.get("launches"), stage_s=st.get("stage_s"),
+                                   engine=self.engine, exchange_seconds=time.time() - t2,
+                                   exchange="nccl all_gather_into_tensor (device records)")
+            return np.ascontiguousarray(roots_all[:, :width]), cnt_all
         if len(mine):
             (roots, nr), ncalls, st = ctx.mode_batch(
-                np.full(len(mine), pm.psi_dispersion.dist_id, dtype=np.int32), kx, kz, al, dom, cfg.n_sample,
+                dist_ids, kx, kz, al, dom, cfg.n_sample,
                 cfg.max_zoom_level, cfg.max_secant_iterations, cfg.tol, cfg.clean_tol, seeds, gl,
                 device_aaa=device, dense=True)
         else:
@@ -263,9 +289,76 @@ class MpiScheduler:
         self.last_stats["exchange_seconds"] = time.time() - t2
         return out, out_n
 
-    def run_all(self, arglist):
-        """Results of every item, on every rank."""
+    def _records_ok(self, arglist):
+        """Device-to-device exchange: device engine, NCCL, no search beyond the pipeline's 512 samples, batch within
+        the device budget (one piece)."""
+        if self.engine != "device" or not _dist.nccl_active() or not arglist:
+            return False
+        if len(arglist) > int(os.environ.get("PSI_B200_RECORD_ITEMS", "4000000")):
+            return False
+        return True
+
+    def _run_records(self, arglist, to_host):
+        """Multi-GPU map with the results gathered device to device: every rank solves its items i = rank (mod
+        world), the packed records go through ONE ncclAllGather out of the library's own buffer, and only ranks
+        that need the values (``to_host``) copy the gathered table to the host.  Returns the table rows in global
+        item order as (root matrix, root counts), or None (general path needed)."""
+        n, world = len(arglist), _dist.world_size()
+        mine = _dist.my_items(n)
+        rows = (n + world - 1)//world
+        max_roots = 8
+        while True:
+            try:
+                done = self._run_native(arglist, mine, rec_rows=rows, max_roots=max_roots)
+            except Exception as exc:             # (capacity etc.): every rank must still reach the collective
+                done, err = "error", exc
+            flag = _dist.all_reduce_max(0 if isinstance(done, tuple) else (2 if done == "error" else 1))
+            if flag == 2:
+                raise err if done == "error" else RuntimeError("root search failed on another rank")
+            if flag == 1:
+                return None
+            (rec, _), st = done
+            table, top, worst = _dist.all_gather_device_records(rec, to_host=to_host)
+            if worst not in (0, 4):
+                raise RuntimeError("device root search failed on some rank (status %d)" % worst)
+            if top > max_roots:                   # rare: more roots than slots somewhere -> every rank redoes it
+                max_roots = top
+                continue
+            break
+        self.last_stats = dict(items=len(mine), passes=st.get("passes", 0), function_calls=None,
+                               evals=st.get("evals", 0), launches=st.get("launches"), stage_s=st.get("stage_s"),
+                               engine=self.engine, exchange="nccl all_gather_into_tensor (device records)")
+        if table is None:
+            return ()
+        from ._device import DeviceRecords
+        roots, cnt, _, calls = DeviceRecords.unpack(table[:n], max_roots)
+        self.last_stats["function_calls"] = int(calls.sum())
+        return roots, cnt
+
+    @staticmethod
+    def _as_dict(n, mat, cnt):
+        """{index: roots}: root-less items (the majority on a map) share one read-only empty array."""
+        none = np.zeros(0, dtype=np.complex128)
+        none.flags.writeable = False
+        res = dict.fromkeys(range(n), none)
+        for k in np.flatnonzero(cnt > 0).tolist():
+            res[k] = mat[k, :cnt[k]].copy()
+        return res
+
+    def run_all(self, arglist, root_only=False):
+        """Results of every item, on every rank (``root_only``: on rank 0, None elsewhere)."""
         t0 = time.time()
+        if self._records_ok(arglist):
+            got = self._run_records(arglist, to_host=(not root_only) or self.rank == 0)
+            if got is not None:
+                self.last_stats["seconds"] = time.time() - t0
+                if got == ():
+                    return None
+                res = self._as_dict(len(arglist), *got)
+                if self.verbose:
+                    for i in _dist.my_items(len(arglist)):
+                        print(i, 'result ', res[i])
+                return res
         mine = _dist.my_items(len(arglist))
         if self.engine != "python":
             done = self._run_native(arglist, mine)
@@ -308,7 +401,7 @@ class MpiScheduler:
         return {i: self._decode(merged[i]) for i in sorted(merged)}
 
     def run(self, arglist):
-        res = self.run_all(arglist)
+        res = self.run_all(arglist, root_only=True)
         return res if self.rank == 0 else None
 
 
@@ -321,7 +414,7 @@ class DispersionRelationMpiScheduler(MpiScheduler):
         pm = self._cache.get(args['__init__'])
         return pm.dispersion(**args['dispersion'])
 
-    def run_all(self, arglist):
+    def run_all(self, arglist, root_only=False):
         mine = _dist.my_items(len(arglist))
         local = {}
         if mine:

@@ -216,8 +216,10 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
                              const double* alpha, const double* domain, const int* iparams,
                              const double* dparams, const double* uni, long long n_uni, const int* uni_off,
                              const int* guess_off, const double* guesses, int cap, int max_roots,
-                             double* roots, int* n_roots, int* n_calls, int* status, long long* stats) {
+                             double* roots, int* n_roots, int* n_calls, int* status, long long* stats,
+                             const PsiModeExtra* extra) {
     (void)n_uni;
+    if (extra && extra->rec_dev) return psi_internal_fail(PSI_ERR_ARG, "no device records in the CPU harness");
     long long total = 0;
     if (g_mode_lanes > 1) {
         for (int i = 0; i < n_items; ++i) {
@@ -247,9 +249,21 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
             cfg.tol = dparams[2 * i]; cfg.clean_tol = dparams[2 * i + 1];
             const int g0 = guess_off[i], ng = guess_off[i + 1] - g0;
             int nr = 0, nc = 0;
+            ModeDetail det;
             status[i] = mode_run<WarpOne>(ev, cfg, reinterpret_cast<const cx*>(guesses) + g0, ng, uni + uni_off[i], sc,
-                                          reinterpret_cast<cx*>(roots) + (size_t)i * max_roots, max_roots, &nr, &nc);
+                                          reinterpret_cast<cx*>(roots) + (size_t)i * max_roots, max_roots, &nr, &nc,
+                                          &det);
             n_roots[i] = nr; n_calls[i] = nc;
+            if (extra) {
+                if (extra->M) extra->M[i] = det.M;
+                if (extra->upos) extra->upos[i] = det.upos;
+                if (extra->conv) extra->conv[i] = det.conv;
+                for (int k = 0; k < det.M; ++k) {
+                    if (extra->Z) { extra->Z[2 * ((size_t)i * cap + k)] = sc.Z[k].re; extra->Z[2 * ((size_t)i * cap + k) + 1] = sc.Z[k].im; }
+                    if (extra->F) { extra->F[2 * ((size_t)i * cap + k)] = sc.F[k].re; extra->F[2 * ((size_t)i * cap + k) + 1] = sc.F[k].im; }
+                    if (extra->mask) extra->mask[(size_t)i * cap + k] = sc.mask[k];
+                }
+            }
             total += ev.evals;
         });
     }

@@ -7,6 +7,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from common import carr, load
 from test_host_logic import same_root_sets
@@ -63,3 +64,28 @@ def _single_rank_refine():
                 "roots": {str(k): [[z.real, z.imag] for z in g['results'][k]] for k in g['results']}}
     finally:
         _device.get_context = saved
+
+
+@pytest.mark.gpu
+def test_two_gpu_device_records(tmp_path, built):
+    """world_size 2 over NCCL on two GPUs (skipped on a one-GPU box): the map and the refinement campaign, whose
+    results are exchanged device to device (psi_mode_batch_device_rec + all_gather_into_tensor on the library's
+    buffer), equal the single-GPU run bit for bit on both ranks."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    worker = os.path.join(ROOT, "tests", "_rank_worker_nccl.py")
+    subprocess.run([sys.executable, worker, str(tmp_path)], check=True, timeout=900, cwd=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29741", worker, str(tmp_path)]
+    subprocess.run(cmd, check=True, timeout=900, cwd=ROOT)
+    one = json.load(open(tmp_path / "rank0_of1.json"))
+    two = [json.load(open(tmp_path / ("rank%d_of2.json" % r))) for r in range(2)]
+    assert one["exchange"] is None and one["map_with_roots"] > 50
+    for o in two:
+        assert o["world"] == 2 and o["exchange"] and "device records" in o["exchange"]
+        assert o["refine_exchange"] and "device records" in o["refine_exchange"]
+        assert o["map_hash"] == one["map_hash"] and o["map_with_roots"] == one["map_with_roots"]
+        assert o["refine_log"] == one["refine_log"] and o["refine_runs"] == one["refine_runs"]
+        assert o["refine_hash"] == one["refine_hash"]
+        assert o["run_is_none"] == (o["rank"] != 0)
