@@ -208,11 +208,17 @@ class PSIMode:
                  sound_speed_over_eta=1/0.05, size_distribution_power=3.5, single_size_flag=False,
                  n_sample=20, max_zoom_domains=1, verbose_flag=False, size_density=None,
                  tol=1.0e-13, clean_tol=1.0e-4, max_secant_iterations=100,
-                 tanhsinh_integrator=None, device=None):
+                 tanhsinh_integrator=None, device=None, engine=None):
         self.psi_dispersion = psid.PSIDispersion(dust_to_gas_ratio, stokes_range, sound_speed_over_eta,
                                                  size_distribution_power, single_size_flag,
                                                  size_density, tanhsinh_integrator, device=device)
         self.dispersion = self.psi_dispersion.calculate
+        # "device" (default): a calculate() call is one search of the K4 pipeline; "python": the generator form
+        # below (LAPACK AAA on the host, D on the GPU) -- what verbose and count_roots=True calls always use
+        import os
+        self.engine = engine or os.environ.get("PSI_B200_ENGINE", "device")
+        if self.engine == "native":
+            self.engine = "python"
         self.cfg = ModeSettings(real_range, imag_range, n_sample, max_zoom_domains, tol, clean_tol,
                                 max_secant_iterations)
         self.domain = self.cfg.domain
@@ -249,10 +255,69 @@ class PSIMode:
                             self.log_print if self.verbose_flag else None)
         return Job(mach, self.psi_dispersion.dist_id, wave_number_x, wave_number_z, viscous_alpha)
 
+    def _device_search_ok(self, guess_roots, count_roots):
+        """A single search goes through the K4 pipeline (everything on the GPU) unless it needs what only the
+        generator form offers: verbose logging, the count_roots coupling, non-default internal knobs, more than 512
+        samples, or a context without the pipeline."""
+        ctx = self.psi_dispersion.ctx
+        if self.engine != "device" or not hasattr(ctx, "mode_search_detail"):
+            return False
+        if self.verbose_flag or count_roots:
+            return False
+        if (self.max_zoom_domains_per_level, self.minimum_interpolation_nodes, self.force_at_least_one_root) != \
+                (4, 4, True):
+            return False
+        return self.n_sample >= 2 and self.n_sample*(1 + len(guess_roots) + 4*self.max_zoom_level) <= 512
+
+    def _calculate_on_device(self, wave_number_x, wave_number_z, viscous_alpha, guess_roots):
+        """PSIMode.calculate as ONE search of the K4 pipeline (C ABI psi_mode_search_detail).  The sample points come
+        from numpy's global legacy stream exactly as in the reference (complex_roots.py:404-409): the numbers the
+        longest possible search could need are drawn ahead, and afterwards the generator is put where the reference
+        would have left it (only the numbers actually consumed count)."""
+        ns, mz = int(self.n_sample), int(self.max_zoom_level)
+        guesses = [complex(g) for g in guess_roots]
+        state = np.random.get_state()
+        u = np.random.random_sample(2*ns*(1 + len(guesses) + 4*mz))
+        d = self.domain
+        res = self.psi_dispersion.ctx.mode_search_detail(
+            self.psi_dispersion.dist_id, float(wave_number_x), float(wave_number_z), float(viscous_alpha),
+            [d.xmin, d.xmax, d.ymin, d.ymax], ns, mz, int(self.max_secant_iterations), float(self.ra.tol),
+            float(self.ra.clean_tol), u, guesses)
+        np.random.set_state(state)
+        np.random.random_sample(res["n_uniforms_used"])
+        self.n_function_call = res["n_function_call"]
+        self.z_sample, self.f_sample = res["z_sample"], res["f_sample"]
+        if res["status"] == 1:
+            raise ValueError('Nan or Inf in sample points or function samples')
+        if res["status"] == 3:
+            raise ValueError('tol too small (0 <= 0)')
+        if res["status"] not in (0, 4):
+            raise RuntimeError('device root search failed with status %d' % res["status"])
+        self.max_convergence_iterations = max(self.max_convergence_iterations, res["max_convergence_iterations"])
+        # the rational approximation callers look at (ra.maskF, ra.evaluate, find_minimum, plot_dispersion): support
+        # points from the device, weights refitted on the host (one small SVD; the device's own weights differ from
+        # them by a phase only)
+        ra = cr.RationalApproximation(self.domain, tol=self.ra.tol, clean_tol=self.ra.clean_tol)
+        ra.F = ra.f = res["f_sample"]
+        ra.Z = ra.z = res["z_sample"]
+        ra.M = len(res["z_sample"])
+        ra.maskF = res["mask"].astype(float)
+        if ra.maskF.sum() >= 1 and ra.M > ra.maskF.sum():
+            ra.calc_weights_residuals()
+        self.ra = ra
+        return res["roots"]
+
     def calculate(self, wave_number_x, wave_number_z, viscous_alpha=0, guess_roots=[],
                   count_roots=False):
         """Complex mode frequencies at (Kx, Kz) and viscosity parameter viscous_alpha."""
         self.disp = lambda z: self.dispersion(z, wave_number_x, wave_number_z, viscous_alpha)
+        if self._device_search_ok(guess_roots, count_roots):
+            try:
+                return self._calculate_on_device(wave_number_x, wave_number_z, viscous_alpha, guess_roots)
+            except Exception:
+                print(('Root search failed at Kx = {}, Kz = {}, alpha = {}, guess_roots = {}')
+                      .format(wave_number_x, wave_number_z, viscous_alpha, guess_roots))
+                raise
         trace = ModeTrace()
         job = self.make_job(wave_number_x, wave_number_z, viscous_alpha, guess_roots, count_roots,
                             None, trace)

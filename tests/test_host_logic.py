@@ -32,6 +32,22 @@ def test_psimode_reference_cases(backend, case):
     assert pm.n_function_call == case["n_function_call"]
     assert len(pm.z_sample) == len(case["z_sample"])
     np.testing.assert_array_equal(pm.z_sample, carr(case["z_sample"]))   # same random stream
+    # the call was ONE search of the K4 pipeline (psi_mode_search_detail), not the host generators ...
+    assert pm._device_search_ok([], False)
+    # ... which leaves numpy's global stream exactly where the reference leaves it (2 numbers per sample point)
+    after = np.random.random_sample()
+    np.random.seed(case["seed"])
+    np.random.random_sample(2*len(case["z_sample"]))
+    assert after == np.random.random_sample()
+    # ... and the attributes callers read: samples, support mask, a usable approximant
+    assert pm.ra.maskF.shape == (len(pm.z_sample),) and 4 <= pm.ra.maskF.sum() <= len(pm.z_sample)/2
+    assert abs(pm.ra.evaluate(roots[0])) < 1e-6*np.max(np.abs(pm.f_sample))
+    # the generator form (engine='python': LAPACK AAA on the host) gives the same root and call count
+    np.random.seed(case["seed"])
+    pg = PSIMode(tanhsinh_integrator=TanhSinh(), engine="python", **kw)
+    rg = pg.calculate(wave_number_x=case["K"][0], wave_number_z=case["K"][1], viscous_alpha=case["alpha"])
+    assert len(rg) == 1 and abs(rg[0] - roots[0]) <= 1e-8*abs(roots[0])
+    assert pg.n_function_call == case["n_function_call"]
 
 
 @pytest.mark.parametrize("engine", ["device", "native", "python"])
