@@ -50,6 +50,23 @@ typedef struct psi_dist_desc {
     double poles[PSI_MAX_POLES];
 } psi_dist_desc;
 
+/* Tabulated size density (kind PSI_KIND_TABLE): for ANY callable sigma(a) the reference accepts
+ * (SizeDensity(sigma, size_range), sizedensity.py:25-48, consumed at psi_dispersion.py:57-67, 139-145) the host
+ * tabulates the quadrature weight w(u) = e^u F(e^u), u = ln s, s = tau/tau_max in [tau_min/tau_max, 1], once per
+ * distribution: per smooth piece between the size density's kinks (SizeDensity.poles / tau_max) a uniform grid of
+ * cells, on each cell the cubic v(t) = c0 + t (c1 + t (c2 + t c3)), t in [0, 1), that interpolates w -- or ln w where
+ * w > 0 -- at four points of the cell.  Four doubles per cell, pieces one after the other: the device reads a cell
+ * with two 16-byte loads.  brk: n_seg + 1 break points (brk[0] = ln(tau_min/tau_max), brk[n_seg] = 0). */
+#define PSI_KIND_TABLE 3
+#define PSI_MAX_TABLE_SEGS (PSI_MAX_POLES + 1)
+typedef struct psi_table_desc {
+    int n_seg;
+    double brk[PSI_MAX_TABLE_SEGS + 1];
+    int n_cells[PSI_MAX_TABLE_SEGS];
+    int log_mode[PSI_MAX_TABLE_SEGS];
+    const double* coef;                         /* host pointer, 4 * sum(n_cells) doubles */
+} psi_table_desc;
+
 /* Library / device info. */
 const char* psi_version(void);
 const char* psi_last_error(void);
@@ -77,6 +94,9 @@ long long psi_ctx_launch_count(psi_ctx* ctx);
  * replaces PSIDispersion.__init__ (psi_dispersion.py:43-84) + int_j (:183-187).
  * Returns the distribution id (>= 0) or an error code. */
 int psi_dist_add(psi_ctx* ctx, const psi_dist_desc* desc);
+/* The same for a tabulated size density: desc->kind = PSI_KIND_TABLE with mu, tau range, sound speed, rhod,
+ * single_size and poles filled in (the analytic-family fields are ignored); the table is copied to the device. */
+int psi_dist_add_table(psi_ctx* ctx, const psi_dist_desc* desc, const psi_table_desc* table);
 /* out = {J0, J1, denom, vgx, vgy}  (psi_dispersion.py:74-79) */
 int psi_dist_get_background(psi_ctx* ctx, int dist, double out[5]);
 
@@ -95,7 +115,8 @@ int psi_disp_eval_host(psi_ctx* ctx, long long n, int broadcast, const int* dist
 int psi_disp_eval_dev(psi_ctx* ctx, long long n, int broadcast, const int* dist, const double* kx,
                       const double* kz, const double* alpha, const double* w, double* D, double* M,
                       unsigned long long* node_evals_dev, unsigned class_mask, void* stream);
-/* Work class (0..7) of a point of distribution `dist` at viscosity parameter alpha. */
+/* Work class (0..9: node generator {MRN sqrt, general power law, PowerBump, PowerBumpTail, table} x {inviscid,
+ * viscous}) of a point of distribution `dist` at viscosity parameter alpha. */
 int psi_point_class(psi_ctx* ctx, int dist, double alpha);
 
 /* ---- native lock-step engine (csrc/psi_engine.cu): whole batches of root searches / contour counts,

@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("PSI_B200_LIB", os.path.join(_HERE, "libpsi_b200.so"))
 
 PSI_MAX_POLES = 4
 MODE_MAX_SAMPLES = 512            # PSI_MODE_MAX_SAMPLES of include/psi_b200.h
-KIND_POWERLAW, KIND_POWERBUMP, KIND_POWERBUMPTAIL = 0, 1, 2
+KIND_POWERLAW, KIND_POWERBUMP, KIND_POWERBUMPTAIL, KIND_TABLE = 0, 1, 2, 3
+PSI_MAX_TABLE_SEGS = PSI_MAX_POLES + 1
 
 
 class PsiError(RuntimeError):
@@ -33,6 +34,87 @@ class DistDesc(C.Structure):
 
     def key(self):
         return bytes(self)
+
+
+class TableDescStruct(C.Structure):
+    """Mirror of ``psi_table_desc`` (include/psi_b200.h)."""
+    _fields_ = [("n_seg", C.c_int), ("brk", C.c_double*(PSI_MAX_TABLE_SEGS + 1)),
+                ("n_cells", C.c_int*PSI_MAX_TABLE_SEGS), ("log_mode", C.c_int*PSI_MAX_TABLE_SEGS),
+                ("coef", C.c_void_p)]
+
+
+class SizeDensityTable:
+    """Host side of a tabulated size density (C ABI psi_dist_add_table): the quadrature weight w(u) = e^u F(e^u),
+    u = ln s, of ANY callable the reference accepts (SizeDensity(sigma, size_range), sizedensity.py:25-48), as
+    piecewise cubics on uniform grids between the kinks of sigma (``poles``, in units of stopping time).
+
+    Per cell the cubic interpolates w -- ln w wherever w > 0 on the whole piece: exact for power laws, and it keeps
+    the RELATIVE error uniform over the eight decades of s -- at the four Chebyshev points of the cell.  The cell
+    count starts at ``cells`` per piece and doubles until the interpolant reproduces the callable to ``rtol`` at
+    random probe points (sigma is called with arrays, as the reference's quadrature does)."""
+
+    def __init__(self, size_density, tau_min, tau_max, poles, cells=16384, rtol=2e-13, max_cells=1 << 21):
+        self.f = size_density
+        smin = tau_min/tau_max
+        brk = [np.log(smin)] + sorted(np.log(p/tau_max) for p in poles if tau_min < p < tau_max) + [0.0]
+        if len(brk) - 1 > PSI_MAX_TABLE_SEGS:
+            raise ValueError("at most %d size-density poles are supported" % PSI_MAX_POLES)
+        self.brk = np.array(brk)
+        self.n_cells, self.log_mode, coef = [], [], []
+        self.max_rel_err = 0.0
+        rng = np.random.RandomState(12345)
+        for a, b in zip(brk[:-1], brk[1:]):
+            n = max(16, int(cells*(b - a)/(brk[-1] - brk[0])) + 1)
+            while True:
+                c, logm = self._fit(a, b, n)
+                err = self._probe(a, b, n, c, logm, rng)
+                if err <= rtol or 2*n > max_cells:
+                    break
+                n *= 2
+            self.max_rel_err = max(self.max_rel_err, err)
+            self.n_cells.append(n)
+            self.log_mode.append(int(logm))
+            coef.append(c)
+        self.coef = np.ascontiguousarray(np.concatenate(coef), dtype=np.float64)
+
+    def weight(self, u):
+        """w(u) = e^u F(e^u) from the callable."""
+        s = np.exp(u)
+        return s*np.asarray(self.f(s), dtype=np.float64)
+
+    _T = 0.5 - 0.5*np.cos((2*np.arange(4) + 1)*np.pi/8)          # Chebyshev points of [0, 1]
+    _VINV = np.linalg.inv(np.vander(_T, 4, increasing=True))       # values at _T -> monomial coefficients
+
+    def _fit(self, a, b, n):
+        h = (b - a)/n
+        u = a + h*(np.arange(n)[:, None] + self._T[None, :])
+        w = self.weight(u.ravel()).reshape(n, 4)
+        logm = bool(np.all(w > 0) and np.all(np.isfinite(w)))
+        v = np.log(w) if logm else w
+        return v @ self._VINV.T, logm
+
+    def _probe(self, a, b, n, c, logm, rng):
+        t = rng.uniform(0, 1, 4096)
+        i = rng.randint(0, n, 4096)
+        u = a + (b - a)/n*(i + t)
+        v = ((c[i, 3]*t + c[i, 2])*t + c[i, 1])*t + c[i, 0]
+        got = np.exp(v) if logm else v
+        ref = self.weight(u)
+        scale = np.abs(ref) if logm else np.maximum(np.abs(ref), 1e-300 + np.max(np.abs(ref))*1e-6)
+        return float(np.max(np.abs(got - ref)/scale))
+
+    def key(self):
+        return self.brk.tobytes() + self.coef.tobytes()
+
+    def struct(self):
+        t = TableDescStruct()
+        t.n_seg = len(self.n_cells)
+        for k, v in enumerate(self.brk):
+            t.brk[k] = v
+        for k, (n, m) in enumerate(zip(self.n_cells, self.log_mode)):
+            t.n_cells[k], t.log_mode[k] = n, m
+        t.coef = self.coef.ctypes.data
+        return t
 
 
 _lib = None
@@ -55,6 +137,7 @@ _SIGNATURES = {
     "psi_ctx_synchronize": (C.c_int, [_vp]),
     "psi_ctx_launch_count": (C.c_longlong, [_vp]),
     "psi_dist_add": (C.c_int, [_vp, C.POINTER(DistDesc)]),
+    "psi_dist_add_table": (C.c_int, [_vp, C.POINTER(DistDesc), C.POINTER(TableDescStruct)]),
     "psi_dist_get_background": (C.c_int, [_vp, C.c_int, _dp]),
     "psi_disp_eval_host": (C.c_int, [_vp, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      C.POINTER(C.c_ulonglong)]),
@@ -580,10 +663,14 @@ class Context(EngineAPI):
     def synchronize(self):
         check(self.lib.psi_ctx_synchronize(self.handle), "psi_ctx_synchronize")
 
-    def add_dist(self, desc):
-        k = desc.key()
+    def add_dist(self, desc, table=None):
+        k = desc.key() + (table.key() if table is not None else b"")
         if k not in self._dists:
-            self._dists[k] = check(self.lib.psi_dist_add(self.handle, C.byref(desc)), "psi_dist_add")
+            if table is None:
+                self._dists[k] = check(self.lib.psi_dist_add(self.handle, C.byref(desc)), "psi_dist_add")
+            else:
+                self._dists[k] = check(self.lib.psi_dist_add_table(self.handle, C.byref(desc),
+                                                                   C.byref(table.struct())), "psi_dist_add_table")
         return self._dists[k]
 
     def background(self, dist_id):
@@ -687,9 +774,45 @@ def _bump_constants(pb):
     return beta, norm_pl, amp, curv
 
 
+def _analytic_F(d, s):
+    """F(s) = taumax*sigma(taumax*s)/rhod of an analytic descriptor, as the device evaluates it (csrc/psi_math.cuh:
+    sigma_of, F_of) -- used to CHECK that a recognised callable really is the family its name suggests."""
+    a = d.tau_max*np.asarray(s, dtype=float)
+    if d.kind == KIND_POWERLAW:
+        sig = a**d.q
+    else:
+        pl = d.norm_pl*a**d.beta
+        if d.kind == KIND_POWERBUMPTAIL:
+            pl = np.where(a > d.aBT, pl, d.norm_pl*d.aBT**d.beta*np.sqrt(a/d.aBT))
+        bb = d.amp*np.exp(d.curv*(a - d.aP)**2)
+        v = np.where(a > d.aL, np.maximum(pl, bb), pl)
+        v = np.where(a > d.aP, bb, v)
+        sig = v*a**3*d.scale
+    return d.tau_max*sig/d.rhod
+
+
+def _matches_callable(d, size_density, n_probe=48):
+    """True when the analytic descriptor reproduces the user's callable at n_probe log-spaced sizes (1e-12)."""
+    s = np.exp(np.linspace(np.log(d.tau_min/d.tau_max), 0.0, n_probe + 2)[1:-1])
+    try:
+        ref = np.asarray(size_density(s), dtype=float)
+    except Exception:
+        return False
+    got = _analytic_F(d, s)
+    return bool(np.all(np.isfinite(ref)) and np.all(np.abs(got - ref) <= 1e-12*np.abs(ref) + 1e-300))
+
+
 def describe_size_density(mu, stokes_range, sound_speed, power, single_size, size_density):
-    """Build the ``psi_dist_desc`` for PSIDispersion's constructor arguments
-    (reference psi_dispersion.py:43-66)."""
+    """Build the device description of PSIDispersion's constructor arguments (reference psi_dispersion.py:43-66):
+    (``psi_dist_desc``, table or None).
+
+    * no size density: the power law a^(3 - power) with its closed-form rho_d;
+    * a SizeDensity wrapping PowerBump.sigma0 / PowerBumpTail.sigma0: the analytic family -- AFTER checking at 48
+      probe sizes that the callable really evaluates to the family's formula (a subclass with its own sigma0 does
+      not, and is tabulated instead of being silently mistaken for the stock bump);
+    * any other callable (the reference takes any ``SizeDensity(sigma, size_range)``, sizedensity.py:25-48): kind
+      TABLE -- the quadrature weight tabulated once on the host (SizeDensityTable) and read on the device as
+      piecewise cubics, two 16-byte loads per node."""
     d = DistDesc()
     d.single_size = int(bool(single_size))
     d.mu = float(mu)
@@ -698,34 +821,39 @@ def describe_size_density(mu, stokes_range, sound_speed, power, single_size, siz
     d.sound_speed = float(sound_speed)
     d.scale = 1.0
     poles = []
+    table = None
     if size_density is None:
         d.kind = KIND_POWERLAW
         d.q = 3 - power
         d.rhod = (stokes_range[0]**(4.0 - power) - stokes_range[1]**(4.0 - power))/(power - 4.0)
     else:
+        poles = [float(p) for p in size_density.poles]
+        if len(poles) > PSI_MAX_POLES:
+            raise ValueError("at most %d size-density poles are supported" % PSI_MAX_POLES)
+        d.rhod = float(size_density.rhod)
         sigma = _find_sigma(size_density)
         pb = getattr(sigma, "__self__", None)
         is_sigma0 = getattr(sigma, "__name__", "") == "sigma0"
-        if pb is None or not is_sigma0 or not all(hasattr(pb, k) for k in ("aP", "aL", "aR", "amin")):
-            raise NotImplementedError(
-                "size_density must be None (power law) or a SizeDensity wrapping PowerBump.sigma0 / "
-                "PowerBumpTail.sigma0: the device evaluates sigma(a) analytically and cannot call "
-                "an arbitrary Python function")
-        beta, norm_pl, amp, curv = _bump_constants(pb)
-        d.kind = KIND_POWERBUMPTAIL if hasattr(pb, "aBT") else KIND_POWERBUMP
-        d.beta, d.norm_pl, d.amp, d.curv = beta, norm_pl, amp, curv
-        d.aL, d.aP = float(pb.aL), float(pb.aP)
-        d.aBT = float(getattr(pb, "aBT", -1.0))
-        if getattr(pb, "epstot", None) is not None:
-            d.scale = float(pb.epstot)/float(pb.mnorm)
-        d.rhod = float(size_density.rhod)
-        if float(size_density.amax) != d.tau_max:
-            # F(s) = amax*sigma(amax*s)/rhod uses the SizeDensity's own amax (sizedensity.py:41)
-            raise NotImplementedError("SizeDensity.amax must equal stokes_range[1]")
-        poles = [float(p) for p in size_density.poles]
-    if len(poles) > PSI_MAX_POLES:
-        raise ValueError("at most %d size-density poles are supported" % PSI_MAX_POLES)
+        analytic = (pb is not None and is_sigma0 and all(hasattr(pb, k) for k in ("aP", "aL", "aR", "amin"))
+                    and float(size_density.amax) == d.tau_max)
+        if analytic:
+            try:
+                beta, norm_pl, amp, curv = _bump_constants(pb)
+                d.kind = KIND_POWERBUMPTAIL if hasattr(pb, "aBT") else KIND_POWERBUMP
+                d.beta, d.norm_pl, d.amp, d.curv = beta, norm_pl, amp, curv
+                d.aL, d.aP = float(pb.aL), float(pb.aP)
+                d.aBT = float(getattr(pb, "aBT", -1.0))
+                if getattr(pb, "epstot", None) is not None:
+                    d.scale = float(pb.epstot)/float(pb.mnorm)
+                analytic = _matches_callable(d, size_density)
+            except Exception:
+                analytic = False
+        if not analytic:
+            d.kind = KIND_TABLE
+            d.q = d.beta = d.norm_pl = d.amp = d.curv = d.aL = d.aP = d.aBT = 0.0
+            d.scale = 1.0
+            table = SizeDensityTable(size_density, d.tau_min, d.tau_max, poles)
     d.n_poles = len(poles)
     for i, p in enumerate(poles):
         d.poles[i] = p
-    return d
+    return d, table

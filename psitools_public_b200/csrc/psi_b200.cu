@@ -225,6 +225,7 @@ struct psi_ctx {
     int fast_cap = 8;                      // K1 fast path: last level a thread-per-point evaluation may use (0 = off)
     long long* d_hard = nullptr;           // indices of the points the fast path handed to the warp kernel
     size_t hard_cap = 0;
+    std::vector<double*> d_tables;         // tabulated size densities (psi_dist_add_table)
 };
 
 extern "C" { static int ensure_stage(psi_ctx* c, size_t bytes); }
@@ -434,7 +435,9 @@ static thread_kernel_t thread_kernel_for(int cls) {
     case 4: return disp_eval_thread_kernel<2, false>;
     case 5: return disp_eval_thread_kernel<2, true>;
     case 6: return disp_eval_thread_kernel<3, false>;
-    default: return disp_eval_thread_kernel<3, true>;
+    case 7: return disp_eval_thread_kernel<3, true>;
+    case 8: return disp_eval_thread_kernel<4, false>;
+    default: return disp_eval_thread_kernel<4, true>;
     }
 }
 
@@ -447,7 +450,9 @@ static eval_kernel_t eval_kernel_for(int cls) {
     case 4: return disp_eval_kernel<2, false>;
     case 5: return disp_eval_kernel<2, true>;
     case 6: return disp_eval_kernel<3, false>;
-    default: return disp_eval_kernel<3, true>;
+    case 7: return disp_eval_kernel<3, true>;
+    case 8: return disp_eval_kernel<4, false>;
+    default: return disp_eval_kernel<4, true>;
     }
 }
 
@@ -735,11 +740,11 @@ __global__ void mode_pack_kernel(ModeDev m, int n_items, int rows, double* rec) 
 
 #define PSI_CLASS_TABLE(NAME)                                                                      \
     {NAME<0, false>, NAME<0, true>, NAME<1, false>, NAME<1, true>, NAME<2, false>, NAME<2, true>,    \
-     NAME<3, false>, NAME<3, true>}
+     NAME<3, false>, NAME<3, true>, NAME<4, false>, NAME<4, true>}
 typedef decltype(&polish_kernel<0, false, false>) polish_kernel_t;
 #define PSI_CLASS_TABLE_CTA(NAME)                                                                          \
     {NAME<0, false, true>, NAME<0, true, true>, NAME<1, false, true>, NAME<1, true, true>, NAME<2, false, true>, \
-     NAME<2, true, true>, NAME<3, false, true>, NAME<3, true, true>}
+     NAME<2, true, true>, NAME<3, false, true>, NAME<3, true, true>, NAME<4, false, true>, NAME<4, true, true>}
 typedef decltype(&contour_kernel<0, false>) contour_kernel_t;
 static const polish_kernel_t kPolishKernels[kNumClasses] = PSI_CLASS_TABLE(polish_kernel);
 static const polish_kernel_t kPolishKernelsCta[kNumClasses] = PSI_CLASS_TABLE_CTA(polish_kernel);
@@ -839,6 +844,7 @@ void psi_ctx_destroy(psi_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_nodes); cudaFree(c->d_level_off); cudaFree(c->d_dists); cudaFree(c->d_counter);
     cudaFree(c->d_stage); cudaFree(c->d_contour_scratch); cudaFree(c->d_mode_scratch); cudaFree(c->d_hard);
+    for (double* t : c->d_tables) cudaFree(t);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -859,9 +865,25 @@ int psi_ctx_synchronize(psi_ctx* c) {
     return PSI_OK;
 }
 
+static int dist_add_common(psi_ctx* c, const psi_dist_desc* s, const psi_table_desc* tb);
+
 int psi_dist_add(psi_ctx* c, const psi_dist_desc* s) {
     if (!c || !s) return fail(PSI_ERR_ARG, "psi_dist_add: null argument");
     if (s->kind < 0 || s->kind > 2) return fail(PSI_ERR_ARG, "psi_dist_add: unknown kind");
+    return dist_add_common(c, s, nullptr);
+}
+
+int psi_dist_add_table(psi_ctx* c, const psi_dist_desc* s, const psi_table_desc* tb) {
+    if (!c || !s || !tb || !tb->coef) return fail(PSI_ERR_ARG, "psi_dist_add_table: null argument");
+    if (s->kind != PSI_KIND_TABLE) return fail(PSI_ERR_ARG, "psi_dist_add_table: desc->kind must be PSI_KIND_TABLE");
+    if (tb->n_seg < 1 || tb->n_seg > PSI_MAX_TABLE_SEGS) return fail(PSI_ERR_ARG, "psi_dist_add_table: bad n_seg");
+    for (int k = 0; k < tb->n_seg; ++k)
+        if (tb->n_cells[k] < 1 || !(tb->brk[k + 1] > tb->brk[k]))
+            return fail(PSI_ERR_ARG, "psi_dist_add_table: pieces must be non-empty and ascending");
+    return dist_add_common(c, s, tb);
+}
+
+static int dist_add_common(psi_ctx* c, const psi_dist_desc* s, const psi_table_desc* tb) {
     if (s->n_poles < 0 || s->n_poles > PSI_MAX_POLES)
         return fail(PSI_ERR_CAPACITY, "psi_dist_add: too many size-density poles");
     if ((int)c->h_dists.size() >= kMaxDists) return fail(PSI_ERR_CAPACITY, "too many distributions");
@@ -869,6 +891,22 @@ int psi_dist_add(psi_ctx* c, const psi_dist_desc* s) {
         return fail(PSI_ERR_ARG, "psi_dist_add: bad Stokes range or rhod");
     CK(cudaSetDevice(c->device));
     DistParams d = dist_from_desc(*s);
+    if (tb) {
+        size_t cells = 0;
+        d.tab_nseg = tb->n_seg;
+        for (int k = 0; k < tb->n_seg; ++k) {
+            d.tab_off[k] = (int)cells; d.tab_n[k] = tb->n_cells[k]; d.tab_log[k] = tb->log_mode[k];
+            d.tab_brk[k] = tb->brk[k];
+            d.tab_invh[k] = tb->n_cells[k] / (tb->brk[k + 1] - tb->brk[k]);
+            cells += (size_t)tb->n_cells[k];
+        }
+        d.tab_brk[tb->n_seg] = tb->brk[tb->n_seg];
+        double* dev = nullptr;
+        CK(cudaMalloc(&dev, 32 * cells));
+        CK(cudaMemcpy(dev, tb->coef, 32 * cells, cudaMemcpyHostToDevice));
+        c->d_tables.push_back(dev);
+        d.tab = dev;
+    }
     const int id = (int)c->h_dists.size();
     CK(cudaMemcpyAsync(c->d_dists + id, &d, sizeof(d), cudaMemcpyHostToDevice, c->stream));
     background_kernel<<<1, 32, 0, c->stream>>>(table_view(c), c->d_dists, id);
@@ -905,7 +943,7 @@ static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* d
     long long want = (n + warps - 1) / warps;
     int grid = (int)(want < c->sm_count ? want : c->sm_count);
     NodeTableView t = table_view(c);
-    if ((class_mask & 0xffu) == 0) class_mask = 0xffu;
+    if ((class_mask & 0x3ffu) == 0) class_mask = 0x3ffu;
     // fast path: thread per point first, the warp kernel only for what that leaves (needs the predictor rule,
     // no M output, and enough points to fill the machine with one thread each)
     const bool fast = c->predict_exit != 0 && c->fast_cap > 0 && M == nullptr && n >= 4096;

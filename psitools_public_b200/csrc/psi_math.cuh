@@ -70,7 +70,8 @@ PSI_HD cx div_safe(cx a, cx b) {
 }
 
 // ---- dust distributions ----------------------------------------------------------------------------
-enum DistKind { kPowerLaw = 0, kPowerBump = 1, kPowerBumpTail = 2 };
+enum DistKind { kPowerLaw = 0, kPowerBump = 1, kPowerBumpTail = 2, kTable = 3 };
+constexpr int kMaxTableSegs = 5;     // smooth pieces of a tabulated size density (at most kMaxPoles kinks)
 constexpr int kMaxPoles = 4;
 
 struct DistParams {
@@ -88,7 +89,34 @@ struct DistParams {
     int n_init_poles, n_calc_poles;
     double init_poles[kMaxPoles];
     double calc_poles[kMaxPoles];
+    // tabulated size density (kind == kTable): w(u) = e^u F(e^u), u = ln s in [ln smin, 0], as piecewise cubics on
+    // a uniform grid per smooth piece [brk[k], brk[k+1]) -- cell i of piece k: v(t) = c0 + t (c1 + t (c2 + t c3)),
+    // t in [0, 1), four doubles at tab[4 * (tab_off[k] + i)] (32 bytes: two 16-byte loads); tab_log[k]: v = ln w
+    const double* tab;
+    int tab_nseg;
+    int tab_off[kMaxTableSegs], tab_n[kMaxTableSegs], tab_log[kMaxTableSegs];
+    double tab_brk[kMaxTableSegs + 1], tab_invh[kMaxTableSegs];
 };
+
+// weight e^u F(e^u) of a tabulated size density
+PSI_HD double table_weight(const DistParams& d, double u) {
+    int k = 0;
+    while (k + 1 < d.tab_nseg && u >= d.tab_brk[k + 1]) ++k;
+    double t = (u - d.tab_brk[k]) * d.tab_invh[k];
+    int i = (int)t;
+    if (i < 0) i = 0;
+    if (i > d.tab_n[k] - 1) i = d.tab_n[k] - 1;
+    t -= (double)i;
+    const double* c = d.tab + 4 * ((size_t)d.tab_off[k] + i);
+#if defined(__CUDA_ARCH__)
+    const double2 c01 = __ldg(reinterpret_cast<const double2*>(c));
+    const double2 c23 = __ldg(reinterpret_cast<const double2*>(c) + 1);
+    const double v = fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
+#else
+    const double v = ((c[3] * t + c[2]) * t + c[1]) * t + c[0];
+#endif
+    return d.tab_log[k] ? exp(v) : v;
+}
 
 // ---- fast reciprocal / reciprocal square root (MUFU seed + Newton, ~1 ulp) ---------------------------
 PSI_HD double fast_rcp(double a) {
@@ -120,6 +148,10 @@ PSI_HD cx fast_recip(cx a) { const double s = fast_rcp(norm2(a)); return cx(a.re
 // sigma(a) of the analytic families (straightforward form; the quadrature uses NodeGen below)
 PSI_HD double sigma_of(const DistParams& d, double a) {
     if (d.kind == kPowerLaw) return pow(a, d.q);
+    if (d.kind == kTable) {          // w(u) = e^u F(e^u) = s taumax sigma(taumax s)/rhod  ->  sigma = w rhod/a
+        const double u = log(a / d.taumax);
+        return table_weight(d, u) * d.rhod / a;
+    }
     // PowerBump.mnn (power_bump.py:97-123) / PowerBumpTail.fnn (:193-212)
     double pl = d.norm_pl * pow(a, d.beta);
     if (d.kind == kPowerBumpTail && !(a > d.aBT))
@@ -143,10 +175,11 @@ PSI_HD double F_of(const DistParams& d, double s) {
 // e^u F(e^u) = taumax^(q+1)/rhod * e^{(q+1)u}  (psi_dispersion.py:57-66), i.e. a second exp pair --
 // or a square root when q + 1 = 1/2 (MRN).  For the bump families e^u F(e^u) = tau^4 v(tau) scale/rhod
 // with v the piecewise max(power law, Gaussian) of power_bump.py:97-123.
-enum NodeKind { kNodePowerSqrt = 0, kNodePowerGen = 1, kNodeBump = 2, kNodeBumpTail = 3 };
+enum NodeKind { kNodePowerSqrt = 0, kNodePowerGen = 1, kNodeBump = 2, kNodeBumpTail = 3, kNodeTable = 4 };
 
 PSI_HD int node_kind_of(const DistParams& d) {
     if (d.kind == kPowerLaw) return (d.q == -0.5) ? kNodePowerSqrt : kNodePowerGen;
+    if (d.kind == kTable) return kNodeTable;
     return d.kind == kPowerBump ? kNodeBump : kNodeBumpTail;
 }
 
@@ -154,18 +187,21 @@ struct NodeVals { double tau, it, wt; };      // stopping time, 1/tau, e^u F(e^u
 
 template <int NK>
 struct NodeGen {
-    double half, tm, itm, cw, qe, plm, tailc;
+    double half, tm, itm, cw, qe, plm, tailc, umid;
     const DistParams* d;
     PSI_HD void begin(const DistParams& dd, double a, double b) {
         d = &dd;
         half = 0.5 * (b - a);
         const double mid = 0.5 * (b + a);
+        umid = mid;
         const double em = exp(mid);
         tm = dd.taumax * em;                    // tau at x = 0
         itm = 1.0 / tm;
         if (NK == kNodePowerSqrt || NK == kNodePowerGen) {
             qe = dd.q + 1.0;
             cw = pow(dd.taumax, qe) / dd.rhod * exp(qe * mid);
+        } else if (NK == kNodeTable) {
+            cw = 1.0;
         } else {
             cw = dd.scale / dd.rhod;
             plm = dd.norm_pl * pow(tm, dd.beta);                         // power law at x = 0
@@ -200,6 +236,9 @@ struct NodeGen {
         if (NK == kNodePowerGen) {
             const double G = exp(qe * h);
             p.wt = cw * G; n.wt = cw * fast_rcp(G);
+        } else if (NK == kNodeTable) {
+            p.wt = table_weight(*d, umid + h);
+            n.wt = table_weight(*d, umid - h);
         } else {
             const double B = exp(d->beta * h);
             p.wt = bump_weight(p.tau, plm * B);
@@ -208,7 +247,9 @@ struct NodeGen {
     }
     PSI_HD NodeVals centre() const {            // x = 0
         NodeVals c; c.tau = tm; c.it = itm;
-        if (NK == kNodePowerSqrt || NK == kNodePowerGen) c.wt = cw; else c.wt = bump_weight(tm, plm);
+        if (NK == kNodePowerSqrt || NK == kNodePowerGen) c.wt = cw;
+        else if (NK == kNodeTable) c.wt = table_weight(*d, umid);
+        else c.wt = bump_weight(tm, plm);
         return c;
     }
 };

@@ -211,7 +211,8 @@ PSI_HD void background_warp(const NodeTableView& t, DistParams& d, unsigned long
         case kNodePowerSqrt: average_kind<W, 2, kNodePowerSqrt>(t, d, d.init_poles, d.n_init_poles, JNode(), one, j, nodes_done); break;
         case kNodePowerGen:  average_kind<W, 2, kNodePowerGen>(t, d, d.init_poles, d.n_init_poles, JNode(), one, j, nodes_done); break;
         case kNodeBump:      average_kind<W, 2, kNodeBump>(t, d, d.init_poles, d.n_init_poles, JNode(), one, j, nodes_done); break;
-        default:             average_kind<W, 2, kNodeBumpTail>(t, d, d.init_poles, d.n_init_poles, JNode(), one, j, nodes_done); break;
+        case kNodeBumpTail:  average_kind<W, 2, kNodeBumpTail>(t, d, d.init_poles, d.n_init_poles, JNode(), one, j, nodes_done); break;
+        default:             average_kind<W, 2, kNodeTable>(t, d, d.init_poles, d.n_init_poles, JNode(), one, j, nodes_done); break;
         }
     }
     d.j0 = j[0].re;
@@ -223,7 +224,7 @@ PSI_HD void background_warp(const NodeTableView& t, DistParams& d, unsigned long
 
 // Work class of a point: which specialisation of K1 evaluates it (kernels are compiled per class so
 // that each keeps its own, smaller register footprint).  class = node kind * 2 + (viscous ? 1 : 0).
-constexpr int kNumClasses = 8;
+constexpr int kNumClasses = 10;
 constexpr double kNearPoleBand = 2.5;      // |Re d(tau*)| below which the damped-frequency split point is added
 constexpr double kResonantBand = 1.0e-5;   // |Im(w - kx ux + i(...))| at a resonance pole below which the exit predictor is off
 PSI_HD int point_class(const DistParams& d, double alpha) {
@@ -315,7 +316,9 @@ PSI_HD cx disp_eval_any(const NodeTableView& t, const DistParams& d, cx w, doubl
     case 4: return disp_eval_warp<W, 2, false>(t, d, w, kx, kz, alpha, m_out, nodes_done);
     case 5: return disp_eval_warp<W, 2, true>(t, d, w, kx, kz, alpha, m_out, nodes_done);
     case 6: return disp_eval_warp<W, 3, false>(t, d, w, kx, kz, alpha, m_out, nodes_done);
-    default: return disp_eval_warp<W, 3, true>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    case 7: return disp_eval_warp<W, 3, true>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    case 8: return disp_eval_warp<W, 4, false>(t, d, w, kx, kz, alpha, m_out, nodes_done);
+    default: return disp_eval_warp<W, 4, true>(t, d, w, kx, kz, alpha, m_out, nodes_done);
     }
 }
 

@@ -34,7 +34,8 @@ class PSIDispersion:
         sound_speed_over_eta: gas sound speed / eta (default 1/0.05)
         size_distribution_power: power-law index (default 3.5 = MRN); ignored with size_density
         single_size_flag: single size at tau_max
-        size_density: SizeDensity wrapping PowerBump.sigma0 / PowerBumpTail.sigma0, or None
+        size_density: any SizeDensity(sigma, size_range) -- PowerBump.sigma0 / PowerBumpTail.sigma0 are evaluated
+            analytically on the device, every other callable through a table (_device.SizeDensityTable) -- or None
         tanhsinh_integrator: TanhSinh instance whose tables are uploaded to the device
     """
 
@@ -48,9 +49,9 @@ class PSIDispersion:
         self.ssf = single_size_flag
         self.tanhsinh_integrator = tanhsinh_integrator
         integ = default_integrator() if tanhsinh_integrator is None else tanhsinh_integrator
-        self.desc = _device.describe_size_density(dust_to_gas_ratio, stokes_range, sound_speed_over_eta,
-                                                  size_distribution_power, single_size_flag,
-                                                  size_density)
+        self.desc, self.table = _device.describe_size_density(dust_to_gas_ratio, stokes_range, sound_speed_over_eta,
+                                                              size_distribution_power, single_size_flag,
+                                                              size_density)
         self.size_density = size_density
         if size_density is None:
             q = 3 - size_distribution_power
@@ -58,7 +59,7 @@ class PSIDispersion:
                                             sigma_integral=self.desc.rhod)
         self.poles = list(self.size_density.poles)
         self.ctx = _device.get_context(integ, device)
-        self.dist_id = self.ctx.add_dist(self.desc)
+        self.dist_id = self.ctx.add_dist(self.desc, self.table)
         bg = self.ctx.background(self.dist_id)           # computed on the device (K0)
         j0, j1, denom = bg["j0"], bg["j1"], bg["denom"]
         self.j0, self.j1 = j0, j1

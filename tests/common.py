@@ -59,10 +59,12 @@ def product_kwargs(spec):
 def product_desc(spec):
     from psitools_public_b200 import _device
     kw = product_kwargs(spec)
-    return _device.describe_size_density(kw["dust_to_gas_ratio"], kw["stokes_range"],
-                                         kw["sound_speed_over_eta"],
-                                         kw.get("size_distribution_power", 3.5),
-                                         kw.get("single_size_flag", False), kw.get("size_density"))
+    desc, table = _device.describe_size_density(kw["dust_to_gas_ratio"], kw["stokes_range"],
+                                                kw["sound_speed_over_eta"],
+                                                kw.get("size_distribution_power", 3.5),
+                                                kw.get("single_size_flag", False), kw.get("size_density"))
+    assert table is None          # the fixture distributions are analytic families
+    return desc
 
 
 def det_extended(M7, w, kx, kz, alpha, c, vgx):

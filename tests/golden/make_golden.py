@@ -427,7 +427,45 @@ def sec_multistart():
     dump("multistart.json", dict(stokes_range=[1e-8, 0.1], seed=2, cases=res))
 
 
-SECTIONS = dict(multistart=sec_multistart, modegrid16=sec_modegrid16, nodes=sec_nodes, background=sec_background, disp=sec_disp, contour=sec_contour,
+def table_sigma(a):
+    """A user-style size density no analytic family covers: MRN slope with a log-normal enhancement around a = 0.02
+    and a steeper slope above a = 0.05 (continuous, kink at 0.05 -> SizeDensity.poles = [0.05])."""
+    a = np.asarray(a, dtype=float)
+    base = a**-0.5*(1.0 + 3.0*np.exp(-np.log(a/0.02)**2/0.5))
+    return np.where(a > 0.05, base*(a/0.05)**-1.0, base)
+
+
+def sec_table():
+    """Opaque callable size density (sizedensity.py:25-48 with a user lambda): background, D(omega) at 10 points
+    (inviscid and viscous) and two PSIMode searches, for the tabulated-size-density path of the product."""
+    ns = refshim.load()
+    sd = ns.sizedensity.SizeDensity(table_sigma, [1e-6, 0.2])
+    sd.poles = [0.05]
+    ts = ns.tanhsinh.TanhSinhNoDeepCopy()
+    pd = ns.psi_dispersion.PSIDispersion(2.0, [1e-6, 0.2], size_density=sd, tanhsinh_integrator=ts)
+    rng = np.random.RandomState(77)
+    w = list(rng.uniform(-2, 2, 8) + 1j*rng.uniform(-1, 1, 8)) + [0.35 + 1e-4j, -0.8 + 2e-3j]
+    out = dict(mu=2.0, stokes_range=[1e-6, 0.2], poles=[0.05], rhod=float(sd.rhod), vgx=float(pd.vgx),
+               vgy=float(pd.vgy), cases=[])
+    for kx, kz, alpha in ((8.0, 40.0, 0.0), (60.0, 300.0, 0.0), (8.0, 40.0, 1e-6)):
+        D, M = [], []
+        for x in w:
+            D.append(complex(pd.calculate(x, kx, kz, alpha)))
+            m = pd.matrix_M(x)
+            M.append([m[0, 0], m[0, 1], m[0, 2], m[1, 0], m[1, 1], m[1, 2], m[2, 2]])
+        out["cases"].append(dict(kx=kx, kz=kz, alpha=alpha, w=cl(w), D=cl(D), M=[cl(m) for m in M]))
+    modes = []
+    for kx, kz, seed in ((1.0, 100.0, 0), (30.0, 10.0, 0), (100.0, 1000.0, 0), (3.0, 30.0, 1)):
+        np.random.seed(seed)
+        pm = ns.psi_mode.PSIMode(2.0, [1e-6, 0.2], [-2, 2], [1e-8, 1], size_density=sd, tanhsinh_integrator=ts)
+        roots = pm.calculate(wave_number_x=kx, wave_number_z=kz)
+        modes.append(dict(kx=kx, kz=kz, seed=seed, roots=cl(roots), n_function_call=int(pm.n_function_call)))
+        print(kx, kz, roots, pm.n_function_call, flush=True)
+    out["modes"] = modes
+    dump("table.json", out)
+
+
+SECTIONS = dict(table=sec_table, multistart=sec_multistart, modegrid16=sec_modegrid16, nodes=sec_nodes, background=sec_background, disp=sec_disp, contour=sec_contour,
                 mode=sec_mode, modegrid=sec_modegrid, refine=sec_refine)
 
 if __name__ == "__main__":

@@ -393,8 +393,27 @@ void hs_ctx_destroy(psi_ctx* c) { delete c; }
 void hs_set_exit_rule(psi_ctx* c, int predict) { c->view.predict_exit = predict; }      // 0, 1 or 2 (fast path)
 void hs_set_level_cap(psi_ctx* c, int cap) { c->view.level_cap = cap; }
 
-int hs_dist_add(psi_ctx* c, const psi_dist_desc* desc) {
+static std::vector<std::vector<double>> g_tables;      // tabulated size densities stay alive with the process
+
+int hs_dist_add_table(psi_ctx* c, const psi_dist_desc* desc, const psi_table_desc* tb);
+
+int hs_dist_add(psi_ctx* c, const psi_dist_desc* desc) { return hs_dist_add_table(c, desc, nullptr); }
+
+int hs_dist_add_table(psi_ctx* c, const psi_dist_desc* desc, const psi_table_desc* tb) {
     DistParams d = dist_from_desc(*desc);
+    if (tb) {
+        size_t cells = 0;
+        d.tab_nseg = tb->n_seg;
+        for (int k = 0; k < tb->n_seg; ++k) {
+            d.tab_off[k] = (int)cells; d.tab_n[k] = tb->n_cells[k]; d.tab_log[k] = tb->log_mode[k];
+            d.tab_brk[k] = tb->brk[k];
+            d.tab_invh[k] = tb->n_cells[k] / (tb->brk[k + 1] - tb->brk[k]);
+            cells += (size_t)tb->n_cells[k];
+        }
+        d.tab_brk[tb->n_seg] = tb->brk[tb->n_seg];
+        g_tables.emplace_back(tb->coef, tb->coef + 4 * cells);
+        d.tab = g_tables.back().data();
+    }
     unsigned long long nodes = 0;
     NodeTableView literal = c->view;
     literal.predict_exit = 0;                 // like the product: background integrals use the literal rule

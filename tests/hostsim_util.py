@@ -88,10 +88,13 @@ class HostsimContext(EngineAPI):
     def _last_error(self):
         return self.lib.hs_last_error().decode()
 
-    def add_dist(self, desc):
-        k = desc.key()
+    def add_dist(self, desc, table=None):
+        k = desc.key() + (table.key() if table is not None else b"")
         if k not in self._dists:
-            self._dists[k] = self.lib.hs_dist_add(self.handle, C.byref(desc))
+            if table is None:
+                self._dists[k] = self.lib.hs_dist_add(self.handle, C.byref(desc))
+            else:
+                self._dists[k] = self.lib.hs_dist_add_table(self.handle, C.byref(desc), C.byref(table.struct()))
         return self._dists[k]
 
     def background(self, dist_id):

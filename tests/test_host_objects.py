@@ -70,18 +70,43 @@ def test_descriptor_from_reference_style_objects():
             self.f = lambda x: self.amax*sigma(self.amax*x)/self.rhod
             self.poles = []
 
+        def __call__(self, x):                      # sizedensity.py:46-48
+            return self.f(x)
+
     spec = load("background.json")["bump"]["spec"]
     mine = product_desc(spec)
     pb = RefStyleBump(spec["amin"], spec["aP"], spec["aL"], spec["aR"], spec["bumpfac"])
     sd = RefStyleDensity(pb.sigma0, [spec["amin"], spec["aR"]], mine.rhod)
     sd.poles = list(mine.poles[:mine.n_poles])
-    other = _device.describe_size_density(spec["mu"], [spec["amin"], spec["aR"]], 20.0, 3.5, False, sd)
-    assert other.key() == mine.key()
+    other, table = _device.describe_size_density(spec["mu"], [spec["amin"], spec["aR"]], 20.0, 3.5, False, sd)
+    assert table is None and other.key() == mine.key()
 
 
-def test_opaque_callable_rejected():
-    from psitools_public_b200 import SizeDensity
-    import pytest
+def test_opaque_callable_is_tabulated():
+    """Any callable the reference accepts is served: kind TABLE with the quadrature weight as piecewise cubics that
+    reproduce the callable to 2e-13 (power law: exactly linear in ln w); a PowerBump SUBCLASS with its own sigma0
+    is not mistaken for the stock bump (the analytic route is taken only after a numerical probe)."""
+    from psitools_public_b200 import PowerBump, SizeDensity
     sd = SizeDensity(lambda a: a**-0.5, [1e-8, 1.0])
-    with pytest.raises(NotImplementedError):
-        _device.describe_size_density(1.0, [1e-8, 1.0], 20.0, 3.5, False, sd)
+    d, tab = _device.describe_size_density(1.0, [1e-8, 1.0], 20.0, 3.5, False, sd)
+    assert d.kind == _device.KIND_TABLE and tab is not None and tab.max_rel_err < 2e-13
+    u = np.linspace(np.log(1e-8), 0.0, 1001)[:-1]
+    k = np.minimum((u - tab.brk[0])/(tab.brk[1] - tab.brk[0])*tab.n_cells[0], tab.n_cells[0] - 1).astype(int)
+    t = (u - tab.brk[0])/(tab.brk[1] - tab.brk[0])*tab.n_cells[0] - k
+    c = tab.coef.reshape(-1, 4)[k]
+    got = np.exp(((c[:, 3]*t + c[:, 2])*t + c[:, 1])*t + c[:, 0])
+    np.testing.assert_allclose(got, tab.weight(u), rtol=1e-13)
+
+    class MyBump(PowerBump):
+        def sigma0(self, a):
+            return 2.0*PowerBump.sigma0(self, a)*(1 + a)
+    pb = MyBump(amin=1e-8, aP=0.1, aL=2.0/3.0*0.1, aR=0.156, bumpfac=2.0)
+    sd = SizeDensity(pb.sigma0, [1e-8, 0.156])
+    sd.poles = [pb.get_discontinuity()]
+    d, tab = _device.describe_size_density(10.0, [1e-8, 0.156], 20.0, 3.5, False, sd)
+    assert d.kind == _device.KIND_TABLE and len(tab.n_cells) == 2
+    stock = PowerBump(amin=1e-8, aP=0.1, aL=2.0/3.0*0.1, aR=0.156, bumpfac=2.0)
+    sd2 = SizeDensity(stock.sigma0, [1e-8, 0.156])
+    sd2.poles = [stock.get_discontinuity()]
+    d2, tab2 = _device.describe_size_density(10.0, [1e-8, 0.156], 20.0, 3.5, False, sd2)
+    assert d2.kind == _device.KIND_POWERBUMP and tab2 is None
