@@ -333,6 +333,42 @@ class ClosedPath:
         shifted = self.f_points + 1.0e-30j
         return 0.5*np.sum(np.angle(np.roll(shifted, -1)/shifted))/np.pi
 
+    @staticmethod
+    def interweave(a, b):
+        """a[0], b[0], a[1], b[1], ... (reference complex_roots.py:540-546)."""
+        a, b = np.asarray(a), np.asarray(b)
+        out = np.empty(a.size + b.size, dtype=np.result_type(a, b))
+        out[0::2], out[1::2] = a, b
+        return out
+
+    def refine(self):
+        """Double the number of points: the mid-point of every edge (point -> next point) is inserted behind its
+        first end (reference complex_roots.py:548-554); one batched evaluation of f."""
+        mids = 0.5*(self.points + np.roll(self.points, -1))
+        self.points = self.interweave(self.points, mids)
+        self.f_points = self.interweave(self.f_points, np.asarray(self.func(mids)))
+
+    def refine_select(self, tol=0.1, max_step=0.1):
+        """ONE refinement pass of count_roots (reference complex_roots.py:556-595): bisect the edges across which
+        the argument of f jumps by more than ``tol``, that are more than twice as long as a neighbour or longer
+        than ``max_step`` (never below 1e-8).  Returns the number of points added; ValueError on non-finite f."""
+        st = {}
+        mach = contour_machine(self.points, 1, tol, max_step, st)
+        next(mach)
+        try:
+            req = mach.send(np.asarray(self.f_points, dtype=complex))      # the pass asks for its mid-points ...
+        except StopIteration:
+            return 0                                                       # ... or finds nothing to split
+        except RuntimeError:                                               # winding sum not an integer: not this
+            return 0                                                       # method's business
+        n_add = len(req)
+        try:
+            mach.send(np.asarray(self.func(req)))
+        except RuntimeError:                                               # "maximum number of iterations": the one
+            pass                                                           # pass is done
+        self.points, self.f_points = st["points"], st["f_points"]
+        return n_add
+
     def count_roots(self, verbose=False, max_iter=100, tol=0.1, max_step=0.1):
         """Number of roots inside the contour.  RuntimeError when the winding sum does not settle on
         an integer or max_iter passes are exhausted; ValueError on non-finite function values."""

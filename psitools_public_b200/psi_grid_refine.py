@@ -511,13 +511,21 @@ class PSIGridRefiner:
             top = h5f.create_group(self.batchname)
             top.attrs['run_walltime'] = time.time() - self.wall_start
             for i, g in enumerate(self.grids):
-                grp = h5f.create_group(self.batchname + '/' + str(i))
-                grp.attrs['stokes_range'] = init['stokes_range']
-                grp.attrs['dust_to_gas_ratio'] = init['dust_to_gas_ratio']
-                if 'viscous_alpha' in self.baseargs['calculate']:
-                    grp.attrs['viscous_alpha'] = self.baseargs['calculate']['viscous_alpha']
-                grp.attrs['real_range'] = init['real_range']
-                grp.attrs['imag_range'] = init['imag_range']
-                for name, arr in self.grid_arrays(g).items():
-                    grp.create_dataset(name, data=arr)
+                self.write_grid(i, g, h5f)
         return self.datafile_hdf5
+
+    def write_grid(self, igrid, grid, h5f):
+        """One grid into an open HDF5 file (reference psi_grid_refine.py:347-386): group ``batchname/igrid`` with the
+        run attributes and the datasets Kxgrid, Kzgrid, root_real, root_imag (depth = largest root multiplicity)
+        and error (= number of roots per pixel, -1 where no run exists)."""
+        init = self.baseargs['__init__']
+        grp = h5f.create_group(self.batchname + '/' + str(igrid))
+        grp.attrs['stokes_range'] = init['stokes_range']
+        grp.attrs['dust_to_gas_ratio'] = init['dust_to_gas_ratio']
+        if 'viscous_alpha' in self.baseargs['calculate']:
+            grp.attrs['viscous_alpha'] = self.baseargs['calculate']['viscous_alpha']
+        grp.attrs['real_range'] = init['real_range']
+        grp.attrs['imag_range'] = init['imag_range']
+        arrays = self.grid_arrays(grid)
+        for name in ('Kxgrid', 'Kzgrid', 'root_real', 'root_imag', 'error'):
+            grp.create_dataset(name, data=arrays[name])

@@ -311,6 +311,8 @@ class PSIMode:
                   count_roots=False):
         """Complex mode frequencies at (Kx, Kz) and viscosity parameter viscous_alpha."""
         self.disp = lambda z: self.dispersion(z, wave_number_x, wave_number_z, viscous_alpha)
+        pd = self.psi_dispersion                     # the reference's PSIDispersion.calculate leaves these behind
+        pd.kx, pd.kz, pd.nu = wave_number_x, wave_number_z, viscous_alpha*pd.c**2
         if self._device_search_ok(guess_roots, count_roots):
             try:
                 return self._calculate_on_device(wave_number_x, wave_number_z, viscous_alpha, guess_roots)
@@ -347,6 +349,39 @@ class PSIMode:
         run_lockstep(self.psi_dispersion.ctx, [job])
         self.n_function_call += trace.n_function_call
         return job.result
+
+    def add_extra_domain(self, extra_domain_size=[0.1, 0.1], centre=0.0):
+        """n_sample more random samples in a box around ``centre`` (shifted to lie inside the search domain), appended
+        to z_sample / f_sample; their D values are ONE K1 launch (reference psi_mode.py:354-397).  Needs a preceding
+        calculate call (or ``self.disp``) like the reference."""
+        centre = _boxed_centre(self.domain, complex(centre), extra_domain_size)
+        self.log_print('Adding zoom domain around {}'.format(centre))
+        box = cr.Rectangle([centre.real - 0.5*extra_domain_size[0], centre.real + 0.5*extra_domain_size[0]],
+                           [centre.imag - 0.5*extra_domain_size[1], centre.imag + 0.5*extra_domain_size[1]])
+        z_new = box.generate_random_sample_points(self.n_sample)
+        f_new = self.disp(z_new)
+        self.z_sample = np.concatenate((self.z_sample, z_new))
+        self.f_sample = np.concatenate((self.f_sample, f_new))
+        self.n_function_call += self.n_sample
+
+    def find_root(self, w0, max_iter=1000, select_inside_domain=True, initial_iterations=5):
+        """Secant polish of one start value or of an array of them on the exact dispersion relation of the last
+        calculate call (reference psi_mode.py:411-491): ``initial_iterations`` first, then up to ``max_iter`` from where
+        that stopped if it has not run away; failures and (with ``select_inside_domain``) roots outside the search
+        rectangle give -1j.  The step tolerance min(1.48e-8, 1e-5*min|Im w0|) runs over the WHOLE start array, as in
+        the reference (find_dispersion_roots calls this with one scalar at a time).  Same shape out as in."""
+        w0 = np.asarray(w0, dtype=complex)
+        trace = ModeTrace()
+        self._sync_cfg()
+        pd = self.psi_dispersion
+        job = Job(polish_machine(self.cfg, w0, max_iter, trace, self.log_print if self.verbose_flag else (lambda *a: None),
+                                 initial_iterations, select_inside_domain, per_start=False, keep_all=True),
+                  pd.dist_id, pd.kx, pd.kz, pd.nu/pd.c**2)
+        run_lockstep(pd.ctx, [job])
+        self.n_function_call += trace.n_function_call
+        self.max_convergence_iterations = max(self.max_convergence_iterations, trace.max_convergence_iterations)
+        out = np.asarray(job.result, dtype=complex)
+        return np.squeeze(out) if w0.ndim == 0 else out.reshape(w0.shape)
 
     def find_minimum(self):
         """Location of the minimum of |rational approximation| in the domain (reference

@@ -465,7 +465,60 @@ def sec_table():
     dump("table.json", out)
 
 
-SECTIONS = dict(table=sec_table, multistart=sec_multistart, modegrid16=sec_modegrid16, nodes=sec_nodes, background=sec_background, disp=sec_disp, contour=sec_contour,
+def sec_boundary():
+    """Public methods of the boundary classes beyond calculate/count_roots: PSIDispersion.matrix_P
+    and the stopping-time matrices, average/int_j, PSIMode.find_root (scalar and array) and add_extra_domain,
+    ClosedPath.refine / refine_select / interweave -- values from the unmodified reference."""
+    ns = refshim.load()
+    ts = ns.tanhsinh.TanhSinhNoDeepCopy()
+    pd = ns.psi_dispersion.PSIDispersion(3.0, [1e-8, 1.0], tanhsinh_integrator=ts)
+    w, kx, kz, alpha = 0.3 + 0.2j, 10.0, 100.0, 1e-6
+    out = dict(w=cl([w])[0], kx=kx, kz=kz, alpha=alpha)
+    out["D"] = cl([complex(pd.calculate(w, kx, kz, alpha))])[0]
+    out["P"] = [cl(row) for row in pd.matrix_P(w)]
+    taus = [1e-6, 3e-3, 0.2, 0.9]
+    out["taus"] = taus
+    A = pd.matrix_inverse_A(w)
+    AD = pd.matrix_AD(A, w)
+    VAD = pd.matrix_VAD(AD, w)
+    W = pd.matrix_W(w)
+    ev = lambda mat: [[cl([complex(np.asarray(mat[i][j](np.asarray(taus)) + 0*np.asarray(taus))[k]) for k in range(4)])
+                       for j in range(3)] for i in range(3)]
+    out["Ainv"], out["AD"], out["VAD"], out["W"] = ev(A), ev(AD), ev(VAD), ev(W)
+    out["int_j"] = [float(np.real(pd.int_j(0))), float(np.real(pd.int_j(1)))]
+    out["average_tau2"] = cl([complex(pd.average(lambda x: x**2/(1 + 1j*x)))])[0]
+    # PSIMode: calculate, then find_root on a scalar and on an array, then add_extra_domain
+    np.random.seed(3)
+    pm = ns.psi_mode.PSIMode(3.0, [1e-8, 1.0], [-2, 2], [1e-8, 1], tanhsinh_integrator=ts)
+    roots = pm.calculate(wave_number_x=0.1, wave_number_z=10.0)
+    out["mode_roots"] = cl(roots)
+    n0 = pm.n_function_call
+    r1 = pm.find_root(roots[0]*(1 + 1e-3), max_iter=50)
+    n1 = pm.n_function_call
+    starts = np.array([roots[0]*(1 - 2e-3), 0.5 + 0.3j, roots[0] + 1e-4])
+    r2 = pm.find_root(starts.copy(), max_iter=30)
+    n2 = pm.n_function_call
+    r3 = pm.find_root(np.array([1.9 + 0.9j]), max_iter=8, select_inside_domain=False)
+    out["find_root"] = dict(scalar_start=cl([roots[0]*(1 + 1e-3)])[0], scalar=cl([complex(r1)])[0], calls_scalar=n1 - n0,
+                            array_start=cl(starts), array=cl(r2), calls_array=n2 - n1,
+                            outside_start=cl([1.9 + 0.9j]), outside=cl(r3), calls_outside=pm.n_function_call - n2)
+    n3, m3 = pm.n_function_call, len(pm.z_sample)
+    pm.add_extra_domain(extra_domain_size=[0.05, 0.02], centre=roots[0])
+    out["extra_domain"] = dict(z_new=cl(pm.z_sample[m3:]), f_new=cl(pm.f_sample[m3:]), calls=pm.n_function_call - n3)
+    # ClosedPath
+    f = lambda z: pd.calculate(z, 0.1, 10.0)
+    z_list = [-2.0 + 2e-7j, 2.0 + 2e-7j, 2.0 + 2.0j, -2.0 + 2.0j]
+    cp = ns.complex_roots.ClosedPath(f, z_list)
+    added = [cp.refine_select(tol=0.1, max_step=0.1) for _ in range(3)]
+    out["closed_path"] = dict(z_list=cl(z_list), added=added, points=cl(cp.points), f_points=cl(cp.f_points))
+    cp2 = ns.complex_roots.ClosedPath(f, z_list)
+    cp2.refine()
+    out["closed_path"]["refined_points"] = cl(cp2.points)
+    out["closed_path"]["interweave"] = [float(v) for v in cp2.interweave(np.array([1.0, 2.0, 3.0]), np.array([10.0, 20.0, 30.0]))]
+    dump("boundary.json", out)
+
+
+SECTIONS = dict(boundary=sec_boundary, table=sec_table, multistart=sec_multistart, modegrid16=sec_modegrid16, nodes=sec_nodes, background=sec_background, disp=sec_disp, contour=sec_contour,
                 mode=sec_mode, modegrid=sec_modegrid, refine=sec_refine)
 
 if __name__ == "__main__":
