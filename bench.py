@@ -304,7 +304,8 @@ def run_config4(barrier, world):
         out = inner(*a, **k)
         sched["scheduler"] = sched.get("scheduler", 0.0) + time.perf_counter() - t
         st = gr.ms.last_stats
-        for key in ("prep_seconds", "batch_seconds", "exchange_seconds"):
+        for key in ("prep_seconds", "batch_seconds", "exchange_seconds", "wait_seconds", "lib_setup_seconds",
+                    "lib_call_seconds"):
             sched[key] = sched.get(key, 0.0) + (st.get(key) or 0.0)
         for key, v in (st.get("stage_s") or {}).items():
             sched["dev_" + key] = sched.get("dev_" + key, 0.0) + v

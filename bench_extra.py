@@ -62,10 +62,13 @@ def refine(nbase, fills, reruns):
         out = inner(*a, **k)
         sched["s"] += time.perf_counter() - t
         st = gr.ms.last_stats
-        for key in ("prep_seconds", "batch_seconds", "exchange_seconds"):
+        for key in ("prep_seconds", "batch_seconds", "exchange_seconds", "wait_seconds", "lib_setup_seconds",
+                    "lib_call_seconds"):
             sched[key] = sched.get(key, 0.0) + (st.get(key) or 0.0)
         for key, v in (st.get("stage_s") or {}).items():
             sched["dev_" + key] = sched.get("dev_" + key, 0.0) + v
+        sched["redone"] = sched.get("redone", 0) + (st.get("redone_for_root_slots") or 0)
+        sched["max_roots"] = max(sched.get("max_roots", 0), st.get("max_roots") or 0)
         return out
     gr.ms.run_arrays = timed
     t0 = time.perf_counter()

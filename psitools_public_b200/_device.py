@@ -419,9 +419,26 @@ class EngineAPI:
                     bad = int(np.flatnonzero(st != 0)[0])
                     raise PsiError("device root search failed for item %d (Kx=%g, Kz=%g): status %d"
                                    % (bad, kx[bad], kz[bad], st[bad]))
-            if n and nr.max() > max_roots:           # rare: more roots than slots, redo with room
-                max_roots = int(nr.max())
-                continue
+            if n and nr.max() > max_roots:           # rare: more roots than slots -> redo JUST those searches with room
+                over = np.flatnonzero(nr > max_roots)
+                if len(over) == n:
+                    max_roots = int(nr.max())
+                    continue
+                g_over = None
+                if len(flat):
+                    length = (goff[1:] - goff[:-1])[over].astype(np.int64)
+                    off = np.zeros(len(over) + 1, dtype=np.int64)
+                    np.cumsum(length, out=off[1:])
+                    take = np.repeat(goff[:-1][over].astype(np.int64) - off[:-1], length) + np.arange(off[-1])
+                    g_over = (np.asarray(gz)[take], off)
+                (r2, n2), c2, _ = self._mode_batch(dist[over], kx[over], kz[over], alpha[over], domain[over],
+                                                   ip[over, 0], ip[over, 1], ip[over, 2], dp[over, 0], dp[over, 1],
+                                                   seeds[over], g_over, int(nr.max()), device_aaa, True)
+                wide = np.zeros((n, r2.shape[1]), dtype=np.complex128)
+                wide[:, :max_roots] = roots
+                wide[over] = r2
+                roots, max_roots = wide, r2.shape[1]
+                nr[over], nc[over] = n2, c2
             break
         if np.any(st == 1):
             bad = int(np.flatnonzero(st == 1)[0])
@@ -467,6 +484,7 @@ class EngineAPI:
                                                        _ptr(goff), _ptr(gz), C.c_int(max_roots), C.c_int(rows),
                                                        C.byref(ptr), _ptr(stats)), "psi_mode_batch_device_rec")
         st = dict(passes=1, evals=int(stats[1]), launches=int(stats[0]), logic_s=0.0, eval_s=0.0, polish_evals=0,
+                  setup_s=stats[3]*1e-6, call_s=stats[4]*1e-6,
                   stage_s=dict(zip(("sample", "k1", "analyze", "k3", "decide"), (stats[8:13]*1e-6).tolist())))
         return DeviceRecords(ptr.value, rows, 4 + 2*max_roots, n, max_roots), st
 

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -1167,6 +1168,11 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
                              const int* guess_off, const double* guesses, int cap, int max_roots,
                              double* roots, int* n_roots, int* n_calls, int* status, long long* stats,
                              const PsiModeExtra* extra) {
+    const auto wall0 = std::chrono::steady_clock::now();
+    auto wall_us = [&]() {
+        return (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - wall0).count();
+    };
+    long long us_setup = 0;
     if (n_items == 0) {
         if (extra && extra->rec_dev) {                      // a rank without work still contributes (zero) records
             CK(cudaSetDevice(c->device));
@@ -1263,6 +1269,8 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
             if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) stage_us[k] += 1e3 * ms;
         }
     };
+    CK(cudaStreamSynchronize(st));
+    us_setup = wall_us();                  // allocations + upload of the inputs
     for (int round = 0; round <= max_zoom; ++round) {
         CK(cudaMemsetAsync(m.counters, 0, 2 * sizeof(unsigned long long), st));
         CK(cudaEventRecord(ev[0], st));
@@ -1358,6 +1366,7 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     for (auto& e : ev) cudaEventDestroy(e);
     if (stats) {
         stats[0] = launches; stats[1] = evals + (long long)cnt2[1]; stats[2] = (long long)cnt2[0];
+        stats[3] = us_setup; stats[4] = wall_us();                             // host wall clock: setup, whole call
         for (int k = 0; k < 5; ++k) stats[8 + k] = (long long)stage_us[k];     // stats has 16 slots
     }
     return PSI_OK;

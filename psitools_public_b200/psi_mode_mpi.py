@@ -217,9 +217,11 @@ class MpiScheduler:
         n = len(kx)
         lo, step = _dist.rank(), _dist.world_size()
         mine = np.arange(lo, n, step)
-        kx, kz = np.asarray(kx, dtype=float)[mine], np.asarray(kz, dtype=float)[mine]
+        kx_in, kz_in, seeds_in = np.asarray(kx, dtype=float), np.asarray(kz, dtype=float), seeds
+        al_in = np.broadcast_to(np.asarray(alpha, dtype=float), (n,))
+        kx, kz = kx_in[mine], kz_in[mine]
         seeds = np.broadcast_to(np.asarray(seeds, dtype=np.int64), (n,))[mine]
-        al = np.broadcast_to(np.asarray(alpha, dtype=float), (n,))[mine]
+        al = al_in[mine]
         gl = None
         if guesses is not None and len(guesses[0]):
             flat, off = np.asarray(guesses[0], dtype=np.complex128), np.asarray(guesses[1], dtype=np.int64)
@@ -237,9 +239,11 @@ class MpiScheduler:
         n_guess_max = int(np.max(gl[1][1:] - gl[1][:-1])) if gl is not None and len(mine) else 0
         cap = cfg.n_sample*(1 + n_guess_max + 4*cfg.max_zoom_level)
         fits = cap <= 512 and 60*cap*max(len(mine), 1) <= int(os.environ.get("PSI_B200_BATCH_BYTES", str(48 << 30)))
-        if device and _dist.nccl_active() and _dist.all_reduce_max(0 if fits else 1) == 0:
+        use_records = device and _dist.nccl_active() and _dist.all_reduce_max(0 if fits else 1) == 0
+        t1b = time.time()                        # (the all-reduce doubles as the point where ranks wait for each other)
+        if use_records:
             # results stay on the device: one ncclAllGather of packed records out of the library's buffer
-            rows, max_roots = (n + step - 1)//step, 8
+            rows, max_roots, redone = (n + step - 1)//step, 8, 0
             while True:
                 rec, st = ctx.mode_batch_records(dist_ids, kx, kz, al, dom, cfg.n_sample, cfg.max_zoom_level,
                                                  cfg.max_secant_iterations, cfg.tol, cfg.clean_tol, seeds, gl,
@@ -248,16 +252,41 @@ class MpiScheduler:
                 table, top, worst = _dist.all_gather_device_records(rec, to_host=True)
                 if worst not in (0, 4):
                     raise RuntimeError("device root search failed on some rank (status %d)" % worst)
-                if top <= max_roots:
-                    break
-                max_roots = top
+                break
             from ._device import DeviceRecords
             roots_all, cnt_all, _, calls = DeviceRecords.unpack(table[:n], max_roots)
+            over = np.flatnonzero(cnt_all > max_roots)
+            if len(over):
+                # rare: a search found more roots than the records have slots.  Every rank holds the whole table, so
+                # every rank redoes just those searches itself (deterministic: identical everywhere), no second exchange
+                redone = len(over)
+                seeds_all = np.broadcast_to(np.asarray(seeds_in, dtype=np.int64), (n,))
+                g_over = None
+                if guesses is not None and len(guesses[0]):
+                    flat, off = np.asarray(guesses[0], dtype=np.complex128), np.asarray(guesses[1], dtype=np.int64)
+                    length = (off[1:] - off[:-1])[over]
+                    o2 = np.zeros(len(over) + 1, dtype=np.int64)
+                    np.cumsum(length, out=o2[1:])
+                    g_over = (flat[np.repeat(off[:-1][over] - o2[:-1], length) + np.arange(o2[-1])], o2)
+                (r2, n2), _, _ = ctx.mode_batch(np.full(len(over), pm.psi_dispersion.dist_id, dtype=np.int32),
+                                                kx_in[over], kz_in[over], al_in[over],
+                                                np.tile(np.array([[pm.domain.xmin, pm.domain.xmax, pm.domain.ymin,
+                                                                   pm.domain.ymax]], dtype=float), (len(over), 1)),
+                                                cfg.n_sample, cfg.max_zoom_level, cfg.max_secant_iterations, cfg.tol,
+                                                cfg.clean_tol, seeds_all[over], g_over, max_roots=top,
+                                                device_aaa=True, dense=True)
+                wide = np.zeros((n, r2.shape[1]), dtype=np.complex128)
+                wide[:, :roots_all.shape[1]] = roots_all
+                wide[over] = r2
+                roots_all = wide
+                cnt_all[over] = n2
             width = max(1, int(cnt_all.max()) if n else 1)
             self.last_stats = dict(items=len(mine), passes=1, function_calls=int(calls[lo::step].sum()),
                                    evals=st.get("evals", 0), seconds=time.time() - t0, prep_seconds=t1 - t0,
-                                   batch_seconds=t2 - t1, launches=st.get("launches"), stage_s=st.get("stage_s"),
-                                   engine=self.engine, exchange_seconds=time.time() - t2,
+                                   batch_seconds=t2 - t1b, wait_seconds=t1b - t1, launches=st.get("launches"),
+                                   lib_setup_seconds=st.get("setup_s"), lib_call_seconds=st.get("call_s"),
+                                   redone_for_root_slots=redone, max_roots=max_roots,
+                                   stage_s=st.get("stage_s"), engine=self.engine, exchange_seconds=time.time() - t2,
                                    exchange="nccl all_gather_into_tensor (device records)")
             return np.ascontiguousarray(roots_all[:, :width]), cnt_all
         if len(mine):

@@ -236,6 +236,33 @@ def test_mode_batch_chunking_is_invisible(backend, monkeypatch):
     assert s0["evals"] == s1["evals"]
 
 
+def test_root_slot_overflow_redoes_only_those_searches(backend):
+    """More roots than result slots (a refinement pixel whose guesses lead to the same root returns it several
+    times): only the overflowing searches are run again with room, the answer equals the one obtained with enough
+    slots from the start.  The searches are those of the tiny refinement campaign of test_grid_refine.py."""
+    from test_grid_refine import make_refiner
+    gr, log = make_refiner("device")
+    if backend == "gpu":                     # a campaign large enough to contain such searches (35 x 35 map)
+        gr.nbase, gr.krange, gr.reruns = (16, 16), (-1.0, 3.0), 1
+    gr.run_basegrid()
+    gr.fill_in_grid()
+    items = [(kx, kz, list(g)) for batch in log[1:] for kx, kz, g, _ in batch]
+    if max(len(r) for batch in log[1:] for _, _, _, r in batch) < 2:
+        assert backend != "gpu"
+        pytest.skip("no search with two roots in the tiny CPU campaign")
+    pm = gr.ms._cache.get(gr._shared_init(0))
+    ctx, did = pm.psi_dispersion.ctx, pm.psi_dispersion.dist_id
+    n = len(items)
+    args = ([did]*n, [i[0] for i in items], [i[1] for i in items], np.zeros(n), [[-2, 2, 1e-7, 1.0]]*n, 20, 0,
+            100, 1e-13, 1e-4, [2]*n, [i[2] for i in items])
+    (r8, n8), c8, _ = ctx.mode_batch(*args, max_roots=8, device_aaa=True, dense=True)
+    (r1, n1), c1, _ = ctx.mode_batch(*args, max_roots=1, device_aaa=True, dense=True)
+    assert n8.max() >= 2 and r1.shape[1] == n8.max()
+    assert np.array_equal(n1, n8) and np.array_equal(c1, c8)
+    for i in range(n):
+        assert np.array_equal(r1[i, :n1[i]], r8[i, :n8[i]]), i
+
+
 @pytest.mark.gpu
 def test_k3_block_mode_equals_warp_mode(built, monkeypatch):
     """K3 polishes a launch with few root searches with one 384-thread block per search (CtaCuda policy)
