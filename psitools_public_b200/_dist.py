@@ -133,6 +133,9 @@ def all_gather_ragged(cnt, flat):
     return cnts, flats
 
 
+_NCCL_CACHE = {}
+
+
 def all_reduce_max(value):
     """Maximum of a small non-negative integer over all ranks (error / fallback flags ahead of a collective)."""
     td = _td()
@@ -147,15 +150,22 @@ def all_reduce_max(value):
 def nccl_active():
     """True when results can be exchanged device to device (torch.distributed with the NCCL backend, > 1 rank)."""
     td = _td()
-    return td is not None and td.get_world_size() > 1 and td.get_backend() == "nccl"
+    if td is None:
+        return False
+    key = id(td.group.WORLD)
+    if _NCCL_CACHE.get("key") != key:                       # (get_backend costs milliseconds: asked once per group)
+        _NCCL_CACHE.update(key=key, on=td.get_world_size() > 1 and td.get_backend() == "nccl")
+    return _NCCL_CACHE["on"]
 
 
-def all_gather_device_records(rec, to_host=True):
+def all_gather_device_records(rec, n_items, to_host=True):
     """ONE ncclAllGather of fixed-slot result records straight out of the library's device buffer (``rec``: a
-    _device.DeviceRecords with the same number of rows on every rank).  Returns (table, max_n_roots, max_status):
-    ``table`` is the host copy with rows in GLOBAL item order (rank q owns items q::world, so row j of rank q is
-    item q + j*world) or None when ``to_host`` is false; the two maxima are reduced on the device so that every
-    rank can act on them (truncated root lists, failed searches) without pulling the table."""
+    _device.DeviceRecords with the same number of rows on every rank; rank q owns items q::world, so row j of rank
+    q is item q + j*world).  What comes to the host is compacted on the device first -- on a growth-rate map most
+    searches return nothing: the root count of every item (int32) and the root slots of the items that have any.
+    Returns a dict: ``cnt`` (n_items,), ``idx`` (indices of the items with roots), ``roots`` (len(idx), max_roots)
+    complex -- all three None when ``to_host`` is false -- and, reduced on the device so that EVERY rank can act on
+    them, ``top`` (largest root count), ``worst`` (largest status) and ``calls`` (sum of n_function_call)."""
     import torch
     td = _td()
     world = td.get_world_size()
@@ -163,11 +173,16 @@ def all_gather_device_records(rec, to_host=True):
     mine = torch.as_tensor(rec, device=dev)                       # zero-copy view of the library's buffer
     out = torch.empty((world, rec.rows, rec.width), dtype=torch.float64, device=dev)
     td.all_gather_into_tensor(out.view(-1), mine.reshape(-1))
-    head = out[:, :, :2].amax(dim=(0, 1)).cpu()                   # [max n_roots, max status]
-    table = None
+    head = torch.stack((out[:, :, 0].max(), out[:, :, 1].max(), out[:, :, 2].sum())).cpu()
+    res = dict(top=int(head[0]), worst=int(head[1]), calls=int(head[2]), cnt=None, idx=None, roots=None)
     if to_host:
-        table = out.permute(1, 0, 2).reshape(world*rec.rows, rec.width).cpu().numpy()
-    return table, int(head[0]), int(head[1])
+        table = out.permute(1, 0, 2).reshape(world*rec.rows, rec.width)[:n_items]      # global item order
+        cnt = table[:, 0].to(torch.int32)
+        has = cnt > 0
+        res["cnt"] = cnt.cpu().numpy().astype(np.int64)
+        res["idx"] = np.flatnonzero(res["cnt"] > 0)
+        res["roots"] = np.ascontiguousarray(table[has][:, 4:].contiguous().cpu().numpy()).view(np.complex128)
+    return res
 
 
 def barrier():

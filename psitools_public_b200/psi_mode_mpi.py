@@ -243,18 +243,19 @@ class MpiScheduler:
         t1b = time.time()                        # (the all-reduce doubles as the point where ranks wait for each other)
         if use_records:
             # results stay on the device: one ncclAllGather of packed records out of the library's buffer
-            rows, max_roots, redone = (n + step - 1)//step, 8, 0
+            rows, max_roots, redone = (n + step - 1)//step, 4, 0
             while True:
                 rec, st = ctx.mode_batch_records(dist_ids, kx, kz, al, dom, cfg.n_sample, cfg.max_zoom_level,
                                                  cfg.max_secant_iterations, cfg.tol, cfg.clean_tol, seeds, gl,
                                                  max_roots=max_roots, rec_rows=rows)
                 t2 = time.time()
-                table, top, worst = _dist.all_gather_device_records(rec, to_host=True)
-                if worst not in (0, 4):
-                    raise RuntimeError("device root search failed on some rank (status %d)" % worst)
+                got = _dist.all_gather_device_records(rec, n, to_host=True)
+                if got["worst"] not in (0, 4):
+                    raise RuntimeError("device root search failed on some rank (status %d)" % got["worst"])
                 break
-            from ._device import DeviceRecords
-            roots_all, cnt_all, _, calls = DeviceRecords.unpack(table[:n], max_roots)
+            top, cnt_all = got["top"], got["cnt"]
+            roots_all = np.zeros((n, max_roots), dtype=np.complex128)
+            roots_all[got["idx"]] = got["roots"]
             over = np.flatnonzero(cnt_all > max_roots)
             if len(over):
                 # rare: a search found more roots than the records have slots.  Every rank holds the whole table, so
@@ -281,7 +282,7 @@ class MpiScheduler:
                 roots_all = wide
                 cnt_all[over] = n2
             width = max(1, int(cnt_all.max()) if n else 1)
-            self.last_stats = dict(items=len(mine), passes=1, function_calls=int(calls[lo::step].sum()),
+            self.last_stats = dict(items=len(mine), passes=1, function_calls=got["calls"],
                                    evals=st.get("evals", 0), seconds=time.time() - t0, prep_seconds=t1 - t0,
                                    batch_seconds=t2 - t1b, wait_seconds=t1b - t1, launches=st.get("launches"),
                                    lib_setup_seconds=st.get("setup_s"), lib_call_seconds=st.get("call_s"),
@@ -347,22 +348,21 @@ class MpiScheduler:
             if flag == 1:
                 return None
             (rec, _), st = done
-            table, top, worst = _dist.all_gather_device_records(rec, to_host=to_host)
-            if worst not in (0, 4):
-                raise RuntimeError("device root search failed on some rank (status %d)" % worst)
-            if top > max_roots:                   # rare: more roots than slots somewhere -> every rank redoes it
-                max_roots = top
+            got = _dist.all_gather_device_records(rec, n, to_host=to_host)
+            if got["worst"] not in (0, 4):
+                raise RuntimeError("device root search failed on some rank (status %d)" % got["worst"])
+            if got["top"] > max_roots:            # rare: more roots than slots somewhere -> every rank redoes it
+                max_roots = got["top"]
                 continue
             break
-        self.last_stats = dict(items=len(mine), passes=st.get("passes", 0), function_calls=None,
+        self.last_stats = dict(items=len(mine), passes=st.get("passes", 0), function_calls=got["calls"],
                                evals=st.get("evals", 0), launches=st.get("launches"), stage_s=st.get("stage_s"),
                                engine=self.engine, exchange="nccl all_gather_into_tensor (device records)")
-        if table is None:
+        if got["cnt"] is None:
             return ()
-        from ._device import DeviceRecords
-        roots, cnt, _, calls = DeviceRecords.unpack(table[:n], max_roots)
-        self.last_stats["function_calls"] = int(calls.sum())
-        return roots, cnt
+        roots = np.zeros((n, max_roots), dtype=np.complex128)
+        roots[got["idx"]] = got["roots"]
+        return roots, got["cnt"]
 
     @staticmethod
     def _as_dict(n, mat, cnt):
