@@ -111,7 +111,9 @@ int psi_disp_eval_host(psi_ctx* ctx, long long n, int broadcast, const int* dist
 /* Same with device pointers; node_evals_dev (optional) is a device counter that is INCREMENTED.
  * K1 is compiled once per work class (size-density family x viscous/inviscid, psi_point_class);
  * class_mask has bit c set when the batch may contain points of class c (0 = all classes, i.e. one
- * launch per class, each skipping foreign points). */
+ * launch per class, each skipping foreign points).  stream: a cudaStream_t (NULL = the context's own); the
+ * launches of ONE context share its work queue and counters, so calls given different streams are chained
+ * (each waits for the context's previous K1 launch): use one context per stream for concurrent batches. */
 int psi_disp_eval_dev(psi_ctx* ctx, long long n, int broadcast, const int* dist, const double* kx,
                       const double* kz, const double* alpha, const double* w, double* D, double* M,
                       unsigned long long* node_evals_dev, unsigned class_mask, void* stream);

@@ -227,6 +227,11 @@ struct psi_ctx {
     long long* d_hard = nullptr;           // indices of the points the fast path handed to the warp kernel
     size_t hard_cap = 0;
     std::vector<double*> d_tables;         // tabulated size densities (psi_dist_add_table)
+    // K1 launches of one context share its work-queue head, hard-point list and counters: launches given
+    // DIFFERENT streams (psi_disp_eval_dev) are therefore chained through this event -- a launch starts only after
+    // the context's previous one has finished, whatever stream that ran on
+    cudaEvent_t ev_k1 = nullptr;
+    bool ev_k1_recorded = false;
 };
 
 extern "C" { static int ensure_stage(psi_ctx* c, size_t bytes); }
@@ -799,6 +804,7 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
     CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_k1, cudaEventDisableTiming));
     c->n_nodes = n_nodes; c->max_m = max_level; c->eps = eps;
     {
         const char* rule = getenv("PSI_B200_EXIT_RULE");          // "reference" = the literal rule of tanhsinh.py
@@ -847,6 +853,7 @@ void psi_ctx_destroy(psi_ctx* c) {
     cudaFree(c->d_stage); cudaFree(c->d_contour_scratch); cudaFree(c->d_mode_scratch); cudaFree(c->d_hard);
     for (double* t : c->d_tables) cudaFree(t);
     cudaStreamDestroy(c->stream);
+    if (c->ev_k1) cudaEventDestroy(c->ev_k1);
     delete c;
 }
 
@@ -945,6 +952,7 @@ static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* d
     int grid = (int)(want < c->sm_count ? want : c->sm_count);
     NodeTableView t = table_view(c);
     if ((class_mask & 0x3ffu) == 0) class_mask = 0x3ffu;
+    if (c->ev_k1_recorded) CK(cudaStreamWaitEvent(st, c->ev_k1, 0));
     // fast path: thread per point first, the warp kernel only for what that leaves (needs the predictor rule,
     // no M output, and enough points to fill the machine with one thread each)
     const bool fast = c->predict_exit != 0 && c->fast_cap > 0 && M == nullptr && n >= 4096;
@@ -981,6 +989,8 @@ static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* d
         c->launches++;
         CK(cudaGetLastError());
     }
+    CK(cudaEventRecord(c->ev_k1, st));
+    c->ev_k1_recorded = true;
     return PSI_OK;
 }
 
@@ -1260,8 +1270,12 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     int launches = 0;
     long long evals = 0;
     // stage timing (sample, K1, analysis, K3, decide) with CUDA events on the context's stream
-    cudaEvent_t ev[6];
-    for (auto& e : ev) CK(cudaEventCreate(&e));
+    struct Events {                        // destroyed on every return path
+        cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+    } events;
+    cudaEvent_t* ev = events.e;
+    for (int k = 0; k < 6; ++k) CK(cudaEventCreate(&ev[k]));
     double stage_us[5] = {0, 0, 0, 0, 0};
     auto collect = [&](int upto) {
         for (int k = 0; k < upto; ++k) {
@@ -1363,7 +1377,6 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     }
     CK(cudaMemcpyAsync(cnt2, c->d_counter + 4, sizeof(cnt2), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (auto& e : ev) cudaEventDestroy(e);
     if (stats) {
         stats[0] = launches; stats[1] = evals + (long long)cnt2[1]; stats[2] = (long long)cnt2[0];
         stats[3] = us_setup; stats[4] = wall_us();                             // host wall clock: setup, whole call

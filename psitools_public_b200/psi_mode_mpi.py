@@ -390,7 +390,14 @@ class MpiScheduler:
                 return res
         mine = _dist.my_items(len(arglist))
         if self.engine != "python":
-            done = self._run_native(arglist, mine)
+            try:
+                done, err = self._run_native(arglist, mine), None
+            except Exception as exc:             # a failing search on one rank: every rank still reaches the
+                done, err = None, exc            # collective, and every rank raises
+            if _dist.all_reduce_max(0 if err is None else 1):
+                raise err if err is not None else RuntimeError("root search failed on another rank")
+            if _dist.all_reduce_max(0 if done is not None else 1):
+                done = None
             if done is not None:
                 (roots, nr), st = done
                 self.last_stats = dict(items=len(mine), passes=st.get("passes", 0),
@@ -444,17 +451,34 @@ class DispersionRelationMpiScheduler(MpiScheduler):
         return pm.dispersion(**args['dispersion'])
 
     def run_all(self, arglist, root_only=False):
+        """{index: D}: every item's 'w' may be a scalar or an array of any shape (the reference hands it straight to
+        PSIMode.dispersion, psi_mode_mpi.py:185-192); all frequencies of a rank's items go through ONE K1 launch and
+        come back in the shape they were given."""
         mine = _dist.my_items(len(arglist))
         local = {}
         if mine:
             pms = [self._cache.get(arglist[i]['__init__']) for i in mine]
             d = [arglist[i]['dispersion'] for i in mine]
             ctx = pms[0].psi_dispersion.ctx
-            vals = ctx.disp_eval(np.array([p.psi_dispersion.dist_id for p in pms], dtype=np.int32),
-                                 np.array([float(x['wave_number_x']) for x in d]),
-                                 np.array([float(x['wave_number_z']) for x in d]),
-                                 np.array([float(x.get('viscous_alpha', 0)) for x in d]),
-                                 np.array([complex(x['w']) for x in d]))
-            local = {i: np.array([v.real, v.imag]) for i, v in zip(mine, vals)}
+            ws = [np.asarray(x['w'], dtype=np.complex128) for x in d]
+            size = np.array([w.size for w in ws], dtype=np.int64)
+            per_point = lambda vals, dt: np.repeat(np.asarray(vals, dtype=dt), size)
+            vals = ctx.disp_eval(per_point([p.psi_dispersion.dist_id for p in pms], np.int32),
+                                 per_point([float(x['wave_number_x']) for x in d], float),
+                                 per_point([float(x['wave_number_z']) for x in d], float),
+                                 per_point([float(x.get('viscous_alpha', 0)) for x in d], float),
+                                 np.concatenate([w.ravel() for w in ws]) if ws else np.zeros(0, complex))
+            at = np.concatenate(([0], np.cumsum(size)))
+            self._shapes = {i: w.shape for i, w in zip(mine, ws)}
+            local = {i: np.concatenate(([float(w.ndim)], np.asarray(w.shape, dtype=float),
+                                        vals[at[k]:at[k + 1]].view(np.float64)))
+                     for k, (i, w) in enumerate(zip(mine, ws))}
         merged = _dist.all_gather_records(local)
-        return {i: np.squeeze(np.array([complex(merged[i][0], merged[i][1])])) for i in sorted(merged)}
+        out = {}
+        for i in sorted(merged):
+            rec = merged[i]
+            nd = int(rec[0])
+            shape = tuple(int(v) for v in rec[1:1 + nd])
+            val = np.ascontiguousarray(rec[1 + nd:]).view(np.complex128).reshape(shape)
+            out[i] = np.squeeze(val) if nd == 0 else val
+        return out

@@ -131,6 +131,16 @@ def test_dispersion_scheduler(backend):
     np.testing.assert_allclose(res[3].real, -8.18797751107521e+07, rtol=1e-7)
     np.testing.assert_allclose(res[3].imag, +8.84518043425989e+07, rtol=1e-7)
     assert res[1].shape == ()
+    # array-valued 'w' items (the reference passes w straight to PSIMode.dispersion, which takes any shape)
+    w2 = np.array([[-2 - 2j, 2 - 2j], [-2 + 2j, 2 + 2j]])
+    mixed = [dict(items[0], dispersion=dict(items[0]['dispersion'], w=w2)), items[3],
+             dict(items[0], dispersion=dict(items[0]['dispersion'], w=w2.ravel()[:3]))]
+    res2 = psi_mode_mpi.DispersionRelationMpiScheduler(time.time(), 3600, verbose=False).run(mixed)
+    assert res2[0].shape == (2, 2) and res2[1].shape == () and res2[2].shape == (3,)
+    flat = np.array([res[i] for i in range(4)])
+    np.testing.assert_allclose(res2[0].ravel(), flat, rtol=1e-13)
+    np.testing.assert_allclose(res2[2], flat[:3], rtol=1e-13)
+    np.testing.assert_allclose(res2[1], res[3], rtol=1e-13)
 
 
 def count_arglist(ts):
