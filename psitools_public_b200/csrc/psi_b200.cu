@@ -340,12 +340,14 @@ disp_eval_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restri
                  double2* __restrict__ M, unsigned long long* __restrict__ queue,
                  unsigned long long* __restrict__ node_evals, const long long* __restrict__ elem,
                  int elem_cap, const long long* __restrict__ remap,
-                 const unsigned long long* __restrict__ n_dev) {
+                 const unsigned long long* __restrict__ n_dev, unsigned long long min_work) {
+    // second stage of the fast path: the work list is the `remap` array, its length sits in device memory; with
+    // fewer than min_work points on it the block-per-point kernel below has taken them
+    const unsigned long long n_work = n_dev != nullptr ? *n_dev : (unsigned long long)n;
+    if (n_dev != nullptr && n_work < min_work) return;
     const NodeTableView t = stage_table(gt, table_in_smem != 0);
     const int lane = threadIdx.x & 31;
     unsigned long long nodes = 0;
-    // second stage of the fast path: the work list is the `remap` array, its length sits in device memory
-    const unsigned long long n_work = n_dev != nullptr ? *n_dev : (unsigned long long)n;
     while (true) {
         unsigned long long idx = 0;
         if (lane == 0) idx = atomicAdd(queue, 1ull);
@@ -377,7 +379,44 @@ disp_eval_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restri
 typedef void (*eval_kernel_t)(NodeTableView, int, const DistParams*, long long, int, const int*, const double*,
                               const double*, const double*, const int*, const double2*, double2*, double2*,
                               unsigned long long*, unsigned long long*, const long long*, int, const long long*,
-                              const unsigned long long*);
+                              const unsigned long long*, unsigned long long);
+
+// Left-over stage of the fast path when only a HANDFUL of points is left (with the split at tau* = -1/Im w that is the
+// rule: ~0.02 % of BASELINE config 2's grid, each needing all twelve levels -- 30 k nodes): one BLOCK per point, the
+// nodes of a level spread over its 384 threads (the block policy of K3's block mode), instead of one warp grinding
+// through a point for a millisecond while 99 % of the machine idles.  Runs only when the list holds fewer than
+// `max_work` points; the warp kernel takes longer lists.
+template <int NK, bool VISC>
+__global__ void __launch_bounds__(kEvalThreads, 1)
+disp_eval_cta_kernel(NodeTableView gt, int table_in_smem, const DistParams* __restrict__ dists, int broadcast,
+                     const int* __restrict__ dist, const double* __restrict__ kx, const double* __restrict__ kz,
+                     const double* __restrict__ alpha, const int* __restrict__ pidx, const double2* __restrict__ w,
+                     double2* __restrict__ D, unsigned long long* __restrict__ queue,
+                     unsigned long long* __restrict__ node_evals, const long long* __restrict__ elem, int elem_cap,
+                     const long long* __restrict__ remap, const unsigned long long* __restrict__ n_dev,
+                     unsigned long long max_work) {
+    const unsigned long long n_work = *n_dev;
+    if (n_work == 0 || n_work >= max_work) return;
+    const NodeTableView t = stage_table(gt, table_in_smem != 0);
+    typedef CtaCuda<kEvalThreads> W;
+    W::phase() = 0u;
+    unsigned long long nodes = 0;
+    long long k;
+    while (next_item_cta(queue, (long long)n_work, k)) {
+        const long long idx = remap[k];
+        const long long e = elem != nullptr ? elem[idx] : idx;
+        const long long pi = elem != nullptr ? e / elem_cap
+                             : (pidx != nullptr ? (long long)pidx[idx] : (broadcast ? 0 : idx));
+        const DistParams& d = dists[dist[pi]];
+        const double al = alpha[pi];
+        if (point_class(d, al) != NK * 2 + (VISC ? 1 : 0)) continue;
+        const double2 wv = w[e];
+        const cx val = disp_eval_warp<W, NK, VISC>(t, d, cx(wv.x, wv.y), kx[pi], kz[pi], al, nullptr, nodes);
+        if (threadIdx.x == 0) D[e] = make_double2(val.re, val.im);
+    }
+    if (node_evals != nullptr && threadIdx.x == 0 && nodes) atomicAdd(node_evals, nodes);
+}
+typedef decltype(&disp_eval_cta_kernel<0, false>) eval_cta_kernel_t;
 
 // K1 fast path.  Most evaluations converge within the first few levels of the rule (a few hundred nodes: the
 // exit predictor of psi_quad.cuh); for them a whole warp per point spends most of its time in per-level
@@ -748,6 +787,7 @@ __global__ void mode_pack_kernel(ModeDev m, int n_items, int rows, double* rec) 
     {NAME<0, false>, NAME<0, true>, NAME<1, false>, NAME<1, true>, NAME<2, false>, NAME<2, true>,    \
      NAME<3, false>, NAME<3, true>, NAME<4, false>, NAME<4, true>}
 typedef decltype(&polish_kernel<0, false, false>) polish_kernel_t;
+static const eval_cta_kernel_t kEvalCtaKernels[kNumClasses] = PSI_CLASS_TABLE(disp_eval_cta_kernel);
 #define PSI_CLASS_TABLE_CTA(NAME)                                                                          \
     {NAME<0, false, true>, NAME<0, true, true>, NAME<1, false, true>, NAME<1, true, true>, NAME<2, false, true>, \
      NAME<2, true, true>, NAME<3, false, true>, NAME<3, true, true>, NAME<4, false, true>, NAME<4, true, true>}
@@ -829,9 +869,12 @@ int psi_ctx_create(psi_ctx** out, int device, const double* xj, const double* wj
         for (int cls = 0; cls < kNumClasses; ++cls)
             CK(cudaFuncSetAttribute(eval_kernel_for(cls), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)c->table_smem));
-        for (int cls = 0; cls < kNumClasses; ++cls)
+        for (int cls = 0; cls < kNumClasses; ++cls) {
             CK(cudaFuncSetAttribute(thread_kernel_for(cls), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)c->table_smem));
+            CK(cudaFuncSetAttribute(kEvalCtaKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)c->table_smem));
+        }
         for (int cls = 0; cls < kNumClasses; ++cls) {
             CK(cudaFuncSetAttribute(kPolishKernels[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
             CK(cudaFuncSetAttribute(kPolishKernelsCta[cls], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->table_smem));
@@ -975,17 +1018,23 @@ static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* d
                 (double2*)D, c->d_counter, node_evals_dev, elem, elem_cap, c->fast_cap, c->d_hard, c->d_counter + 9);
             c->launches++;
             CK(cudaGetLastError());
+            // what the thread kernel left: a block per point when it is a handful, a warp per point otherwise
+            const unsigned long long few = 4ull * (unsigned long long)c->sm_count;
+            CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+            kEvalCtaKernels[cls]<<<c->sm_count, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
+                t, c->table_in_smem ? 1 : 0, c->d_dists, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w,
+                (double2*)D, c->d_counter, node_evals_dev, elem, elem_cap, c->d_hard, c->d_counter + 9, few);
             CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
             k<<<c->sm_count, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
                 t, c->table_in_smem ? 1 : 0, c->d_dists, n, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w,
-                (double2*)D, nullptr, c->d_counter, node_evals_dev, elem, elem_cap, c->d_hard, c->d_counter + 9);
-            c->launches++;
+                (double2*)D, nullptr, c->d_counter, node_evals_dev, elem, elem_cap, c->d_hard, c->d_counter + 9, few);
+            c->launches += 2;
             CK(cudaGetLastError());
             continue;
         }
         k<<<grid, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
             t, c->table_in_smem ? 1 : 0, c->d_dists, n, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w, (double2*)D,
-            (double2*)M, c->d_counter, node_evals_dev, elem, elem_cap, nullptr, nullptr);
+            (double2*)M, c->d_counter, node_evals_dev, elem, elem_cap, nullptr, nullptr, 0ull);
         c->launches++;
         CK(cudaGetLastError());
     }
