@@ -94,6 +94,14 @@ int psi_refine_open(psi_refine** out, int device, int nz, int nx, const int* run
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev)
         return psi_internal_fail(PSI_ERR_NODEVICE, "psi_refine_open: no such CUDA device");
     RCK(cudaSetDevice(device));
+    {   // the per-sweep temporaries come from the stream-ordered pool: keep freed blocks in the pool instead of
+        // returning them to the driver at every synchronisation (the default) and re-mapping them the next sweep
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     psi_refine* r = new psi_refine();
     r->device = device; r->nz = nz; r->nx = nx; r->width = width; r->key_capacity = key_capacity;
     const size_t np = (size_t)nz * nx;
