@@ -572,7 +572,8 @@ def run_b200(args):
                  "rank0_host_logic_seconds": st.get("host_logic_seconds"),
                  "rank0_device_seconds": st.get("device_seconds"),
                  "rank0_D_evals_in_K3": st.get("polish_evals"), "host_threads": ctx.default_engine_threads(),
-                 "engine": st.get("engine"), "exchange": st.get("exchange"), "rank0_stage_seconds": st.get("stage_s")}
+                 "engine": st.get("engine"), "exchange": st.get("exchange"), "rank0_stage_seconds": st.get("stage_s"),
+                 "rank0_host_split": st.get("host_split")}
         if args.modes_compare:
             # same map through the host-AAA engine (LAPACK on the host cores + K1/K3), for comparison
             ms2 = psi_mode_mpi.MpiScheduler(time.time(), 1e9, verbose=False, engine="native")

@@ -55,6 +55,7 @@ def refine(nbase, fills, reruns):
                 'random_seed': 2}
     gr = PSIGridRefiner('bench', baseargs=baseargs, nbase=(nbase, nbase), reruns=reruns, krange=(-1, 3))
     sched = {"s": 0.0}
+    per_sweep = []                                # [items, seconds in the scheduler, batch, exchange] per sweep
     inner = gr.ms.run_arrays                      # time spent inside the scheduler (device + exchange)
 
     def timed(*a, **k):
@@ -62,6 +63,9 @@ def refine(nbase, fills, reruns):
         out = inner(*a, **k)
         sched["s"] += time.perf_counter() - t
         st = gr.ms.last_stats
+        per_sweep.append([len(a[1]), round(time.perf_counter() - t, 4), round(st.get("batch_seconds") or 0.0, 4),
+                          round(st.get("exchange_seconds") or 0.0, 4),
+                          {k: round(v, 4) for k, v in (st.get("stage_s") or {}).items()}, st.get("function_calls"), st.get("calls_pct")])
         for key in ("prep_seconds", "batch_seconds", "exchange_seconds", "wait_seconds", "lib_setup_seconds",
                     "lib_call_seconds"):
             sched[key] = sched.get(key, 0.0) + (st.get(key) or 0.0)
@@ -87,7 +91,8 @@ def refine(nbase, fills, reruns):
                           "runs_per_s": runs/times[-1], "sweeps": len(gr.sweep_log),
                           "seconds_in_scheduler": sched["s"], "seconds_host_bookkeeping": times[-1] - sched["s"],
                           "scheduler_split": {k: round(v, 3) for k, v in sched.items() if k != "s"},
-                          "pixels_with_roots": with_roots}), flush=True)
+                          "pixels_with_roots": with_roots,
+                          **({"per_sweep": per_sweep} if os.environ.get("PSI_BENCH_PER_SWEEP") else {})}), flush=True)
 
 
 def sweep(n_mu, n_tau, n_axis, level):

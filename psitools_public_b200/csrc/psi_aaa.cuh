@@ -38,9 +38,11 @@ static __device__ unsigned long long g_psi_prof[32];
 #if defined(PSI_PROF) && defined(__CUDA_ARCH__)
 #define PROF_T0(v) const long long v = clock64()
 #define PROF_ADD(id, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_psi_prof[id], (unsigned long long)(clock64() - (v))); } while (0)
+#define PROF_MAX(id, val_) do { if ((threadIdx.x & 31) == 0) atomicMax(&g_psi_prof[id], (unsigned long long)(val_)); } while (0)
 #else
 #define PROF_T0(v)
 #define PROF_ADD(id, v)
+#define PROF_MAX(id, val_)
 #endif
 
 // Out-of-line copies of the small helpers.  The analysis kernel is instruction-fetch bound (ncu: 83 % of
@@ -279,6 +281,7 @@ PSI_NOINLINE int loewner_min_vector(cx* A, cx* Rm, cx* vec, cx* w, int r, int m,
         W::sync();
     }
     PROF_ADD(3, t_qr);
+    if (m > 48) { PROF_ADD(20, t_qr); PROF_MAX(21, m); }
     PROF_T0(t_ii);
     // R: strict upper triangle from A (rows < r), diagonal already in place (zero where no step ran)
 #pragma unroll 1
@@ -591,12 +594,16 @@ PSI_NOINLINE int aberth_roots(const AAAScratch& s, const AAAState& st, bool with
     double scale = 0.0;
     for (int j = 0; j < m; ++j) scale = fmax(scale, a_abs(s.Z[s.on[j]] - cx(cre, cim)));
     if (!(scale > 0.0)) scale = 1.0;
-    // start values: between consecutive support points, nudged off the connecting line
+    // start values: between consecutive support points, nudged off the connecting line by a fraction of THEIR
+    // distance.  (The samples around guess roots and in zoom boxes form clusters 1e-5 of the domain wide that hold
+    // as many roots as support points; a nudge on the scale of the whole set starts all of them far outside their
+    // cluster, from where it looks like one root of high multiplicity and the iteration crawls.)
 #pragma unroll 1
     for (int k = lane; k < nr; k += W::width) {
         const cx a = s.Z[s.on[k]], b = s.Z[s.on[k + 1]];
         const cx d = b - a;
-        out[k] = cx(0.5 * (a.re + b.re) - 0.31 * d.im + 0.013 * scale, 0.5 * (a.im + b.im) + 0.31 * d.re + 0.017 * scale);
+        const double len = a_abs(d);
+        out[k] = cx(0.5 * (a.re + b.re) - 0.31 * d.im + 0.013 * len, 0.5 * (a.im + b.im) + 0.31 * d.re + 0.017 * len);
     }
     W::sync();
     // Convergence per root: Aberth contracts cubically until the step reaches the rounding noise of

@@ -718,8 +718,11 @@ mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, c
         st.M = m.M[idx]; st.m = 0; st.r = 0; st.fmax = 0.0; st.tol = cfg.tol; st.clean_tol = cfg.clean_tol;
         st.dom = cfg.dom; st.memo_next = 0; st.slot = 0; st.v_m = 0;
         ModePlan plan;
+        PROF_T0(t_an);
         const bool ok = mode_analyze<W>(cfg, m.level[idx], guess_off[idx + 1] - guess_off[idx], sc, st, plan);
         W::sync();
+        PROF_ADD(12, t_an);
+        PROF_MAX(22, ((unsigned long long)(clock64() - t_an) << 22) | (unsigned long long)(idx & 0x3fffff));
         if (m.mask_out != nullptr && ok)
             for (int i = lane; i < st.M; i += W::width) m.mask_out[(size_t)idx * m.cap + i] = sc.mask[i];
         if (lane == 0) {

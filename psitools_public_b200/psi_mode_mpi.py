@@ -304,6 +304,10 @@ class MpiScheduler:
                                host_logic_seconds=st.get("logic_s"), device_seconds=st.get("eval_s"),
                                launches=st.get("launches"), polish_evals=st.get("polish_evals"),
                                stage_s=st.get("stage_s"), engine=self.engine)
+        if os.environ.get("PSI_B200_CALL_STATS") and len(mine):      # diagnostic: spread of samples per search
+            c = np.asarray(ncalls)
+            self.last_stats["calls_pct"] = [int(v) for v in np.percentile(c, [50, 90, 99, 99.9, 100])] + \
+                [int(np.sum(c > 160)), int(np.sum(c > 320))]
         # exchange: per item a count, and the roots of the items that have any (rank q owns items q::world)
         nr = np.asarray(nr, dtype=np.int64)
         valid = np.arange(roots.shape[1])[None, :] < nr[:, None]
@@ -337,18 +341,23 @@ class MpiScheduler:
         mine = _dist.my_items(n)
         rows = (n + world - 1)//world
         max_roots = 8
+        tick = [time.time()]
+        lap = lambda: tick.append(time.time())
         while True:
             try:
                 done = self._run_native(arglist, mine, rec_rows=rows, max_roots=max_roots)
             except Exception as exc:             # (capacity etc.): every rank must still reach the collective
                 done, err = "error", exc
+            lap()
             flag = _dist.all_reduce_max(0 if isinstance(done, tuple) else (2 if done == "error" else 1))
+            lap()
             if flag == 2:
                 raise err if done == "error" else RuntimeError("root search failed on another rank")
             if flag == 1:
                 return None
             (rec, _), st = done
             got = _dist.all_gather_device_records(rec, n, to_host=to_host)
+            lap()
             if got["worst"] not in (0, 4):
                 raise RuntimeError("device root search failed on some rank (status %d)" % got["worst"])
             if got["top"] > max_roots:            # rare: more roots than slots somewhere -> every rank redoes it
@@ -357,7 +366,9 @@ class MpiScheduler:
             break
         self.last_stats = dict(items=len(mine), passes=st.get("passes", 0), function_calls=got["calls"],
                                evals=st.get("evals", 0), launches=st.get("launches"), stage_s=st.get("stage_s"),
-                               engine=self.engine, exchange="nccl all_gather_into_tensor (device records)")
+                               engine=self.engine, exchange="nccl all_gather_into_tensor (device records)",
+                               host_split=dict(solve=tick[-3] - tick[0], lib_call=st.get("call_s"),
+                                               flag_allreduce=tick[-2] - tick[-3], gather=tick[-1] - tick[-2]))
         if got["cnt"] is None:
             return ()
         roots = np.zeros((n, max_roots), dtype=np.complex128)
