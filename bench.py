@@ -319,14 +319,53 @@ def run_config4(barrier, world):
         warm.fill_in_grid()
         warm._close_device_map()
     sched.clear()
+    import gc
+    from psitools_public_b200 import _device as _dev
+    extra_t = {"gc_seconds": 0.0, "device_map_seconds": 0.0}
+    mark = [0.0]
+
+    def on_gc(phase, info):
+        if phase == "start":
+            mark[0] = time.perf_counter()
+        else:
+            extra_t["gc_seconds"] += time.perf_counter() - mark[0]
+    saved = {}
+    for name in ("__init__", "sweep", "update", "close"):       # time spent in the device mirror of the cell queue
+        fn = getattr(_dev.RefineMap, name)
+        saved[name] = fn
+
+        def timed_fn(self, *a, _fn=fn, _name=name.strip('_'), **k):
+            t = time.perf_counter()
+            try:
+                return _fn(self, *a, **k)
+            finally:
+                extra_t["device_map_seconds"] += time.perf_counter() - t
+                extra_t["map_" + _name] = extra_t.get("map_" + _name, 0.0) + time.perf_counter() - t
+        setattr(_dev.RefineMap, name, timed_fn)
+    gc.callbacks.append(on_gc)
+    prof = None
+    if os.environ.get("PSI_BENCH_PROFILE"):                # diagnostic: where the host time of the campaign goes
+        import cProfile
+        prof = cProfile.Profile()
     barrier()
     t0 = time.perf_counter()
     with contextlib.redirect_stdout(io.StringIO()):
+        if prof:
+            prof.enable()
         gr.run_basegrid()
         for _ in range(6):
             gr.fill_in_grid()
+        if prof:
+            prof.disable()
     barrier()
     dt = time.perf_counter() - t0
+    gc.callbacks.remove(on_gc)
+    for name, fn in saved.items():
+        setattr(_dev.RefineMap, name, fn)
+    sched.update(extra_t)
+    if prof and int(os.environ.get("RANK", "0")) == 0:
+        import pstats
+        pstats.Stats(prof, stream=sys.stderr).sort_stats('tottime').print_stats(14)
     g = gr.grids[-1]
     runs = sum(n for _, n, _ in gr.sweep_log) + gr.grids[0]['runs'].size
     return {"workload": "config4: PSIGridRefiner PowerBump mu=10, nbase 16, reruns 3, 6 fill-ins -> %dx%d map"

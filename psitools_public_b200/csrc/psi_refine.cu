@@ -8,7 +8,11 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "psi_internal.hpp"
 #include "psi_refine.cuh"
@@ -27,7 +31,9 @@ struct psi_refine {
     long long key_capacity = 0;
     cudaStream_t stream = nullptr;
     int *runs = nullptr, *nguess = nullptr, *cnt = nullptr, *nk = nullptr, *overflow = nullptr;
-    cx* mat = nullptr;
+    cx* mat = nullptr;                      // packed pool of roots (pool_used of pool_cap entries in use)
+    long long* off = nullptr;               // [key_capacity] start of a run id's roots in the pool
+    long long pool_cap = 0, pool_used = 0;
     long long *flag_scan = nullptr, *guess_scan = nullptr;     // exclusive scans over the pixels
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
@@ -62,16 +68,77 @@ refine_emit_kernel(RefineView g, const int* nk, const long long* flag_scan, cons
     nguess[p] = n;                         // read by this thread only (refine_pixel above)
 }
 
-__global__ void refine_update_kernel(int* cnt, cx* mat, int width, long long n_changed, const long long* keys,
-                                     const int* new_cnt, const cx* rows, int* runs, long long n_pix,
-                                     const int* pix, const int* run_ids) {
+// store the roots of n_changed run ids (keys == nullptr: ids 0..n_changed-1) from dense rows of `width` slots at
+// start[i] of the pool; set the run id of n_pix pixels
+__global__ void refine_update_kernel(int* cnt, long long* off, cx* pool, int width, long long n_changed,
+                                     const long long* keys, const int* new_cnt, const long long* start,
+                                     const cx* rows, int* runs, long long n_pix, const int* pix, const int* run_ids) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_changed) {
-        const long long key = keys[i];
-        cnt[key] = new_cnt[i];
-        for (int t = 0; t < width; ++t) mat[key * width + t] = rows[i * width + t];
+        const long long key = keys ? keys[i] : i;
+        const int c = new_cnt[i];
+        cnt[key] = c;
+        off[key] = start[i];
+        for (int t = 0; t < c; ++t) pool[start[i] + t] = rows[i * width + t];
     }
     if (i < n_pix) runs[pix[i]] = run_ids[i];
+}
+
+// host half of an update: pool positions of the new rows, pool grown (x2) when they do not fit
+static cudaError_t refine_store(psi_refine* r, long long n_changed, const long long* keys, const int* cnt,
+                                const double* rows, long long n_pix, const int* pix, const int* run_ids) {
+    std::vector<long long> start((size_t)std::max<long long>(n_changed, 1));
+    long long used = r->pool_used;
+    for (long long i = 0; i < n_changed; ++i) {
+        start[i] = used;
+        if (cnt[i] > r->width) return cudaErrorInvalidValue;
+        used += cnt[i] > 0 ? cnt[i] : 0;
+    }
+    cudaError_t e = cudaSuccess;
+    if (used > r->pool_cap) {
+        const long long cap = std::max<long long>(2 * used, 4096);
+        cx* bigger = nullptr;
+        e = cudaMallocAsync(&bigger, 16 * (size_t)cap, r->stream);
+        if (e == cudaSuccess && r->pool_used > 0)
+            e = cudaMemcpyAsync(bigger, r->mat, 16 * (size_t)r->pool_used, cudaMemcpyDeviceToDevice, r->stream);
+        if (e == cudaSuccess && r->mat) e = cudaFreeAsync(r->mat, r->stream);
+        if (e != cudaSuccess) return e;
+        r->mat = bigger; r->pool_cap = cap;
+    }
+    long long *d_keys = nullptr, *d_start = nullptr;
+    int *d_cnt = nullptr, *d_pix = nullptr, *d_ids = nullptr;
+    cx* d_rows = nullptr;
+    const size_t nc = (size_t)std::max<long long>(n_changed, 1), npx = (size_t)std::max<long long>(n_pix, 1);
+    if (keys) e = cudaMallocAsync(&d_keys, 8 * nc, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_start, 8 * nc, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_cnt, 4 * nc, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_rows, 16 * nc * r->width, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_pix, 4 * npx, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_ids, 4 * npx, r->stream);
+    if (e == cudaSuccess && n_changed > 0) {
+        if (keys) e = cudaMemcpyAsync(d_keys, keys, 8 * (size_t)n_changed, cudaMemcpyHostToDevice, r->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_start, start.data(), 8 * (size_t)n_changed, cudaMemcpyHostToDevice, r->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_cnt, cnt, 4 * (size_t)n_changed, cudaMemcpyHostToDevice, r->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_rows, rows, 16 * (size_t)n_changed * r->width, cudaMemcpyHostToDevice, r->stream);
+    }
+    if (e == cudaSuccess && n_pix > 0) {
+        e = cudaMemcpyAsync(d_pix, pix, 4 * (size_t)n_pix, cudaMemcpyHostToDevice, r->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_ids, run_ids, 4 * (size_t)n_pix, cudaMemcpyHostToDevice, r->stream);
+    }
+    const long long n = std::max(n_changed, n_pix);
+    if (e == cudaSuccess && n > 0) {
+        refine_update_kernel<<<(int)((n + 255) / 256), 256, 0, r->stream>>>(r->cnt, r->off, r->mat, r->width, n_changed,
+                                                                            d_keys, d_cnt, d_start, d_rows, r->runs,
+                                                                            n_pix, d_pix, d_ids);
+        e = cudaGetLastError();
+    }
+    void* tmp[] = {d_keys, d_start, d_cnt, d_rows, d_pix, d_ids};
+    for (void* q : tmp) if (q) cudaFreeAsync(q, r->stream);
+    const cudaError_t e2 = cudaStreamSynchronize(r->stream);       // (start[] is read by the copy until here)
+    if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess) r->pool_used = used;
+    return e;
 }
 
 extern "C" {
@@ -79,9 +146,14 @@ extern "C" {
 void psi_refine_close(psi_refine* r) {
     if (!r) return;
     cudaSetDevice(r->device);
-    cudaFree(r->runs); cudaFree(r->nguess); cudaFree(r->cnt); cudaFree(r->nk); cudaFree(r->mat);
-    cudaFree(r->flag_scan); cudaFree(r->guess_scan); cudaFree(r->cub_tmp); cudaFree(r->overflow);
-    if (r->stream) cudaStreamDestroy(r->stream);
+    // back into the stream-ordered pool (a campaign opens one map per refinement level: cudaFree of the previous
+    // level's arrays, which unmaps them and synchronises the device, cost 0.02-0.1 s per level)
+    if (r->stream) {
+        void* p[] = {r->runs, r->nguess, r->cnt, r->nk, r->mat, r->off, r->flag_scan, r->guess_scan, r->cub_tmp, r->overflow};
+        for (void* q : p) if (q) cudaFreeAsync(q, r->stream);
+        cudaStreamSynchronize(r->stream);
+        cudaStreamDestroy(r->stream);
+    }
     delete r;
 }
 
@@ -105,27 +177,32 @@ int psi_refine_open(psi_refine** out, int device, int nz, int nx, const int* run
     psi_refine* r = new psi_refine();
     r->device = device; r->nz = nz; r->nx = nx; r->width = width; r->key_capacity = key_capacity;
     const size_t np = (size_t)nz * nx;
+    const bool trace = getenv("PSI_REFINE_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_a = now();
     cudaError_t e = cudaStreamCreate(&r->stream);
-    if (e == cudaSuccess) e = cudaMalloc(&r->runs, 4 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&r->nguess, 4 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&r->nk, 4 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&r->overflow, 4);
-    if (e == cudaSuccess) e = cudaMalloc(&r->flag_scan, 8 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&r->guess_scan, 8 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&r->cnt, 4 * (size_t)std::max<long long>(key_capacity, 1));
-    if (e == cudaSuccess) e = cudaMalloc(&r->mat, 16 * (size_t)std::max<long long>(key_capacity, 1) * width);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->runs, 4 * np, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->nguess, 4 * np, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->nk, 4 * np, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->overflow, 4, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->flag_scan, 8 * np, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->guess_scan, 8 * np, r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->cnt, 4 * (size_t)std::max<long long>(key_capacity, 1), r->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->off, 8 * (size_t)std::max<long long>(key_capacity, 1), r->stream);
     if (e == cudaSuccess)
         e = cub::DeviceScan::ExclusiveSum(nullptr, r->cub_bytes, r->flag_scan, r->flag_scan, (long long)np, r->stream);
-    if (e == cudaSuccess) e = cudaMalloc(&r->cub_tmp, r->cub_bytes + 256);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->cub_tmp, r->cub_bytes + 256, r->stream);
+    if (trace) cudaStreamSynchronize(r->stream);
+    const double t_b = now();
     if (e == cudaSuccess) e = cudaMemcpyAsync(r->runs, runs, 4 * np, cudaMemcpyHostToDevice, r->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(r->nguess, nguess, 4 * np, cudaMemcpyHostToDevice, r->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(r->cnt, 0xff, 4 * (size_t)std::max<long long>(key_capacity, 1), r->stream);
-    if (e == cudaSuccess && n_keys > 0) {
-        e = cudaMemcpyAsync(r->cnt, cnt, 4 * (size_t)n_keys, cudaMemcpyHostToDevice, r->stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(r->mat, mat, 16 * (size_t)n_keys * width, cudaMemcpyHostToDevice, r->stream);
-    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(r->off, 0, 8 * (size_t)std::max<long long>(key_capacity, 1), r->stream);
+    if (e == cudaSuccess && n_keys > 0) e = refine_store(r, n_keys, nullptr, cnt, mat, 0, nullptr, nullptr);
     if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+    if (trace)
+        fprintf(stderr, "psi_refine_open %dx%d keys %lld cap %lld width %d: alloc %.4f s, upload %.4f s\n", nz, nx, n_keys,
+                key_capacity, width, t_b - t_a, now() - t_b);
     if (e != cudaSuccess) {
         psi_refine_close(r);
         return psi_internal_fail(PSI_ERR_CUDA, std::string("psi_refine_open: ") + cudaGetErrorString(e));
@@ -138,7 +215,7 @@ int psi_refine_sweep(psi_refine* r, long long* n_run, long long* n_guess) {
     if (!r || !n_run || !n_guess) return psi_internal_fail(PSI_ERR_ARG, "psi_refine_sweep: bad argument");
     RCK(cudaSetDevice(r->device));
     const long long np = (long long)r->nz * r->nx;
-    RefineView g{r->nz, r->nx, r->width, r->runs, r->cnt, r->mat, r->nguess};
+    RefineView g{r->nz, r->nx, r->width, r->runs, r->cnt, r->mat, r->nguess, r->off};
     const int grid = (int)((np + 127) / 128);
     RCK(cudaMemsetAsync(r->overflow, 0, 4, r->stream));
     refine_count_kernel<<<grid, 128, 0, r->stream>>>(g, r->nk, r->flag_scan, r->guess_scan, r->overflow);
@@ -178,7 +255,7 @@ int psi_refine_fetch(psi_refine* r, int* pix, int* n_kept, double* guesses) {
     RCK(cudaMallocAsync(&d_pix, 4 * (size_t)r->n_run, r->stream));
     RCK(cudaMallocAsync(&d_nk, 4 * (size_t)r->n_run, r->stream));
     RCK(cudaMallocAsync(&d_g, 16 * (size_t)std::max<long long>(r->n_guess, 1), r->stream));
-    RefineView g{r->nz, r->nx, r->width, r->runs, r->cnt, r->mat, r->nguess};
+    RefineView g{r->nz, r->nx, r->width, r->runs, r->cnt, r->mat, r->nguess, r->off};
     refine_emit_kernel<<<(int)((np + 127) / 128), 128, 0, r->stream>>>(g, r->nk, r->flag_scan, r->guess_scan,
                                                                         r->nguess, d_pix, d_nk, d_g);
     RCK(cudaGetLastError());
@@ -200,32 +277,11 @@ int psi_refine_update(psi_refine* r, long long n_changed, const long long* keys,
     for (long long i = 0; i < n_changed; ++i)
         if (keys[i] < 0 || keys[i] >= r->key_capacity)
             return psi_internal_fail(PSI_ERR_CAPACITY, "psi_refine_update: run id beyond the mirror's capacity");
-    const long long n = std::max(n_changed, n_pix);
-    if (n == 0) return PSI_OK;
+    if (std::max(n_changed, n_pix) == 0) return PSI_OK;
+    for (long long i = 0; i < n_changed; ++i)
+        if (cnt[i] > r->width) return psi_internal_fail(PSI_ERR_ARG, "psi_refine_update: more roots than row slots");
     RCK(cudaSetDevice(r->device));
-    long long* d_keys = nullptr;
-    int *d_cnt = nullptr, *d_pix = nullptr, *d_ids = nullptr;
-    cx* d_rows = nullptr;
-    RCK(cudaMallocAsync(&d_keys, 8 * (size_t)std::max<long long>(n_changed, 1), r->stream));
-    RCK(cudaMallocAsync(&d_cnt, 4 * (size_t)std::max<long long>(n_changed, 1), r->stream));
-    RCK(cudaMallocAsync(&d_rows, 16 * (size_t)std::max<long long>(n_changed, 1) * r->width, r->stream));
-    RCK(cudaMallocAsync(&d_pix, 4 * (size_t)std::max<long long>(n_pix, 1), r->stream));
-    RCK(cudaMallocAsync(&d_ids, 4 * (size_t)std::max<long long>(n_pix, 1), r->stream));
-    if (n_changed > 0) {
-        RCK(cudaMemcpyAsync(d_keys, keys, 8 * (size_t)n_changed, cudaMemcpyHostToDevice, r->stream));
-        RCK(cudaMemcpyAsync(d_cnt, cnt, 4 * (size_t)n_changed, cudaMemcpyHostToDevice, r->stream));
-        RCK(cudaMemcpyAsync(d_rows, rows, 16 * (size_t)n_changed * r->width, cudaMemcpyHostToDevice, r->stream));
-    }
-    if (n_pix > 0) {
-        RCK(cudaMemcpyAsync(d_pix, pix, 4 * (size_t)n_pix, cudaMemcpyHostToDevice, r->stream));
-        RCK(cudaMemcpyAsync(d_ids, run_ids, 4 * (size_t)n_pix, cudaMemcpyHostToDevice, r->stream));
-    }
-    refine_update_kernel<<<(int)((n + 255) / 256), 256, 0, r->stream>>>(r->cnt, r->mat, r->width, n_changed, d_keys,
-                                                                        d_cnt, d_rows, r->runs, n_pix, d_pix, d_ids);
-    RCK(cudaGetLastError());
-    RCK(cudaFreeAsync(d_keys, r->stream)); RCK(cudaFreeAsync(d_cnt, r->stream)); RCK(cudaFreeAsync(d_rows, r->stream));
-    RCK(cudaFreeAsync(d_pix, r->stream)); RCK(cudaFreeAsync(d_ids, r->stream));
-    RCK(cudaStreamSynchronize(r->stream));
+    RCK(refine_store(r, n_changed, keys, cnt, rows, n_pix, pix, run_ids));
     return PSI_OK;
 }
 

@@ -4,8 +4,10 @@
 // pixel WITHOUT roots collects the roots of its eight neighbours (reference order: (iz-1,ix-1), (iz,ix-1),
 // (iz+1,ix-1), (iz-1,ix), (iz+1,ix), (iz-1,ix+1), (iz,ix+1), (iz+1,ix+1); each run's roots in stored
 // order), prunes them with prune_eps (:75-84: greedy, epsilon = mean(Im)*1e-4) and launches a run when it
-// has more guesses than the last time it was run (nguess).  The root map is the dense RootStore: run id per
-// pixel, count per run id, `width` root slots per run id.
+// has more guesses than the last time it was run (nguess).  The root map: run id per pixel, count per run id and
+// the roots of a run id either in `width` dense slots (the numpy RootStore; CPU harness) or, on the device, at
+// off[run id] in one packed pool (most runs of a growth-rate map have no root: dense slots for every possible
+// run id of a 1089^2 map would be 4 GB, the pool is 20 MB).
 // PSI_HD like the other headers: the CPU harness runs the same code against the numpy sweep.
 #pragma once
 #include "psi_batch.cuh"
@@ -18,8 +20,10 @@ struct RefineView {
     int nz, nx, width;
     const int* runs;        // [nz*nx] run id or -1
     const int* cnt;         // [keys]  roots of a run id, -1 = no such run
-    const cx* mat;          // [keys*width]
+    const cx* mat;          // [keys*width], or the packed pool when off is set
     const int* nguess;      // [nz*nx]
+    const long long* off = nullptr;    // [keys] start of a run id's roots in the pool (packed layout)
+    PSI_HD const cx* roots_of(int key) const { return off ? mat + off[key] : mat + (size_t)key * width; }
 };
 
 PSI_HD bool refine_has(const RefineView& g, int iz, int ix) {
@@ -60,9 +64,10 @@ PSI_HD int refine_pixel(const RefineView& g, int iz, int ix, cx* near, cx* kept)
         const int key = g.runs[jz * g.nx + jx];
         if (key < 0) continue;
         const int c = g.cnt[key];
+        const cx* rk = g.roots_of(key);
         for (int t = 0; t < c; ++t) {
             if (n >= kRefineMaxNear) return -1;
-            near[n++] = g.mat[(size_t)key * g.width + t];
+            near[n++] = rk[t];
         }
     }
     if (n == 0) return 0;
