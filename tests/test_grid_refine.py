@@ -78,13 +78,16 @@ def test_refiner_against_reference(backend, engine, tmp_path):
     # final map: distinct roots per pixel agree on all but the knife-edge pixels
     ref_results = {int(k): carr(v) for k, v in gfin["results"].items()}
     ref_runs = np.array(gfin["runs"])
-    agree = 0
+    differ = []
     for iz in range(7):
         for ix in range(7):
             a = distinct(get_if(final['results'], final['runs'][iz, ix]))
             b = distinct(get_if(ref_results, ref_runs[iz, ix]))
-            agree += same_root_sets(a, b)
-    assert agree >= 45, agree                                     # measured: 47 of 49
+            if not same_root_sets(a, b):
+                differ.append((iz, ix))
+    # 47 of 49; the two pixels are fed by the one knife-edge run that test_refine_fixture_divergence_is_a_knife_edge
+    # attributes; the bookkeeping itself is exact (test_refiner_bookkeeping_replay_is_exact)
+    assert set(differ) <= {(5, 6), (6, 6)}, differ
     # every reported root is a root of the dispersion relation
     from psitools_public_b200 import PSIDispersion
     init = gr.baseargs['__init__']
