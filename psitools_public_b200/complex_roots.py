@@ -112,6 +112,69 @@ def drive(machine, func):
         return stop.value
 
 
+class RootFollower:
+    """Follow a root of func(z, k) while the parameter k moves away from k_start, where func(z_start, k_start) = 0
+    (reference complex_roots.py:428-515).  ``calculate(k_want)`` returns the root at every wanted k (sorted
+    ascending; values below and above k_start are marched separately, nearest first), 0 where the march gave up.
+
+    The march, as the reference defines it: try the whole remaining distance; a step is accepted when scipy's
+    secant rule (10 iterations, started from z_start and its companion point -- the start values are NOT moved
+    along with k) converges to a root on the same side of the real axis as z_start; a rejected step is cut
+    tenfold, an accepted one is followed by a step sqrt(2) times longer, clipped to the target.  Two properties of
+    the reference are kept because results depend on them: (1) once a clipped step would reach the target the
+    march stops WITHOUT solving there, so the value reported for a target that needed more than one step is the
+    root at the last intermediate k; (2) the give-up test ``k_step < 1e-6`` is signed, so marching towards
+    smaller k gives up at the first rejected step."""
+
+    def __init__(self, func, z_start, k_start, verbose=False):
+        self.func = func
+        self.z_start = z_start
+        self.k_start = k_start
+        self.verbose = verbose
+
+    def calculate(self, k_want):
+        k_want = np.atleast_1d(k_want)
+        ret = np.zeros(len(k_want), dtype=np.complex128)
+        for side in (k_want < self.k_start, k_want > self.k_start):
+            sel = np.asarray(side).nonzero()
+            ret[sel] = self._calculate(k_want[sel])
+        return ret
+
+    def _solve(self, k):
+        z0 = self.z_start
+        return drive(secant_machine(z0, second_point(z0, 1.0e-4), 10, 1.48e-8),
+                     lambda pts: [self.func(z, k) for z in pts])
+
+    def _calculate(self, k_want):
+        ret = np.zeros(len(k_want), dtype=np.complex128)
+        if len(k_want) == 0:
+            return ret
+        downwards = k_want[0] < self.k_start
+        order = range(len(k_want) - 1, -1, -1) if downwards else range(len(k_want))
+        k = self.k_start
+        for idx in order:
+            target = k_want[idx]
+            step = target - k
+            arrived = False
+            while not arrived:
+                while True:
+                    if self.verbose:
+                        print("Trying to find root at k = ", k + step, step)
+                    res = self._solve(k + step)
+                    if res.converged and res.root.imag*self.z_start.imag > 0:
+                        break
+                    step = step/10
+                    if step < 1.0e-6:
+                        return ret
+                k = k + step
+                step = step*np.sqrt(2)
+                if (step > 0 and k + step > target) or (step <= 0 and k + step < target) or step == 0:
+                    step = target - k          # (step == 0: a target equal to the current k; the reference
+                    arrived = True             # loops forever there)
+            ret[idx] = res.root
+        return ret
+
+
 # ------------------------------------------------------------------------------------------------
 # AAA
 # ------------------------------------------------------------------------------------------------

@@ -518,7 +518,50 @@ def sec_boundary():
     dump("boundary.json", out)
 
 
-SECTIONS = dict(boundary=sec_boundary, table=sec_table, multistart=sec_multistart, modegrid16=sec_modegrid16, nodes=sec_nodes, background=sec_background, disp=sec_disp, contour=sec_contour,
+def _follow_func(z, k):
+    """Toy relation for RootFollower: a cubic whose roots move with k and cross regions where ten secant
+    iterations from the fixed start values are not enough (rejected steps)."""
+    return z**3 - (1.0 + 0.5j)*z - (k + 0.2j)
+
+
+def sec_guessgen():
+    """RootFollower (complex_roots.py:428-515) on a toy relation and PSIModeTV /
+    TerminalVelocitySolver (terminalvelocitysolver.py) -- values from the unmodified reference."""
+    import contextlib
+    import importlib
+    import io
+    ns = refshim.load()
+    tv = importlib.import_module("psitools.terminalvelocitysolver")
+    out = {}
+    cases = []
+    for k_start, k_want in ((0.0, [0.05, 0.2, 0.5, 1.0, 3.0]), (0.0, [-0.4, -0.1, 0.3, 2.0]), (1.0, [1.5, 40.0]),
+                            (0.5, [0.5001, 0.6])):
+        roots0 = np.roots([1.0, 0.0, -(1.0 + 0.5j), -(k_start + 0.2j)])
+        z_start = complex(roots0[np.argmax(roots0.imag)])
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = ns.complex_roots.RootFollower(_follow_func, z_start, k_start).calculate(np.array(k_want))
+        cases.append(dict(k_start=k_start, k_want=k_want, z_start=cj(z_start), roots=cl(got)))
+    out["follow"] = cases
+    tvs = []
+    for mu, tmax, beta, kx, kz, alpha in ((3.0, 0.01, -3.5, 46.0, 1.0, 0.0), (3.0, 0.1, -3.5, 10.0, 100.0, 0.0),
+                                          (1.0, 0.1, -3.5, 30.0, 30.0, 1e-7), (10.0, 0.01, -3.0, 100.0, 20.0, 0.0),
+                                          (0.5, 0.03, -4.5, 20.0, 5.0, 0.0), (3.0, 0.01, -5.5, 46.0, 1.0, 1e-8),
+                                          (3.0, 1.0, -3.5, 1.0, 1000.0, 0.0)):
+        tau_min = np.logspace(-8, np.log10(tmax) - 0.01, 7)
+        with contextlib.redirect_stdout(io.StringIO()):
+            w = tv.PSIModeTV(mu, tmax, beta).find_roots(tau_min, kx, kz, viscous_alpha=alpha)
+            w1 = tv.PSIModeTV(mu, tmax, beta).find_roots(float(tau_min[0]), kx, kz, viscous_alpha=alpha)
+        tvs.append(dict(mu=mu, tau_max=tmax, beta=beta, kx=kx, kz=kz, alpha=alpha, tau_min=[float(t) for t in tau_min],
+                        omega=cl(w), omega_scalar=cj(w1)))
+    out["psimodetv"] = tvs
+    tau_min = np.logspace(-8, -2, 100)
+    with contextlib.redirect_stdout(io.StringIO()):
+        w = tv.TerminalVelocitySolver(3, 46, 1, tau_min, 0.01, -3.5).find_roots()
+    out["tvsolver_test_0"] = cl(w[::9])
+    dump("guessgen.json", out)
+
+
+SECTIONS = dict(guessgen=sec_guessgen, boundary=sec_boundary, table=sec_table, multistart=sec_multistart, modegrid16=sec_modegrid16, nodes=sec_nodes, background=sec_background, disp=sec_disp, contour=sec_contour,
                 mode=sec_mode, modegrid=sec_modegrid, refine=sec_refine)
 
 if __name__ == "__main__":
