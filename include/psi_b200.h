@@ -244,6 +244,17 @@ int psi_refine_update(psi_refine* map, long long n_changed, const long long* key
                       const double* rows, long long n_pix, const int* pix, const int* run_ids);
 void psi_refine_close(psi_refine* map);
 
+/* ---- guess generator: terminal-velocity PSI mode on a map of wave-number pairs --------------------------
+ * Replaces a Python loop over PSIModeTV.find_roots (reference terminalvelocitysolver.py:368-418, one wave-number
+ * pair per call) for ONE minimum Stokes number: one thread per pair follows the growing root of the closed-form
+ * terminal-velocity relation from the single-size limit tau_min = tau_max down to tau_min (step-size controlled
+ * continuation, scipy's secant rule; csrc/psi_tv.cuh).  dust_fraction = mu/(1+mu); b = -(3 + power-law exponent),
+ * one of 0, 0.5, 1.5, 2.5 (PSI_ERR_ARG otherwise); diffusion = viscous_alpha * c_over_eta^2; max_it = PSIModeTV's
+ * maximum_iterations.  omega: n complex mode frequencies; status[i] = 0 mode found, 1 gave up (omega is then the
+ * value the reference returns for z = 0).  Needs no psi_ctx. */
+int psi_tv_roots(int device, double dust_fraction, double tau_max, double b, double tau_min, double diffusion,
+                 int max_it, long long n, const double* kx, const double* kz, double* omega, int* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,6 +161,8 @@ _SIGNATURES = {
     "psi_refine_fetch": (C.c_int, [_vp, _vp, _vp, _vp]),
     "psi_refine_update": (C.c_int, [_vp, C.c_longlong, _vp, _vp, _vp, C.c_longlong, _vp, _vp]),
     "psi_refine_close": (None, [_vp]),
+    "psi_tv_roots": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                               C.c_longlong, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -571,6 +573,19 @@ class EngineAPI:
 
     def _last_error(self):
         return load_library().psi_last_error().decode()
+
+
+def tv_roots(dust_fraction, tau_max, b, tau_min, diffusion, max_it, kx, kz, device=None):
+    """psi_tv_roots: terminal-velocity mode frequency for arrays of wave-number pairs (one thread per pair)."""
+    lib = load_library()
+    kx = np.ascontiguousarray(kx, dtype=np.float64)
+    kz = np.ascontiguousarray(kz, dtype=np.float64)
+    w = np.zeros(len(kx), dtype=np.complex128)
+    st = np.zeros(len(kx), dtype=np.int32)
+    check(lib.psi_tv_roots(default_device() if device is None else int(device), float(dust_fraction), float(tau_max),
+                           float(b), float(tau_min), float(diffusion), int(max_it), len(kx), _ptr(kx), _ptr(kz),
+                           _ptr(w), _ptr(st)), "psi_tv_roots")
+    return w, st
 
 
 class RefineMap:

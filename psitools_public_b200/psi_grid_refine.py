@@ -124,7 +124,8 @@ class RootStore(MutableMapping):
 
 class PSIGridRefiner:
     def __init__(self, batchname, baseargs=None, nbase=(16, 16), reruns=3, verbose=False,
-                 krange=(-1.0, 3.0), scheduler=None):
+                 krange=(-1.0, 3.0), scheduler=None, tv_guesses=False):
+        self.tv_guesses = tv_guesses
         if baseargs:
             self.baseargs = baseargs
         else:
@@ -207,6 +208,26 @@ class PSIGridRefiner:
             args['random_seed'] += seed_shift
         return args
 
+    def _terminal_velocity_guesses(self, kx, kz):
+        """Optional guess roots for the base map (``tv_guesses=True``): the mode of the
+        terminal-velocity approximation at every pixel, computed for the whole map in one kernel
+        (``PSIModeTV.find_roots_map``), kept where it exists, grows and lies inside the search domain.  Needs a
+        power-law size distribution.  Returns the CSR pair (flat guesses, n+1 offsets)."""
+        from .terminalvelocitysolver import PSIModeTV
+        init = self.baseargs['__init__']
+        if init.get('size_density') is not None or init.get('single_size_flag'):
+            raise ValueError('tv_guesses needs a power-law size distribution')
+        tv = PSIModeTV(init['dust_to_gas_ratio'], init['stokes_range'][1],
+                       power_law_exponent_size_distribution=-init.get('size_distribution_power', 3.5))
+        w, status = tv.find_roots_map(init['stokes_range'][0], kx, kz,
+                                      viscous_alpha=self.baseargs['calculate'].get('viscous_alpha', 0),
+                                      c_over_eta=init.get('sound_speed_over_eta', 1/0.05))
+        re, im = init['real_range'], init['imag_range']
+        keep = (status == 0) & (w.real > re[0]) & (w.real < re[1]) & (w.imag > max(im[0], 0.0)) & (w.imag < im[1])
+        off = np.zeros(len(kx) + 1, dtype=np.int64)
+        np.cumsum(keep, out=off[1:])
+        return w[keep], off
+
     # -- public API ----------------------------------------------------------------------------
     def run_basegrid(self):
         kx_axis = self._padded_axis(self.nbase[1])
@@ -214,9 +235,10 @@ class PSIGridRefiner:
         kz_grid, kx_grid = np.meshgrid(kz_axis, kx_axis, indexing='ij')
         runs = np.arange(kx_grid.size, dtype=int).reshape(kx_grid.shape)
         results = None
+        guesses = self._terminal_velocity_guesses(kx_grid.ravel(), kz_grid.ravel()) if self.tv_guesses else None
         if self._array_path():
             got = self.ms.run_arrays(self._shared_init(1), kx_grid.ravel(), kz_grid.ravel(),
-                                     self.baseargs.get('random_seed', 0),
+                                     self.baseargs.get('random_seed', 0), guesses=guesses,
                                      alpha=self.baseargs['calculate'].get('viscous_alpha', 0))
             if got is not None:
                 results = RootStore(width=got[0].shape[1])
@@ -224,7 +246,9 @@ class PSIGridRefiner:
                 results.mat[:kx_grid.size, :got[0].shape[1]] = got[0]
                 results.cnt[:kx_grid.size] = got[1]
         if results is None:
-            arglist = [self._item(1, kx, kz) for kx, kz in zip(kx_grid.ravel(), kz_grid.ravel())]
+            per = [None]*kx_grid.size if guesses is None else \
+                [list(guesses[0][guesses[1][i]:guesses[1][i + 1]]) for i in range(kx_grid.size)]
+            arglist = [self._item(1, kx, kz, g) for kx, kz, g in zip(kx_grid.ravel(), kz_grid.ravel(), per)]
             results = self._run(arglist)
         self.grids.append({'Kx': kx_grid, 'Kz': kz_grid, 'runs': runs, 'results': results,
                            'nguess': np.zeros(kx_grid.shape, dtype=int)})

@@ -16,6 +16,7 @@
 
 #include "../../psitools_public_b200/csrc/psi_mode.cuh"
 #include "../../psitools_public_b200/csrc/psi_refine.cuh"
+#include "../../psitools_public_b200/csrc/psi_tv.cuh"
 #include "../../psitools_public_b200/csrc/psi_internal.hpp"
 #include "../../psitools_public_b200/csrc/psi_table.hpp"
 
@@ -345,6 +346,17 @@ void hs_refine_count(int nz, int nx, const int* runs, const int* nguess, int wid
     std::vector<cx> near(kRefineMaxNear);
     for (int p = 0; p < nz * nx; ++p)
         nk[p] = refine_pixel(g, p / nx, p % nx, near.data(), reinterpret_cast<cx*>(kept) + (size_t)p * kRefineMaxNear);
+}
+
+// csrc/psi_tv.cuh on the host: what one thread of tv_roots_kernel runs, pair by pair
+void hs_tv_roots(double fd, double tau_max, double b, double tau_min, double diffusion, int max_it, long long n,
+                 const double* kx, const double* kz, double* omega, int* status) {
+    TvParams P{fd, tau_max, b, tau_min / tau_max, diffusion, max_it};
+    for (long long i = 0; i < n; ++i) {
+        cx w;
+        status[i] = tv_find_root(P, kx[i], kz[i], &w);
+        omega[2 * i] = w.re; omega[2 * i + 1] = w.im;
+    }
 }
 
 void hs_aaa_stats(long long* out) { for (int i = 0; i < 16; ++i) { out[i] = g_aaa_stats[i]; g_aaa_stats[i] = 0; } }

@@ -128,3 +128,14 @@ def disp_eval(desc, integ, w, kx, kz, alpha, want_M=False):
     ctx = HostsimContext(integ)
     res = ctx.disp_eval(ctx.add_dist(desc), kx, kz, alpha, w, want_M=True)
     return (res[0], res[1], ctx.node_evals) if want_M else res[0]
+
+
+def tv_roots(fd, tau_max, b, tau_min, diffusion, max_it, kx, kz, device=None):
+    """Lane-emulation form of _device.tv_roots (csrc/psi_tv.cuh compiled by g++)."""
+    kx = np.ascontiguousarray(kx, dtype=np.float64)
+    kz = np.ascontiguousarray(kz, dtype=np.float64)
+    w = np.zeros(len(kx), dtype=np.complex128)
+    st = np.zeros(len(kx), dtype=np.int32)
+    lib().hs_tv_roots(C.c_double(fd), C.c_double(tau_max), C.c_double(b), C.c_double(tau_min), C.c_double(diffusion),
+                      C.c_int(max_it), C.c_longlong(len(kx)), _p(kx), _p(kz), _p(w), _p(st))
+    return w, st
