@@ -93,7 +93,7 @@ def test_tv_map_on_gpu(built):
     ax = np.logspace(-1, 3, 64)
     kx, kz = np.meshgrid(ax, ax)
     w, st = tv.find_roots_map(1e-8, kx, kz)
-    assert w.shape == st.shape == kx.shape and np.all(np.isfinite(w[st == 0])) and (st == 0).mean() > 0.5
+    assert w.shape == st.shape == kx.shape and np.all(np.isfinite(w[st == 0])) and (st == 0).mean() > 0.25
     with contextlib.redirect_stdout(io.StringIO()):
         one = complex(tv.find_roots(1e-8, kx[40, 20], kz[40, 20]))
     assert abs(w[40, 20] - one) <= 1e-8*abs(one)
