@@ -34,7 +34,8 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        _lib = C.CDLL(build())
+        # PSI_HOSTSIM_LIB: an alternative build of hostsim.cpp, e.g. with -fsanitize=address (tools/asan_hostsim.sh)
+        _lib = C.CDLL(os.environ.get("PSI_HOSTSIM_LIB") or build())
         _lib.hs_ctx_create.restype = C.c_void_p
         _lib.hs_last_error.restype = C.c_char_p
     return _lib
