@@ -658,7 +658,7 @@ def run_b200(args):
             pass
         roof = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": tf/fp64_peak if fp64_peak else None, "traffic": traffic,
-                "kernel": "disp_eval_thread_kernel (thread per point, levels 0-8) + disp_eval_kernel (warp per point, "
+                "kernel": "disp_eval_thread_kernel (thread per point, levels 0-7) + disp_eval_cta_kernel / disp_eval_kernel (block / warp per point, "
                           "the points left over); timed together; per GPU", "kernel_ms": ms_kernel_max,
                 "kernel_ms_per_rank": [round(x, 4) for x in rank_ms],
                 "node_evals_per_launch": node_evals_all/args.steps/world,

@@ -223,7 +223,8 @@ struct psi_ctx {
     size_t mode_scratch_bytes = 0;
     long long launches = 0;
     int predict_exit = 1;                  // quadrature exit rule of K1-K4 (psi_ctx_set_exit_rule)
-    int fast_cap = 8;                      // K1 fast path: last level a thread-per-point evaluation may use (0 = off)
+    int fast_cap = 7;                      // K1 fast path: last level a thread-per-point evaluation may use (0 = off);
+                                           // measured on config 2: cap 6 / 7 / 8 / 9 = 4.36 / 3.47 / 3.59 / 4.72 ms per step
     long long* d_hard = nullptr;           // indices of the points the fast path handed to the warp kernel
     size_t hard_cap = 0;
     std::vector<double*> d_tables;         // tabulated size densities (psi_dist_add_table)
@@ -1022,7 +1023,8 @@ static int launch_disp_eval(psi_ctx* c, long long n, int broadcast, const int* d
             c->launches++;
             CK(cudaGetLastError());
             // what the thread kernel left: a block per point when it is a handful, a warp per point otherwise
-            const unsigned long long few = 4ull * (unsigned long long)c->sm_count;
+            static const long long few_sms = getenv("PSI_K1_CTA_LIST") ? atoll(getenv("PSI_K1_CTA_LIST")) : 4;
+            const unsigned long long few = (unsigned long long)few_sms * (unsigned long long)c->sm_count;
             CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
             kEvalCtaKernels[cls]<<<c->sm_count, kEvalThreads, c->table_in_smem ? c->table_smem : 0, st>>>(
                 t, c->table_in_smem ? 1 : 0, c->d_dists, broadcast, dist, kx, kz, alpha, pidx, (const double2*)w,
