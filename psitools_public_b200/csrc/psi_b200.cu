@@ -11,6 +11,7 @@
 #include <string.h>
 #include <algorithm>
 #include <chrono>
+#include <cstring>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -233,6 +234,9 @@ struct psi_ctx {
     // the context's previous one has finished, whatever stream that ran on
     cudaEvent_t ev_k1 = nullptr;
     bool ev_k1_recorded = false;
+    // pinned bounce buffers for psi_disp_eval_host (pageable caller memory), grow-only
+    void *h_in = nullptr, *h_out = nullptr;
+    size_t h_in_bytes = 0, h_out_bytes = 0;
 };
 
 extern "C" { static int ensure_stage(psi_ctx* c, size_t bytes); }
@@ -901,6 +905,8 @@ void psi_ctx_destroy(psi_ctx* c) {
     for (double* t : c->d_tables) cudaFree(t);
     cudaStreamDestroy(c->stream);
     if (c->ev_k1) cudaEventDestroy(c->ev_k1);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
     delete c;
 }
 
@@ -1068,6 +1074,32 @@ static int ensure_stage(psi_ctx* c, size_t bytes) {
     return PSI_OK;
 }
 
+// memcpy on all host cores (a single core moves ~10 GB/s, the 16 cores of a GPU box 40+)
+static void copy_parallel(void* dst, const void* src, size_t bytes) {
+    const size_t chunk = (size_t)1 << 20;
+    const long long nchunk = (long long)((bytes + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static) if (nchunk >= 4)
+    for (long long k = 0; k < nchunk; ++k) {
+        const size_t lo = (size_t)k * chunk, len = std::min(chunk, bytes - lo);
+        memcpy((char*)dst + lo, (const char*)src + lo, len);
+    }
+}
+
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int ensure_pinned(void** buf, size_t* have, size_t need) {
+    if (need <= *have) return PSI_OK;
+    if (*buf) cudaFreeHost(*buf);
+    *buf = nullptr; *have = 0;
+    if (cudaHostAlloc(buf, need, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return PSI_ERR_CUDA; }
+    *have = need;
+    return PSI_OK;
+}
+
 int psi_disp_eval_host(psi_ctx* c, long long n, int broadcast, const int* dist, const double* kx,
                        const double* kz, const double* alpha, const double* w, double* D, double* M,
                        unsigned long long* node_evals) {
@@ -1092,7 +1124,20 @@ int psi_disp_eval_host(psi_ctx* c, long long n, int broadcast, const int* dist, 
     if (rc != PSI_OK) return rc;
     char* base = (char*)c->d_stage;
     cudaStream_t st = c->stream;
-    CK(cudaMemcpyAsync(base + o_w, w, 16 * n, cudaMemcpyHostToDevice, st));
+    // Pageable caller memory (numpy arrays): the driver's own staged copies run at 6-8 GB/s, i.e. 4 ms for the
+    // 2 x 16.8 MB of a 1,048,576-point call whose kernels take 3.5 ms.  Large transfers go through pinned bounce
+    // buffers of the context instead, filled and emptied by all host cores.  (Splitting the call into pieces so that
+    // copies overlap the kernels was measured and dropped: every K1 launch has ~0.25 ms of fixed cost -- its tail of
+    // hard points -- and 4 / 8 pieces took e2e from 258 M to 225 M / 177 M evals/s.)
+    static const size_t bounce_min = getenv("PSI_BOUNCE_MIN") ? (size_t)atoll(getenv("PSI_BOUNCE_MIN")) : ((size_t)1 << 20);
+    const bool bounce_in = 16 * (size_t)n >= bounce_min && !is_pinned_host(w) &&
+                           ensure_pinned(&c->h_in, &c->h_in_bytes, 16 * (size_t)n) == PSI_OK;
+    const bool bounce_out = 16 * (size_t)n >= bounce_min && !is_pinned_host(D) &&
+                            ensure_pinned(&c->h_out, &c->h_out_bytes, 16 * (size_t)n) == PSI_OK;
+    if (bounce_in || bounce_out) CK(cudaStreamSynchronize(st));         // an earlier call may still own the buffers
+    if (bounce_in) copy_parallel(c->h_in, w, 16 * (size_t)n);
+    const double* w_src = bounce_in ? (const double*)c->h_in : w;
+    CK(cudaMemcpyAsync(base + o_w, w_src, 16 * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(base + o_kx, kx, 8 * np, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(base + o_kz, kz, 8 * np, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(base + o_al, alpha, 8 * np, cudaMemcpyHostToDevice, st));
@@ -1103,11 +1148,12 @@ int psi_disp_eval_host(psi_ctx* c, long long n, int broadcast, const int* dist, 
                           (const double*)(base + o_w), (double*)(base + o_D),
                           M ? (double*)(base + o_M) : nullptr, c->d_counter + 1, class_mask, st);
     if (rc != PSI_OK) return rc;
-    CK(cudaMemcpyAsync(D, base + o_D, 16 * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(bounce_out ? (double*)c->h_out : D, base + o_D, 16 * n, cudaMemcpyDeviceToHost, st));
     if (M) CK(cudaMemcpyAsync(M, base + o_M, 112 * n, cudaMemcpyDeviceToHost, st));
     unsigned long long ne = 0;
     CK(cudaMemcpyAsync(&ne, c->d_counter + 1, sizeof(ne), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (bounce_out) copy_parallel(D, c->h_out, 16 * (size_t)n);
     if (node_evals) *node_evals = ne;
     return PSI_OK;
 }
