@@ -671,14 +671,17 @@ __global__ void mode_sample_kernel(ModeDev m, int n_items, const double* __restr
 constexpr int kAnClass0 = 32, kAnClass1 = 32;
 // (Appended warp by warp, the 32 searches of a warp in index order: neighbouring searches -- neighbouring pixels of a
 // map, which behave alike -- stay neighbours on the list and end up in the same analysis warp.)
+// With the 16-lane class off (class1 <= class0, the default) its list holds the LARGEST 32-lane searches (more than
+// `huge` samples) instead; the 32-lane kernel takes them first, so that the longest analyses of a level start at
+// once and the short ones fill in behind them instead of the other way round.
 __global__ void mode_classify_kernel(ModeDev m, int n_items, int* lists, unsigned long long* counts, int class0,
-                                     int class1) {
+                                     int class1, int huge) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int cls = -1;
     if (i < n_items && m.phase[i] == kPhaseAnalyze) {
         const int M = m.M[i];
-        cls = M <= class0 ? 0 : (M <= class1 ? 1 : 2);
+        cls = M <= class0 ? 0 : (class1 > class0 ? (M <= class1 ? 1 : 2) : (M > huge ? 1 : 2));
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -703,15 +706,17 @@ mode_analyze_kernel(ModeDev m, int n_items, const double* __restrict__ domain, c
                     const double* __restrict__ dparams, const int* __restrict__ guess_off,
                     unsigned char* scratch, size_t scratch_per_group, int scratch_cap,
                     const int* __restrict__ list, const unsigned long long* __restrict__ n_list,
-                    unsigned long long* queue, unsigned long long* n_polish) {
+                    unsigned long long* queue, unsigned long long* n_polish, const int* __restrict__ list_first,
+                    const unsigned long long* __restrict__ n_first) {
     typedef GroupCuda<G> W;
     const int lane = W::lane();
     const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
     AAAScratch sc = aaa_carve(scratch + (size_t)group * scratch_per_group, scratch_cap);
-    const long long n_work = (long long)*n_list;          // searches of this launch's size class (mode_classify_kernel)
+    const long long n_head = list_first != nullptr ? (long long)*n_first : 0;     // the largest searches, taken first
+    const long long n_work = n_head + (long long)*n_list; // searches of this launch's size class (mode_classify_kernel)
     long long k;
     while (next_item_group<W>(queue, n_work, k)) {
-        const long long idx = list[k];
+        const long long idx = k < n_head ? list_first[k] : list[k - n_head];
         ModeCfg cfg;
         cfg.dom = RectDom{domain[4 * idx], domain[4 * idx + 1], domain[4 * idx + 2], domain[4 * idx + 3]};
         cfg.n_sample = iparams[3 * idx]; cfg.max_zoom = iparams[3 * idx + 1]; cfg.max_secant = iparams[3 * idx + 2];
@@ -1313,6 +1318,7 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
     static const int an_ctas = getenv("PSI_AN_CTAS") ? atoi(getenv("PSI_AN_CTAS")) : 3;
     static const int an_class0 = getenv("PSI_AN_CLASS0") ? atoi(getenv("PSI_AN_CLASS0")) : kAnClass0;
     static const int an_class1 = getenv("PSI_AN_CLASS1") ? atoi(getenv("PSI_AN_CLASS1")) : kAnClass1;
+    static const int an_huge = getenv("PSI_AN_HUGE") ? atoi(getenv("PSI_AN_HUGE")) : 64;   // A/B: profiles/k4_groups_r2.txt
     const int an_threads = 256;
     const int an_g[3] = {8, 16, 32};
     const int an_cap[3] = {std::min(cap, an_class0), std::min(cap, an_class1), cap};
@@ -1410,9 +1416,11 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
             int* an_lists = (int*)d[22];
             unsigned long long* an_counts = (unsigned long long*)d[23];        // [0..2] class sizes, [4..6] queue heads
             CK(cudaMemsetAsync(an_counts, 0, 8 * sizeof(unsigned long long), st));
-            mode_classify_kernel<<<tgrid, 256, 0, st>>>(m, n_items, an_lists, an_counts, an_class0, an_class1);
+            mode_classify_kernel<<<tgrid, 256, 0, st>>>(m, n_items, an_lists, an_counts, an_class0, an_class1, an_huge);
+            const bool head_list = an_class1 <= an_class0;                  // list 1 = largest 32-lane searches
             for (int k = 0; k < 3; ++k) {
                 if (k > 0 && cap <= (k == 1 ? an_class0 : an_class1)) continue;       // no search can be that large
+                if (k == 1 && head_list) continue;
                 const int per_cta = an_threads / an_g[k];
                 const int agrid = std::min(c->sm_count * an_ctas, (n_items + per_cta - 1) / per_cta);
                 auto kern = k == 0 ? mode_analyze_kernel<8> : k == 1 ? mode_analyze_kernel<16> : mode_analyze_kernel<32>;
@@ -1420,7 +1428,9 @@ int psi_internal_mode_device(psi_ctx* c, int n_items, const int* dist, const dou
                                                    (const double*)d[6], (const int*)d[9],
                                                    (unsigned char*)c->d_mode_scratch + an_off[k], an_per_group[k],
                                                    an_cap[k], an_lists + (size_t)k * n_items, an_counts + k,
-                                                   an_counts + 4 + k, c->d_counter + 8);
+                                                   an_counts + 4 + k, c->d_counter + 8,
+                                                   k == 2 && head_list ? an_lists + (size_t)n_items : nullptr,
+                                                   an_counts + 1);
                 ++launches;
             }
         }
