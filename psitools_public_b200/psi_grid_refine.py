@@ -75,6 +75,9 @@ class RootStore(MutableMapping):
     def _reserve(self, n_keys, width):
         if n_keys > len(self.cnt) or width > self.mat.shape[1]:
             rows = max(n_keys, 2*len(self.cnt)) if n_keys > len(self.cnt) else len(self.cnt)
+            # slots grow in steps of four: a wider row means a copy of the whole matrix (0.9 GB on a 1089^2 map) and a
+            # re-opened device mirror, and the widest run of a campaign keeps creeping up by one
+            width = -(-width//4)*4 if width > self.mat.shape[1] else self.mat.shape[1]
             mat = np.zeros((rows, max(width, self.mat.shape[1])), dtype=np.complex128)
             mat[:len(self.cnt), :self.mat.shape[1]] = self.mat
             cnt = np.full(rows, -1, dtype=np.int64)
