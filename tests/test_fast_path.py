@@ -243,3 +243,23 @@ def test_polish_and_contour_loose_predictor_vs_literal(built):
         assert np.max(np.abs(ra - rb)/np.abs(rb)) < 1e-8, np.max(np.abs(ra - rb)/np.abs(rb))
         assert np.array_equal(out["predictedc"][0], out["referencec"][0])
         assert np.array_equal(out["predictedc"][1], out["referencec"][1])
+
+
+def test_host_call_read_back_paths(built):
+    """psi_disp_eval_host on a large batch sends the results back while the leftover stage still runs and patches
+    that stage's points in afterwards (at most 8,192 of them; beyond that it falls back to a plain copy).  Both
+    branches, and the pageable-buffer path through pinned bounce buffers, against the same points evaluated in
+    pieces small enough to take the plain path: bit-identical."""
+    from psitools_public_b200 import PSIDispersion, TanhSinh
+    pd = PSIDispersion(3.0, [1e-8, 0.1], tanhsinh_integrator=TanhSinh())
+    rng = np.random.RandomState(5)
+    n = 1 << 18                                               # the early read-back starts at 262,144 points
+    few = rng.uniform(-2, 2, n) + 1j*rng.uniform(0.05, 1, n)
+    few[:3000] = rng.uniform(-0.2, 0.2, 3000) + 1e-7j         # ~3,000 points for the leftover stage: patches
+    many = rng.uniform(-2, 2, n) + 1j*rng.uniform(0.05, 1, n)
+    many[:20000] = rng.uniform(-0.2, 0.2, 20000) + 1e-7j      # 20,000 of them: more than the patch buffer holds
+    for w in (few, many):
+        whole = pd.calculate(w, 50.0, 100.0)
+        parts = np.concatenate([pd.calculate(w[k:k + (1 << 16)], 50.0, 100.0) for k in range(0, n, 1 << 16)])
+        assert np.all(np.isfinite(whole))
+        assert np.array_equal(whole, parts)
